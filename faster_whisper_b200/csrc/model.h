@@ -1,0 +1,124 @@
+// Model / workspace structures of libb200whisper (host side).
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decode.h"
+#include "engine.h"
+
+namespace b2w {
+
+struct EncLayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  __half *wqkv, *wo, *w1, *w2;
+  float *bqkv, *bo, *b1, *b2;
+};
+struct DecLayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  __half *wqkv, *wo, *wq_x, *wo_x, *w1, *w2;
+  float *bqkv, *bo, *bq_x, *bo_x, *b1, *b2;
+};
+
+struct EncPlan {  // everything bound to the encoder workspace for one sub-batch size
+  int b = 0;
+  GemmPlan conv1, conv2;
+  std::vector<GemmPlan> qkv, proj, ffn1, ffn2;
+  AttnPlan attn;
+};
+
+struct StageTimer {
+  int stage;
+  cudaEvent_t start, stop;
+};
+
+struct Model;
+
+struct Encoded {
+  Model* owner = nullptr;
+  int B = 0;
+  __half* enc_out = nullptr;  // [B][1500][d] fp16
+  __half* xkv = nullptr;      // lazily: [L][2][B][H][T][64] fp16
+  ~Encoded();
+};
+
+struct Model {
+  b2w_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  int cpad = 128;   // mel channels padded to a multiple of 64
+  int vpad = 0;     // vocabulary padded to a multiple of 16
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::vector<void*> allocs;  // weights
+
+  // encoder weights
+  __half *conv1_w = nullptr, *conv2_w = nullptr;
+  float *conv1_b = nullptr, *conv2_b = nullptr, *enc_pos = nullptr, *enc_lnp_g = nullptr, *enc_lnp_b = nullptr;
+  std::vector<EncLayerW> enc;
+  // decoder weights
+  __half* tok_emb = nullptr;  // [vpad][d]
+  float *dec_pos = nullptr, *dec_ln_g = nullptr, *dec_ln_b = nullptr;
+  std::vector<DecLayerW> dec;
+  __half* wxkv = nullptr;  // [L*2d][d]
+  float* bxkv = nullptr;   // [L*2d]
+  double dec_weight_bytes = 0;  // bytes one decode step must stream (all decoder weights incl. the tied embedding)
+
+  std::unique_ptr<MelPlan> mel;
+
+  // encoder workspace (sized for enc_max_b chunks)
+  int enc_max_b = 0;
+  float* e_feats = nullptr;   // [b][n_mels][3000] f32
+  __half* e_x0 = nullptr;     // [b][3000][cpad]
+  __half* e_x1 = nullptr;     // [b][3000][d]
+  float* e_x = nullptr;       // [b*1500][d] residual stream
+  __half* e_xn = nullptr;     // [b*1500][d]
+  __half* e_qkv = nullptr;    // [b*1500][3d]
+  __half* e_ao = nullptr;     // [b*1500][d]
+  __half* e_h = nullptr;      // [b*1500][4d]
+  float* e_pcm = nullptr;     // audio staging
+  size_t e_pcm_cap = 0;
+  MelChunkDesc* e_chunks = nullptr;
+  int* e_chunk_max = nullptr;
+  std::map<int, EncPlan> enc_plans;
+
+  // decoder workspace
+  int dw_rows = 0;
+  size_t kv_elems = 0;        // per layer per K|V
+  __half* kcache = nullptr;   // [L][kv_elems]
+  __half* vcache = nullptr;
+  float* d_x = nullptr;       // [80][d]
+  __half *d_xn = nullptr, *d_q = nullptr, *d_ao = nullptr, *d_h = nullptr;
+  float* d_logits = nullptr;  // [80][vpad]
+  float* d_xpart = nullptr;
+  size_t d_xpart_floats = 0;
+  int* d_counters = nullptr;  // [0]: GEMM ticket, [64..]: cross-attention groups
+  uint8_t* d_suppress = nullptr;
+  // search buffers
+  SearchBuffers sb{};
+  void* sb_blob = nullptr;
+  int sb_B = 0, sb_K = 0;
+  int* h_pinned = nullptr;    // pinned host scratch
+
+  // step graph cache
+  cudaGraphExec_t step_graph = nullptr;
+  int64_t step_graph_kernels = 0;
+  std::vector<uint8_t> step_graph_key;
+
+  // measurement
+  bool timing = false;
+  std::vector<StageTimer> timers;
+  double t_ms[B2W_T_COUNT] = {0};
+  int64_t t_cnt[B2W_T_COUNT] = {0};
+  int64_t launches = 0, decode_steps = 0;
+  double decode_alg_bytes = 0;
+
+  bool use_ref_gemm = false, use_ref_attn = false, use_ref_gemv = false, use_graph = true;
+
+  ~Model();
+};
+
+}  // namespace b2w

@@ -1,0 +1,483 @@
+// On-device decoding logic: logits processors, log-softmax, per-row top-k, beam bookkeeping.
+//
+// Restates CTranslate2 4.x's Whisper decoding as consumed by faster-whisper (reference call sites
+// faster_whisper/transcribe.py:222-236 and 1446-1459): suppress_tokens,
+// suppress_blank, Whisper timestamp rules, repetition penalty, no-repeat-ngram, beam search with 2K
+// candidates / patience / EOS-exclusive length normalisation, greedy and random sampling (Gumbel-max).
+// CTranslate2 runs these as a mix of small kernels and host loops with a device->host sync per token; here
+// a decode step is two kernels and the host only polls a "chunks done" counter every few steps.
+//
+//  search_rows   : one CTA per row; the 51 866-float logits row lives in shared memory while the masks,
+//                  the timestamp-probability rule, the log-softmax and the row top-2K run over it.
+//  search_update : one CTA per chunk; merges the rows' candidates, applies CTranslate2's finished /
+//                  secondary-candidate rule, and re-links token history and KV-slot ancestry (the paged
+//                  self-KV cache is never copied when beams reorder).
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "decode.h"
+
+namespace b2w {
+
+constexpr int kRowThreads = 1024;
+#define B2W_LOWEST (-FLT_MAX)
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = better(a, b);
+  }
+  return a;
+}
+
+__device__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+  return r;
+}
+
+// counter-based uniform -> Gumbel noise; mirrored bit-for-bit (integer part) by oracle/whisper_oracle.py:gumbel_noise
+__device__ __forceinline__ float gumbel_u32(unsigned long long seed, int row, int step, int idx) {
+  unsigned long long x = (unsigned long long)idx * 0x9E3779B97F4A7C15ull + seed * 0xBF58476D1CE4E5B9ull +
+                         (unsigned long long)row * 0x94D049BB133111EBull + (unsigned long long)step * 0xD6E8FEB86659FD93ull;
+  x ^= x >> 30;
+  x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27;
+  x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  const float u = ((float)(unsigned)(x >> 41) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits: exact, strictly in (0,1)
+  return -logf(-logf(u));
+}
+
+__global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* __restrict__ logits, const SearchParams p,
+                                                                   const SearchBuffers bf) {
+  extern __shared__ float s[];  // [vpad]
+  __shared__ float red[32];
+  __shared__ ArgMax wbest[32];
+  __shared__ int sh_flags[4];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const int b = r / p.K, k = r % p.K;
+  const int V = p.n_vocab;
+  const RowInfo ri = bf.rows[r];
+  const int step = ri.pos - (p.prompt_len - 1);
+  const int cur = step & 1;
+  const int* hist = bf.hist + ((long long)cur * p.B * p.K + r) * bf.n_ctx;
+  const int len = step;  // tokens generated so far by this row
+  const float* row = logits + (long long)r * p.vpad;
+
+  // ---- no_speech probability from the raw first-step logits (sot is the last prompt token) ----
+  if (p.want_no_speech_first && step == 0 && k == 0) {
+    float mx = -INFINITY;
+    for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, row[v]);
+    mx = block_max(mx, red);
+    float sm = 0.f;
+    for (int v = tid; v < V; v += kRowThreads) sm += __expf(row[v] - mx);
+    sm = block_sum(sm, red);
+    if (tid == 0) bf.no_speech[b] = __expf(row[p.no_speech] - mx) / sm;
+  }
+
+  // ---- load + static suppression ----
+  for (int v = tid; v < V; v += kRowThreads) s[v] = bf.suppress[v] ? B2W_LOWEST : row[v];
+  __syncthreads();
+  // repetition penalty on the raw value of every distinct generated token
+  if (p.repetition_penalty != 1.0f) {
+    for (int i = tid; i < len; i += kRowThreads) {
+      const int tok = hist[i];
+      bool first = true;
+      for (int j = 0; j < i; ++j)
+        if (hist[j] == tok) {
+          first = false;
+          break;
+        }
+      if (first && !bf.suppress[tok]) {
+        const float x = row[tok];
+        s[tok] = x < 0.f ? x * p.repetition_penalty : x / p.repetition_penalty;
+      }
+    }
+    __syncthreads();
+  }
+  const int ng = p.no_repeat_ngram;
+  if (ng > 0 && len >= ng) {
+    for (int s0 = tid; s0 + ng <= len; s0 += kRowThreads) {
+      bool same = true;
+      for (int j = 0; j < ng - 1; ++j)
+        if (hist[s0 + j] != hist[len - ng + 1 + j]) {
+          same = false;
+          break;
+        }
+      if (same) s[hist[s0 + ng - 1]] = B2W_LOWEST;
+    }
+    __syncthreads();
+  }
+  if (p.suppress_blank && step == 0 && tid < p.n_suppress_begin) s[p.suppress_begin[tid]] = B2W_LOWEST;
+  __syncthreads();
+
+  // ---- Whisper timestamp rules ----
+  if (p.timestamp_rules) {
+    const int ts0 = p.timestamp_begin;
+    if (tid == 0) {
+      s[p.no_timestamps] = B2W_LOWEST;
+      int last_ts = 0, penult_ts = 0, t_last = -1;
+      if (step > 0) {
+        last_ts = hist[len - 1] >= ts0;
+        penult_ts = (len < 2) || (hist[len - 2] >= ts0);
+        for (int i = len - 1; i >= 0; --i)
+          if (hist[i] >= ts0) {
+            t_last = hist[i];
+            break;
+          }
+        if (t_last >= 0 && !(last_ts && !penult_ts)) t_last += 1;
+      }
+      sh_flags[0] = last_ts;
+      sh_flags[1] = penult_ts;
+      sh_flags[2] = t_last;
+    }
+    __syncthreads();
+    const int last_ts = sh_flags[0], penult_ts = sh_flags[1], t_last = sh_flags[2];
+    if (step == 0) {
+      const int hi = ts0 + p.max_initial_ts;
+      for (int v = tid; v < V; v += kRowThreads)
+        if (v < ts0 || (p.max_initial_ts >= 0 && v > hi)) s[v] = B2W_LOWEST;
+    } else {
+      int lo_a = 0, hi_a = 0;  // masked range A
+      if (last_ts) {
+        if (penult_ts) {
+          lo_a = ts0;
+          hi_a = V;
+        } else {
+          lo_a = 0;
+          hi_a = p.eot;
+        }
+      }
+      for (int v = tid; v < V; v += kRowThreads)
+        if ((v >= lo_a && v < hi_a) || (t_last >= 0 && v >= ts0 && v < t_last)) s[v] = B2W_LOWEST;
+      __syncthreads();
+      // if the timestamps' total probability beats every text token, force a timestamp
+      float mx = -INFINITY;
+      for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, s[v]);
+      mx = block_max(mx, red);
+      float sum_all = 0.f, sum_ts = 0.f, max_text = -INFINITY;
+      for (int v = tid; v < V; v += kRowThreads) {
+        const float e = __expf(s[v] - mx);
+        sum_all += e;
+        if (v >= ts0)
+          sum_ts += e;
+        else
+          max_text = fmaxf(max_text, s[v]);
+      }
+      sum_all = block_sum(sum_all, red);
+      sum_ts = block_sum(sum_ts, red);
+      max_text = block_max(max_text, red);
+      const float lse = mx + logf(sum_all);
+      const float ts_lp = (sum_ts > 0.f) ? (mx + logf(sum_ts) - lse) : -INFINITY;
+      const float text_lp = max_text - lse;
+      if (ts_lp > text_lp)
+        for (int v = tid; v < ts0; v += kRowThreads) s[v] = B2W_LOWEST;
+    }
+    __syncthreads();
+  }
+
+  // ---- log-softmax ----
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, s[v]);
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int v = tid; v < V; v += kRowThreads) sm += __expf(s[v] - mx);
+  sm = block_sum(sm, red);
+  const float lse = mx + logf(sm);
+  const float cum = bf.cum[(long long)cur * p.B * p.K + r];
+
+  // ---- candidate selection ----
+  const bool sampling = (p.mode == 1 && p.sampling_topk != 1);
+  const float inv_t = 1.0f / p.temperature;
+  // transform in place to the ranking key; masked entries become -inf so they are never selected before real ones
+  for (int v = tid; v < V; v += kRowThreads) {
+    float x = s[v];
+    if (x <= B2W_LOWEST * 0.5f) {
+      x = sampling ? -INFINITY : (x - lse);  // CT2 keeps "lowest" (finite) scores for masked ids in beam search
+    } else {
+      x = x - lse;
+      if (sampling) x = x * inv_t + gumbel_u32(p.seed, r, step, v);
+    }
+    s[v] = x;
+  }
+  __syncthreads();
+  ArgMax mine{-INFINITY, 0x7fffffff};
+  for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
+  const int ncand = p.ncand;
+  for (int c = 0; c < ncand; ++c) {
+    ArgMax w = warp_argmax(mine);
+    if ((tid & 31) == 0) wbest[tid >> 5] = w;
+    __syncthreads();
+    ArgMax best = wbest[0];
+    for (int i = 1; i < kRowThreads / 32; ++i) best = better(best, wbest[i]);
+    if (tid == 0) {
+      float sc;
+      if (sampling) {
+        // score of a draw: tempered log-prob (what CTranslate2's RandomSampler gathers)
+        sc = (best.v == -INFINITY) ? B2W_LOWEST : (best.v - gumbel_u32(p.seed, r, step, best.i));
+      } else {
+        sc = best.v;
+      }
+      bf.cand_score[(long long)r * kMaxCand + c] = (p.mode == 0) ? cum + sc : sc;
+      bf.cand_tok[(long long)r * kMaxCand + c] = best.i;
+    }
+    if (best.i != 0x7fffffff && (best.i % kRowThreads) == tid) {
+      s[best.i] = -INFINITY;
+      mine = ArgMax{-INFINITY, 0x7fffffff};
+      for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
+      // entries already taken are -inf with a real index; never prefer them over the sentinel
+      if (mine.v == -INFINITY) mine.i = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+
+void search_configure() {
+  B2W_CUDA(cudaFuncSetAttribute(search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+}
+
+void search_rows(const float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
+  const int smem = p.vpad * (int)sizeof(float);
+  B2W_CHECK(smem <= 210 * 1024, "vocabulary too large for the in-shared-memory row search");
+  search_rows_kernel<<<p.B * p.K, kRowThreads, smem, s>>>(logits, p, b);
+  B2W_LAUNCHED();
+}
+
+// ---- beam / greedy bookkeeping ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) search_update_kernel(const SearchParams p, const SearchBuffers bf) {
+  __shared__ float c_score[kMaxCand];
+  __shared__ int c_tok[kMaxCand], c_beam[kMaxCand];
+  __shared__ int parent[kMaxBeam], newtok[kMaxBeam];
+  __shared__ float newcum[kMaxBeam];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int K = p.K, V = p.n_vocab, n_ctx = bf.n_ctx;
+  const int r0 = b * K;
+  const int pos = bf.rows[r0].pos;
+  const int step = pos - (p.prompt_len - 1);
+  const int cur = step & 1, nxt = cur ^ 1;
+  const bool is_last = (step + 1 >= p.max_steps);
+  const long long RB = (long long)p.B * K;
+
+  if (tid == 0) {
+    const bool chunk_done = bf.done[b] != 0;
+    if (p.mode == 0) {
+      // ---- merge rows' sorted candidate lists (step 0: only the first row is live) ----
+      const int nrows = (step == 0) ? 1 : K;
+      int head[kMaxBeam];
+      for (int i = 0; i < nrows; ++i) head[i] = 0;
+      for (int c = 0; c < p.ncand; ++c) {
+        int bi = -1;
+        float bs = 0.f;
+        long long bflat = 0;
+        for (int i = 0; i < nrows; ++i) {
+          if (head[i] >= p.ncand) continue;
+          const float sc = bf.cand_score[(long long)(r0 + i) * kMaxCand + head[i]];
+          const long long flat = (long long)i * V + bf.cand_tok[(long long)(r0 + i) * kMaxCand + head[i]];
+          if (bi < 0 || sc > bs || (sc == bs && flat < bflat)) {
+            bi = i;
+            bs = sc;
+            bflat = flat;
+          }
+        }
+        c_score[c] = bs;
+        c_beam[c] = bi;
+        c_tok[c] = bf.cand_tok[(long long)(r0 + bi) * kMaxCand + head[bi]];
+        head[bi]++;
+      }
+      // ---- CTranslate2 beam step: finished hypotheses are replaced by secondary candidates ----
+      int secondary = K;
+      bool top_finished = false;
+      int nfin = bf.fin_count[b];
+      const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
+      for (int k = 0; k < K; ++k) {
+        int nx = k;
+        const int t = c_tok[k];
+        if ((t == p.eot || is_last) && !chunk_done) {
+          if (k == 0) top_finished = true;
+          if (nfin < kMaxFinished) {
+            const int* src = hist_cur + (long long)(r0 + c_beam[k]) * n_ctx;
+            int* dst = bf.fin_tok + ((long long)b * kMaxFinished + nfin) * n_ctx;
+            for (int i = 0; i < step; ++i) dst[i] = src[i];
+            int len = step;
+            if (t != p.eot) dst[len++] = t;
+            bf.fin_len[b * kMaxFinished + nfin] = len;
+            bf.fin_score[b * kMaxFinished + nfin] = c_score[k];
+            ++nfin;
+          }
+          for (int j = secondary; j < p.ncand; ++j)
+            if (c_tok[j] != p.eot) {
+              nx = j;
+              secondary = j + 1;
+              break;
+            }
+        }
+        parent[k] = c_beam[nx];
+        newtok[k] = c_tok[nx];
+        newcum[k] = c_score[nx];
+      }
+      if (!chunk_done) {
+        bf.fin_count[b] = nfin;
+        bool fin;
+        if (is_last)
+          fin = true;
+        else if (p.allow_early_exit)
+          fin = top_finished && nfin >= p.num_hyp;
+        else
+          fin = nfin >= p.max_finished;
+        if (fin) {
+          bf.done[b] = 1;
+          atomicAdd(&bf.state->n_done, 1);
+        }
+      }
+    } else {
+      // ---- greedy / sampling: rows are independent hypotheses; fin slot k belongs to row k ----
+      int ndone_rows = 0;
+      const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
+      for (int k = 0; k < K; ++k) {
+        const int r = r0 + k;
+        const int t = bf.cand_tok[(long long)r * kMaxCand];
+        const float sc = bf.cand_score[(long long)r * kMaxCand];
+        parent[k] = k;
+        newtok[k] = t;
+        const bool row_done = bf.fin_len[b * kMaxFinished + k] >= 0;
+        float cumv = bf.cum[(long long)cur * RB + r];
+        if (!row_done) {
+          cumv += sc;
+          if (t == p.eot || is_last) {
+            const int* src = hist_cur + (long long)r * n_ctx;
+            int* dst = bf.fin_tok + ((long long)b * kMaxFinished + k) * n_ctx;
+            for (int i = 0; i < step; ++i) dst[i] = src[i];
+            int len = step;
+            if (t != p.eot) dst[len++] = t;
+            bf.fin_len[b * kMaxFinished + k] = len;
+            bf.fin_score[b * kMaxFinished + k] = cumv;
+            ++ndone_rows;
+          }
+        } else {
+          ++ndone_rows;
+        }
+        newcum[k] = cumv;
+      }
+      if (!chunk_done && ndone_rows == K) {
+        bf.fin_count[b] = K;
+        bf.done[b] = 1;
+        atomicAdd(&bf.state->n_done, 1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- re-link history and KV ancestry into the other buffer, append the new token ----
+  const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
+  int* hist_nxt = bf.hist + (long long)nxt * RB * n_ctx;
+  const uint8_t* anc_cur = bf.anc + (long long)cur * RB * n_ctx;
+  uint8_t* anc_nxt = bf.anc + (long long)nxt * RB * n_ctx;
+  for (int k = 0; k < K; ++k) {
+    const int pk = parent[k];
+    const int* hs = hist_cur + (long long)(r0 + pk) * n_ctx;
+    int* hd = hist_nxt + (long long)(r0 + k) * n_ctx;
+    for (int i = tid; i < step; i += blockDim.x) hd[i] = hs[i];
+    const uint8_t* as = anc_cur + (long long)(r0 + pk) * n_ctx;
+    uint8_t* ad = anc_nxt + (long long)(r0 + k) * n_ctx;
+    for (int i = tid; i < pos; i += blockDim.x) ad[i] = as[i];
+    if (tid == 0) {
+      hd[step] = newtok[k];
+      ad[pos] = (uint8_t)pk;
+      bf.cum[(long long)nxt * RB + r0 + k] = newcum[k];
+      bf.tokens_in[r0 + k] = newtok[k];
+      bf.rows[r0 + k].pos = pos + 1;
+    }
+  }
+}
+
+void search_update(const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
+  search_update_kernel<<<p.B, 128, 0, s>>>(p, b);
+  B2W_LAUNCHED();
+}
+
+// ---- deterministic stand-in for the decoder (tests of the search logic only) -------------------------------------------
+// logits[r][v] = u24(hash(token_in, step, v)) * 2^-20 - 8  (+3 for timestamps, +0.25*step for EOT); mirrored in
+// tests/test_search.py so the device search can be compared bit-for-bit with the oracle's search.
+__global__ void fake_logits_kernel(float* __restrict__ logits, const SearchParams p, const SearchBuffers bf) {
+  const int r = blockIdx.y;
+  const int step = bf.rows[r].pos - (p.prompt_len - 1);
+  const unsigned tok = (unsigned)bf.tokens_in[r];
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < p.n_vocab; v += gridDim.x * blockDim.x) {
+    unsigned h = tok * 0x9E3779B1u ^ ((unsigned)step * 0x85EBCA77u) ^ ((unsigned)v * 0xC2B2AE3Du);
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    h *= 0x846CA68Bu;
+    h ^= h >> 16;
+    float x = __fadd_rn(__fmul_rn((float)(h >> 8), 9.5367431640625e-07f), -8.0f);
+    if (v >= p.timestamp_begin) x = __fadd_rn(x, 3.0f);
+    if (v == p.eot) x = __fadd_rn(x, __fmul_rn(0.25f, (float)step));
+    logits[(long long)r * p.vpad + v] = x;
+  }
+}
+void fake_logits(float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
+  fake_logits_kernel<<<dim3(32, p.B * p.K), 256, 0, s>>>(logits, p, b);
+  B2W_LAUNCHED();
+}
+
+// softmax probability of one token for selected rows (no_speech_prob at the SOT position)
+__global__ void token_prob_kernel(const float* __restrict__ logits, int row_stride, int rows_per_chunk, int row_in_chunk,
+                                  int n_vocab, int tok, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* row = logits + (long long)(b * rows_per_chunk + row_in_chunk) * row_stride;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < n_vocab; v += blockDim.x) mx = fmaxf(mx, row[v]);
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int v = threadIdx.x; v < n_vocab; v += blockDim.x) sm += __expf(row[v] - mx);
+  sm = block_sum(sm, red);
+  if (threadIdx.x == 0) out[b] = __expf(row[tok] - mx) / sm;
+}
+void no_speech_from_logits(const float* logits, int row_stride, int R, int rows_per_chunk, int row_in_chunk, int n_vocab,
+                           int no_speech_id, float* out, cudaStream_t s) {
+  token_prob_kernel<<<R / rows_per_chunk, 1024, 0, s>>>(logits, row_stride, rows_per_chunk, row_in_chunk, n_vocab, no_speech_id, out);
+  B2W_LAUNCHED();
+}
+
+__global__ void lang_probs_kernel(const float* __restrict__ logits, int row_stride, int lang_begin, int n_lang,
+                                  float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* row = logits + (long long)b * row_stride + lang_begin;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < n_lang; v += blockDim.x) mx = fmaxf(mx, row[v]);
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int v = threadIdx.x; v < n_lang; v += blockDim.x) sm += __expf(row[v] - mx);
+  sm = block_sum(sm, red);
+  for (int v = threadIdx.x; v < n_lang; v += blockDim.x) out[(long long)b * n_lang + v] = __expf(row[v] - mx) / sm;
+}
+void lang_probs_from_logits(const float* logits, int row_stride, int B, int lang_begin, int n_lang, float* out, cudaStream_t s) {
+  lang_probs_kernel<<<B, 128, 0, s>>>(logits, row_stride, lang_begin, n_lang, out);
+  B2W_LAUNCHED();
+}
+
+}  // namespace b2w

@@ -430,21 +430,24 @@ class WhisperOracle:
     @staticmethod
     def gumbel_noise(seed: int, row: int, step: int, n: int) -> np.ndarray:
         """Counter-based noise shared with the CUDA sampler (csrc/decode_search.cu: gumbel_u32)."""
-        idx = np.arange(n, dtype=np.uint64)
-        x = (idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed) * np.uint64(0xBF58476D1CE4E5B9)
-             + np.uint64(row) * np.uint64(0x94D049BB133111EB) + np.uint64(step) * np.uint64(0xD6E8FEB86659FD93)) & np.uint64(0xFFFFFFFFFFFFFFFF)
-        x ^= x >> np.uint64(30)
-        x = (x * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
-        x ^= x >> np.uint64(27)
-        x = (x * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
-        x ^= x >> np.uint64(31)
-        u = ((x >> np.uint64(40)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
-        return (-np.log(-np.log(u.astype(np.float32)))).astype(np.float32)
+        M = (1 << 64) - 1
+        base = (seed * 0xBF58476D1CE4E5B9 + row * 0x94D049BB133111EB + step * 0xD6E8FEB86659FD93) & M
+        with np.errstate(over="ignore"):
+            x = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(base)  # wraps mod 2^64
+            x ^= x >> np.uint64(30)
+            x = x * np.uint64(0xBF58476D1CE4E5B9)
+            x ^= x >> np.uint64(27)
+            x = x * np.uint64(0x94D049BB133111EB)
+            x ^= x >> np.uint64(31)
+        # 23 random bits + 0.5 is exact in float32 and keeps u strictly inside (0, 1)
+        u = ((x >> np.uint64(41)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+        return (-np.log(-np.log(u))).astype(np.float32)
 
     def _sample(self, logp_row: np.ndarray, topk: int, temperature: float, seed: int, row: int, step: int):
         """Random sampling as Gumbel-max over logp/T (distributionally equal to CT2's multinomial;
         the returned score is the tempered log-prob of the draw, as CT2's RandomSampler gathers it)."""
-        z = logp_row / np.float32(temperature) if temperature != 1 else logp_row.copy()
+        with np.errstate(over="ignore"):
+            z = logp_row / np.float32(temperature) if temperature != 1 else logp_row.copy()
         if topk > 0:
             kth = np.partition(z, -topk)[-topk]
             z = np.where(z >= kth, z, np.float32(LOWEST))
@@ -459,7 +462,7 @@ class WhisperOracle:
         eot = tok["eot"]
         V = self.n_vocab
         ncand = 2 * K
-        max_cand = int(round(K * patience))
+        max_cand = int(math.floor(K * patience + 0.5))  # std::round: halves away from zero
         allow_early_exit = patience == 1 and lp == 0
         # per chunk state
         hist = [[[]] for _ in range(B)]  # hist[b][k] -> tokens ; starts unexpanded with one row per chunk

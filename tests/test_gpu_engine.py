@@ -1,0 +1,202 @@
+"""-m gpu: the engine (encoder, decoder, on-device search) against the CPU oracle, through the C ABI.
+
+Stated tolerances: encoder activations |err| <= 1e-2 absolute on O(1)-magnitude LayerNorm outputs with
+relative Frobenius error <= 3e-3 (fp16 tensor-core inputs, fp32 accumulate and residual stream); teacher-forced
+logits <= 0.05 absolute on logits of standard deviation ~4; tokens exact on greedy/beam unless the oracle
+itself reports a near-tie (margin below the logit tolerance) at the first point of divergence.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import fake_logits_numpy
+from faster_whisper_b200 import engine
+from faster_whisper_b200.synthetic import synthetic_audio
+from oracle import whisper_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.05
+
+
+def make_engine(m, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return engine.Whisper(dims=m["dims"], weights=m["weights"], tokens=m["tokens"], device="cuda")
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="module")
+def eng(micro):
+    return make_engine(micro)
+
+
+@pytest.fixture(scope="module")
+def eng_ml(micro_ml):
+    return make_engine(micro_ml)
+
+
+def features_for(m, n_chunks, seed=0):
+    return np.stack([orc.pad_or_trim(orc.log_mel(synthetic_audio(seed + i, 30.0), m["dims"].n_mels)[:, :-1]) for i in range(n_chunks)])
+
+
+def rel_fro(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+# ---- encoder -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["tc", "ref"])
+def test_encoder_matches_oracle(micro, impl):
+    e = make_engine(micro, B2W_GEMM_IMPL=impl, B2W_ATTN_IMPL=impl)
+    feats = features_for(micro, 2)
+    want = micro["oracle"].encode(feats).numpy()
+    got = e.encode(feats).numpy()
+    assert got.shape == want.shape == (2, 1500, micro["dims"].n_audio_state)
+    assert np.abs(got - want).max() < 1e-2, np.abs(got - want).max()
+    assert rel_fro(got, want) < 3e-3
+
+
+def test_encoder_multilingual_geometry(micro_ml, eng_ml):
+    feats = features_for(micro_ml, 3, seed=4)
+    want = micro_ml["oracle"].encode(feats).numpy()
+    got = eng_ml.encode(feats).numpy()
+    assert np.abs(got - want).max() < 1e-2 and rel_fro(got, want) < 3e-3
+
+
+def test_encode_audio_fused_path(micro, eng):
+    chunks = [synthetic_audio(20, 30.0), synthetic_audio(21, 11.3), synthetic_audio(22, 0.5), np.zeros(0, np.float32)]
+    sv, feats = eng.encode_audio(chunks, return_features=True)
+    want_feats = np.stack([orc.pad_or_trim(orc.log_mel(c, micro["dims"].n_mels)[:, :-1]) for c in chunks])
+    assert np.abs(feats - want_feats).max() < 2e-3
+    want = micro["oracle"].encode(want_feats).numpy()
+    got = sv.numpy()
+    assert np.abs(got - want).max() < 1.5e-2 and rel_fro(got, want) < 4e-3
+
+
+def test_encode_rejects_bad_shapes(eng, micro):
+    with pytest.raises(ValueError):
+        eng.encode(np.zeros((1, micro["dims"].n_mels, 2999), np.float32))
+
+
+# ---- decoder math: teacher-forced logits ---------------------------------------------------------------------
+def test_teacher_forced_logits(micro, eng):
+    st = micro["tokens"]
+    feats = features_for(micro, 2, seed=7)
+    enc_o = micro["oracle"].encode(feats)
+    rng = np.random.default_rng(5)
+    toks = np.concatenate([np.array([[st.sot, st.no_timestamps]] * 2), rng.integers(0, 50000, (2, 21))], axis=1).astype(np.int32)
+    import torch
+
+    o = micro["oracle"]
+    cache = [None] * micro["dims"].n_text_layer
+    want = o.decoder_forward(torch.from_numpy(toks).long(), 0, cache, o.cross_kv(enc_o), torch.arange(2)).numpy()
+    got = eng.debug_logits(eng.encode(feats), toks)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < LOGIT_TOL, np.abs(got - want).max()
+    assert (got.argmax(-1) == want.argmax(-1)).mean() > 0.95
+
+
+# ---- search logic with the deterministic stand-in decoder (bit-level comparison of the decisions) -------------
+def _search_case(eng, m, prompts, **kw):
+    st = m["tokens"]
+    fl = fake_logits_numpy(m["dims"].n_vocab, st.timestamp_begin, st.eot)
+    want = m["oracle"].generate(None, prompts, fake_logits=fl, return_scores=True, return_no_speech_prob=False, **kw)
+    got = eng.generate(None, prompts, _fake_logits=True, return_scores=True, **kw)
+    for w, g in zip(want, got):
+        assert g.sequences_ids == w.sequences_ids, (kw, g.sequences_ids, w.sequences_ids)
+        assert np.allclose(g.scores, w.scores, rtol=1e-4, atol=1e-4), (g.scores, w.scores)
+
+
+@pytest.mark.parametrize("beam", [1, 2, 5])
+@pytest.mark.parametrize("timestamps", [False, True])
+def test_search_matches_oracle(eng, micro, beam, timestamps):
+    st = micro["tokens"]
+    base = [st.sot] + ([] if timestamps else [st.no_timestamps])
+    prompts = [base + [100 + i] for i in range(3)]
+    _search_case(eng, micro, prompts, beam_size=beam, max_length=60, suppress_tokens=[5, 6, 7, st.sot, st.transcribe])
+
+
+def test_search_options(eng, micro):
+    st = micro["tokens"]
+    prompts = [[st.sot, 321], [st.sot, 654]]
+    _search_case(eng, micro, prompts, beam_size=5, patience=2.0, length_penalty=0.6, max_length=40)
+    _search_case(eng, micro, prompts, beam_size=5, length_penalty=0.0, max_length=40)
+    _search_case(eng, micro, prompts, beam_size=4, num_hypotheses=3, repetition_penalty=1.3, no_repeat_ngram_size=2, max_length=50)
+    _search_case(eng, micro, prompts, beam_size=1, repetition_penalty=1.5, no_repeat_ngram_size=3, max_length=50,
+                 max_initial_timestamp_index=10, suppress_blank=False)
+    _search_case(eng, micro, [[st.sot, st.no_timestamps, 9]], beam_size=5, max_length=448)
+
+
+def test_sampling_matches_oracle_rng(eng, micro):
+    st = micro["tokens"]
+    prompts = [[st.sot, st.no_timestamps, 77]] * 2
+    _search_case(eng, micro, prompts, beam_size=1, num_hypotheses=5, sampling_topk=0, sampling_temperature=0.6, seed=1234, max_length=30)
+
+
+# ---- full generate vs oracle -------------------------------------------------------------------------------------
+def _compare_generate(eng, m, feats, prompts, **kw):
+    o = m["oracle"]
+    want = o.generate(o.encode(feats), prompts, return_scores=True, return_no_speech_prob=True, **kw)
+    got = eng.generate(eng.encode(feats), prompts, return_scores=True, return_no_speech_prob=True, **kw)
+    exact = 0
+    for w, g in zip(want, got):
+        assert abs(g.no_speech_prob - w.no_speech_prob) < 5e-3 * max(1.0, w.no_speech_prob) + 1e-6
+        if g.sequences_ids[0] == w.sequences_ids[0]:
+            exact += 1
+            assert abs(g.scores[0] - w.scores[0]) < 0.05
+        else:
+            # divergence is only acceptable at a near-tie the oracle itself reports
+            assert w.min_margin < 2 * LOGIT_TOL, (w.min_margin, g.sequences_ids[0][:12], w.sequences_ids[0][:12])
+    return exact, len(want)
+
+
+def test_generate_greedy_token_exact(micro, eng):
+    st = micro["tokens"]
+    feats = features_for(micro, 3, seed=30)
+    prompts = [[st.sot, st.no_timestamps]] * 3
+    exact, n = _compare_generate(eng, micro, feats, prompts, beam_size=1, max_length=40, suppress_tokens=[st.sot, st.no_speech])
+    assert exact >= n - 1
+
+
+def test_generate_beam5_with_timestamps(micro, eng):
+    st = micro["tokens"]
+    feats = features_for(micro, 2, seed=40)
+    prompts = [[st.sot_prev, 1000, 1001, st.sot]] * 2
+    exact, n = _compare_generate(eng, micro, feats, prompts, beam_size=5, max_length=36)
+    assert exact >= n - 1
+
+
+def test_generate_multilingual_and_language_detection(micro_ml, eng_ml):
+    st = micro_ml["tokens"]
+    feats = features_for(micro_ml, 2, seed=50)
+    prompts = [[st.sot, st.lang_begin + 3, st.transcribe, st.no_timestamps]] * 2
+    _compare_generate(eng_ml, micro_ml, feats, prompts, beam_size=5, max_length=24)
+    o = micro_ml["oracle"]
+    want = o.detect_language(o.encode(feats))
+    got = eng_ml.detect_language(eng_ml.encode(feats))
+    for w, g in zip(want, got):
+        wp = dict(w)
+        from faster_whisper_b200.config import LANGUAGE_CODES
+
+        for name, p in g[:5]:
+            idx = st.lang_begin + LANGUAGE_CODES.index(name[2:-2])
+            assert abs(wp[idx] - p) < 2e-3
+
+
+def test_generate_errors(micro, eng):
+    st = micro["tokens"]
+    feats = features_for(micro, 1)
+    enc = eng.encode(feats)
+    with pytest.raises(ValueError):
+        eng.generate(enc, [[5, 6]])  # no SOT
+    with pytest.raises(ValueError):
+        eng.generate(enc, [[st.sot], [st.sot]])  # batch mismatch
+    r = eng.generate(enc, [[st.sot] * 10], max_length=10, return_scores=True)
+    assert r[0].sequences_ids == [[]]
