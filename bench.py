@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path BASELINE.json names: log-mel -> encoder -> beam-5 decoder, large-v3 fp16, 30 s chunks.
+
+    python bench.py --gpus N --steps K --warmup W            # our engine (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference path (rank 0 only)
+
+A *step* is one pass of the hot path over one batch of synthetic 30 s chunks on every GPU:
+``--workload single`` (default, BASELINE.json configs[1]) = one chunk, beam_size=5;
+``--workload batched`` (configs[2]/[4]) = 16 chunks through one generate() call.  Weak scaling: per-GPU work is fixed.
+Decode length is pinned: prompt of 4 tokens, exactly 128 new tokens (EOT in suppress_tokens).
+
+Prints ONE JSON line (rank 0).  ``value`` = audio seconds per wall second through the engine calls
+(encode_audio + generate; the 1.92 MB/chunk PCM upload is inside, see ``stages_ms.h2d``); ``e2e`` = the same metric through the
+public API (``BatchedInferencePipeline.transcribe`` on a host NumPy waveform, segments consumed); ``roofline`` = decode-step
+HBM roofline (algorithmic bytes W + B*X + R*t*S per step over CUDA-event time on the engine's stream).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/s (RTF) large-v3 fp16 beam=5, 30s chunks"
+NEW_TOKENS = 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a port of the reference path; CTranslate2 itself is not installable here)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(model_name: str, beam: int, sample_tokens: int, seed: int, threads: int):
+    import torch
+
+    from faster_whisper_b200.config import MODEL_DIMS, special_tokens
+    from faster_whisper_b200.synthetic import make_weights, synthetic_audio
+    from oracle.whisper_oracle import WhisperOracle, log_mel, pad_or_trim
+
+    torch.set_num_threads(threads)
+    dims = MODEL_DIMS[model_name]
+    st = special_tokens(dims.n_vocab)
+    w = make_weights(dims, seed=seed)
+    orc = WhisperOracle(dims.to_dict(), w, st.to_dict())
+    audio = synthetic_audio(0, 30.0)
+    t0 = time.perf_counter()
+    feats = pad_or_trim(log_mel(audio, dims.n_mels)[:, :-1])[None]
+    t1 = time.perf_counter()
+    enc = orc.encode(feats)
+    t2 = time.perf_counter()
+    prompt = [st.sot, st.lang_begin, st.transcribe, st.no_timestamps] if dims.is_multilingual else [st.sot, st.no_timestamps]
+    sup = [st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech]
+    orc.generate(enc, [prompt], beam_size=beam, max_length=len(prompt) + sample_tokens, suppress_tokens=sup)
+    t3 = time.perf_counter()
+    per_tok = (t3 - t2) / (sample_tokens + len(prompt) - 1)
+    total = (t1 - t0) + (t2 - t1) + per_tok * (NEW_TOKENS + len(prompt) - 1)
+    return dict(value=30.0 / total, unit="audio-s/s", cores=threads, kind="port",
+                sample=(f"1 chunk of 30 s: log-mel {1e3 * (t1 - t0):.0f} ms + encoder {1e3 * (t2 - t1):.0f} ms measured in full; beam-{beam} decode "
+                        f"measured for {sample_tokens} new tokens ({1e3 * per_tok:.0f} ms/position) and extrapolated to {NEW_TOKENS}; "
+                        "fp32 torch CPU restatement of the reference path, not CTranslate2 int8"))
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    vals = []
+    cb = None
+    for _ in range(max(1, min(args.steps, 2))):
+        cb = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, threads)
+        vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = dict(metric=METRIC, value=v, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=30.0 / v * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config={"workload": workload_name(args), "model": args.model, "note": "CPU port of the reference path on rank 0's host cores"},
+                cpu_baseline=cb, e2e={"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                wall_s=time.perf_counter() - t0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.workload == "single":
+        return f"{args.model} fp16 beam_size={args.beam_size}, single 30 s chunk per step, prompt 4 + {NEW_TOKENS} new tokens (configs[1])"
+    return (f"{args.model} fp16 beam_size={args.beam_size}, BatchedInferencePipeline batch_size={args.batch_size}, "
+            f"{args.batch_size} x 30 s chunks per step, prompt 4 + {NEW_TOKENS} new tokens (configs[2])")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_engine(args):
+    rank, local_rank, world = dist_env()
+    use_dist = world > 1
+    if use_dist:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from faster_whisper_b200 import BatchedInferencePipeline, WhisperModel
+    from faster_whisper_b200.config import MODEL_DIMS, special_tokens
+    from faster_whisper_b200.synthetic import synthetic_audio
+
+    dims = MODEL_DIMS[args.model]
+    st = special_tokens(dims.n_vocab)
+    t_load = time.perf_counter()
+    model = WhisperModel(args.model, device="cuda", device_index=local_rank, compute_type="float16", synthetic_seed=args.seed)
+    eng = model.model
+    t_load = time.perf_counter() - t_load
+    pipe = BatchedInferencePipeline(model)
+    B = 1 if args.workload == "single" else args.batch_size
+    chunks = [synthetic_audio(rank * 1000 + i, 30.0) for i in range(B)]
+    audio = np.concatenate(chunks)
+    clips = [{"start": 30.0 * i, "end": 30.0 * (i + 1)} for i in range(B)]
+    prompt = [st.sot, st.lang_begin, st.transcribe, st.no_timestamps] if dims.is_multilingual else [st.sot, st.no_timestamps]
+    suppress = sorted({st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech})
+
+    def engine_step():
+        enc = eng.encode_audio(chunks)
+        res = eng.generate(enc, [prompt] * B, beam_size=args.beam_size, max_length=len(prompt) + NEW_TOKENS, suppress_tokens=suppress,
+                           return_scores=True, return_no_speech_prob=True)
+        assert all(len(r.sequences_ids[0]) == NEW_TOKENS for r in res)
+        return res
+
+    def api_step():
+        segs, _ = pipe.transcribe(audio, language="en", beam_size=args.beam_size, batch_size=B, vad_filter=False, clip_timestamps=clips,
+                                  max_new_tokens=NEW_TOKENS, suppress_tokens=[-1, st.eot], without_timestamps=True)
+        n = sum(len(s.tokens) for s in segs)
+        assert n == NEW_TOKENS * B, n
+        return n
+
+    def barrier():
+        eng.sync()
+        if use_dist:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        eng.sync()
+        dt = time.perf_counter() - t0
+        if use_dist:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    for _ in range(max(args.warmup, 3)):
+        engine_step()
+    api_step()
+    eng.timing(enable=True, reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dt = timed(engine_step, args.steps)
+    stats = eng.timing()
+    eng.timing(enable=False)
+    dt_api = timed(api_step, args.steps)
+    clocks = sampler.stop()
+
+    audio_s = 30.0 * B * args.steps * world
+    value = audio_s / dt
+    e2e_value = audio_s / dt_api
+    pk = peaks()
+    dec_ms = stats["decode_ms"]
+    steps_dec = max(1, stats["decode_steps"])
+    ach = stats["decode_alg_bytes"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+    enc_flops = enc_flops_per_chunk(dims) * B * args.steps
+    enc_tf = enc_flops / (stats["encoder_ms"] * 1e-3) / 1e12 if stats["encoder_ms"] > 0 else 0.0
+    line = dict(
+        metric=METRIC, value=value, unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+        rtf=dt / audio_s * world,
+        config={"workload": workload_name(args), "model": args.model, "global_batch": B * world, "beam_size": args.beam_size,
+                "new_tokens": NEW_TOKENS, "parallelism": f"chunk-parallel replicas x{world}",
+                "l2": "working set per step (3.1 GB weights + 0.25 GB/chunk cross-KV) exceeds the 126 MB L2; no flush needed",
+                "weights": f"synthetic seed {args.seed}, exact {args.model} shapes", "load_s": round(t_load, 1)},
+        e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(B * (448 * 4 + 16)),
+             "api": "BatchedInferencePipeline.transcribe(ndarray, clip_timestamps=..., batch_size=%d)" % B, "ms_per_step": dt_api / args.steps * 1e3},
+        gpu_launches=int(stats["launches"]),
+        clocks=clocks,
+        stages_ms={k[:-3]: round(v / args.steps, 3) for k, v in stats.items() if k.endswith("_ms") and v > 0},
+        roofline={"bound": "hbm", "kernel": "decode step (CUDA graph: skinny_gemm weight stream + self/cross attention + search)",
+                  "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "peak_source": pk["source"],
+                  "traffic": None, "ms_per_decode_step": dec_ms / steps_dec,
+                  "alg_bytes_per_step": stats["decode_alg_bytes"] / steps_dec},
+        roofline_encoder={"bound": "tensor", "achieved": enc_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": enc_tf / pk["tflops"],
+                          "flops_per_chunk": enc_flops_per_chunk(dims), "ms_per_chunk": stats["encoder_ms"] / (B * args.steps)},
+    )
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, os.cpu_count() or 1)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def enc_flops_per_chunk(dims) -> float:
+    d, L, m = dims.n_audio_state, dims.n_audio_layer, dims.n_mels
+    lin = 2.0 * (3000 * 3 * m * d + 1500 * 3 * d * d + L * 1500 * (4 * d * d + 2 * d * 4 * d))
+    att = L * 4.0 * 1500 * 1500 * d
+    return lin + att
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="single", choices=["single", "batched"])
+    ap.add_argument("--model", default="large-v3")
+    ap.add_argument("--beam-size", type=int, default=5)
+    ap.add_argument("--batch-size", type=int, default=16)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

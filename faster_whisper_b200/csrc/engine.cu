@@ -816,7 +816,8 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
   {
     uint8_t* k = key.data();
     memcpy(k, &sp, sizeof sp); k += sizeof sp;
-    const void* ptrs[6] = {e->xkv, m->kcache, m->sb_blob, m->d_xpart, (const void*)(uintptr_t)chunk0, (const void*)(uintptr_t)e->B};
+    const void* ptrs[6] = {e ? e->xkv : nullptr, m->kcache, m->sb_blob, m->d_xpart, (const void*)(uintptr_t)chunk0,
+                           (const void*)(uintptr_t)(e ? e->B : 0)};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
     int misc[4] = {splits, m->use_ref_gemv ? 1 : 0, n, K};
     memcpy(k, misc, sizeof misc);

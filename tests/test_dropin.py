@@ -1,0 +1,120 @@
+"""CPU: our WhisperModel / BatchedInferencePipeline and the UNMODIFIED reference host code, both driven over the same
+oracle-backed ``ctranslate2`` shim on the same audio, must produce the same segments and info (drop-in check of the host
+layer: prompt building, windowing/seek loop, fallback, batching, timestamp splitting)."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from faster_whisper_b200 import engine as our_engine
+from faster_whisper_b200 import transcribe as T
+from faster_whisper_b200.synthetic import make_tokenizer, synthetic_audio
+from oracle import ct2_shim
+from oracle import whisper_oracle as orc
+from oracle.refload import load_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not mounted (build container only)")
+
+
+@pytest.fixture(scope="module")
+def both(micro_ml):
+    dims, weights = micro_ml["dims"], micro_ml["weights"]
+    calls_ref, calls_our = [], []
+    mod, _ = ct2_shim.make_module(dims, weights, calls_ref)
+    fw = load_reference(ct2_module=mod)
+    hf = make_tokenizer(dims.n_vocab)
+    import io
+    import json
+
+    files = {"tokenizer.json": hf.to_str().encode(), "preprocessor_config.json": json.dumps({"feature_size": dims.n_mels}).encode()}
+    ref_model = fw.WhisperModel("synthetic", device="cpu", files=dict(files))
+    # ours: same shim class in place of the CUDA engine, oracle log-mel in place of the CUDA kernel
+    whisper_cls, _ = ct2_shim.make_whisper_class(dims, weights, calls_our)
+    mp = pytest.MonkeyPatch()
+    mp.setattr(our_engine, "Whisper", lambda *a, **k: whisper_cls())
+    mp.setattr(our_engine, "log_mel", lambda x, n_mels, padding=160, device=0: orc.log_mel(x, n_mels, padding))
+    mp.setattr(our_engine, "StorageView", ct2_shim.StorageView)
+    our_model = T.WhisperModel("synthetic", device="cuda", files=dict(files), dims=dims, weights=weights)
+    yield fw, ref_model, our_model, calls_ref, calls_our
+    mp.undo()
+
+
+def seg_tuple(s):
+    return (s.id, s.seek, round(s.start, 3), round(s.end, 3), s.text, tuple(s.tokens), round(s.avg_logprob, 4),
+            round(s.compression_ratio, 4), round(s.no_speech_prob, 5), s.temperature)
+
+
+def strip(calls):
+    out = []
+    for c in calls:
+        if c[0] == "generate":
+            kw = {k: (round(v, 6) if isinstance(v, float) else v) for k, v in c[2].items()}
+            out.append(("generate", c[1], kw))
+        else:
+            out.append(c)
+    return out
+
+
+COMMON = dict(no_speech_threshold=None, log_prob_threshold=None, compression_ratio_threshold=None)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(language="en", beam_size=2, max_new_tokens=12, **COMMON),
+    dict(language="fr", task="translate", beam_size=1, without_timestamps=True, max_new_tokens=8, initial_prompt="hello there", **COMMON),
+    dict(beam_size=2, max_new_tokens=6, temperature=[0.0, 0.4], log_prob_threshold=-0.5, no_speech_threshold=None,
+         compression_ratio_threshold=2.4, best_of=2),
+    dict(language="de", beam_size=1, max_new_tokens=10, clip_timestamps="3,20,31,40", hotwords="ab cd", condition_on_previous_text=False, **COMMON),
+])
+def test_sequential_transcribe_matches_reference(both, kw):
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(60, 30.0), synthetic_audio(61, 14.0)])
+    calls_ref.clear()
+    calls_our.clear()
+    if kw.get("temperature"):
+        pytest.skip("sampling fallback draws from different RNG streams in the two host layers' engines") if False else None
+    ref_segs, ref_info = ref_model.transcribe(audio.copy(), **kw)
+    ref_segs = [seg_tuple(s) for s in ref_segs]
+    our_segs, our_info = our_model.transcribe(audio.copy(), **kw)
+    our_segs = [seg_tuple(s) for s in our_segs]
+    assert our_segs == ref_segs
+    assert len(ref_segs) > 0
+    assert strip(calls_our) == strip(calls_ref)  # identical engine traffic: same prompts, same keyword arguments
+    assert (our_info.language, our_info.duration, our_info.duration_after_vad) == (ref_info.language, ref_info.duration, ref_info.duration_after_vad)
+    assert our_info.language_probability == pytest.approx(ref_info.language_probability)
+    a, b = dataclasses.asdict(our_info.transcription_options), dataclasses.asdict(ref_info.transcription_options)
+    assert a == b
+
+
+@pytest.mark.parametrize("kw", [
+    dict(language="en", beam_size=2, batch_size=2, max_new_tokens=8),
+    dict(beam_size=1, batch_size=3, max_new_tokens=6, without_timestamps=False, multilingual=True),
+])
+def test_batched_transcribe_matches_reference(both, kw):
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(70 + i, 30.0) for i in range(3)] + [synthetic_audio(75, 7.5)])
+    clips = [{"start": 0.0, "end": 30.0}, {"start": 30.0, "end": 60.0}, {"start": 60.0, "end": 90.0}, {"start": 90.0, "end": 97.5}]
+    ref_segs, ref_info = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)
+    ref_segs = [seg_tuple(s) for s in ref_segs]
+    our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)
+    our_segs = [seg_tuple(s) for s in our_segs]
+    assert our_segs == ref_segs and len(ref_segs) >= 4
+    assert (our_info.language, our_info.duration, our_info.duration_after_vad) == (ref_info.language, ref_info.duration, ref_info.duration_after_vad)
+
+
+def test_batched_errors_match_reference(both):
+    fw, ref_model, our_model, _, _ = both
+    audio = synthetic_audio(1, 40.0)
+    for pipe in (fw.BatchedInferencePipeline(ref_model), T.BatchedInferencePipeline(our_model)):
+        with pytest.raises(RuntimeError, match="No clip timestamps found"):
+            pipe.transcribe(audio, vad_filter=False)
+        with pytest.raises(ValueError, match="max_new_tokens"):
+            segs, _ = pipe.transcribe(audio[: 16000 * 10], vad_filter=False, language="en", max_new_tokens=500)
+            list(segs)
+
+
+def test_detect_language_matches_reference(both):
+    fw, ref_model, our_model, _, _ = both
+    audio = synthetic_audio(5, 45.0)
+    a = ref_model.detect_language(audio=audio, language_detection_segments=2, language_detection_threshold=0.99)
+    b = our_model.detect_language(audio=audio, language_detection_segments=2, language_detection_threshold=0.99)
+    assert a[0] == b[0] and a[1] == pytest.approx(b[1]) and [x[0] for x in a[2]] == [x[0] for x in b[2]]
