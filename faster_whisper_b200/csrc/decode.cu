@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const SelfAttnArgs a
   const RowInfo ri = a.rows[r];
   const int d = a.d, nk = ri.pos + 1;
   const int tid = threadIdx.x;
-  const int cur = (ri.pos - a.step_base) & 1;
+  const int cur = ri.pos & 1;
   const uint8_t* anc = a.anc + cur * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * a.n_ctx;
   // q in registers (64 halves)
   uint4 qv[8];
@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
     qs[i] = (q < nq) ? __half2float(a.q[(long long)(row0 + q) * d + h * 64 + e]) * 0.125f : 0.f;
   }
   __syncthreads();
-  const __half* Kb = a.xk + (((long long)b * a.H + h) * T) * 64;
-  const __half* Vb = a.xv + (((long long)b * a.H + h) * T) * 64;
+  const DecBindings bd = *a.bind;
+  const long long per = (long long)bd.B_total * a.H * T * 64;  // one layer's K (or V) block
+  const __half* Kb = bd.xkv + ((long long)a.layer * 2 + 0) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
+  const __half* Vb = bd.xkv + ((long long)a.layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
   // phase 1: scores, one key per thread
   for (int j = tid; j < nk; j += kXThreads) {
     const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)(k0 + j) * 64);

@@ -45,18 +45,26 @@ struct SelfAttnArgs {
   const __half* q;        // [R][d]
   const __half* kcache;   // this layer: [chunk][pos][slot][d]
   const __half* vcache;
-  const uint8_t* anc;     // [2][chunk][slot][n_ctx]; buffer (pos - step_base) & 1 is current
+  const uint8_t* anc;     // [2][chunk][slot][n_ctx]; buffer (pos & 1) is current
   __half* out;            // [R][d]
   int d, n_ctx, slots;
   long long anc_buf_stride;
-  int step_base;          // prompt_len - 1 (0 outside generate)
+  int step_base;          // unused (kept for ABI stability of the struct)
 };
 void dec_self_attn(const SelfAttnArgs& a, int R, int H, cudaStream_t s);
 
+// Per-generate-call bindings read by the step kernels from device memory, so that the captured CUDA graph of a
+// decode step does not depend on which encoder output (or which slice of it) is being decoded.
+struct DecBindings {
+  const __half* xkv;  // [L][2][B_total][H][T][64]
+  int B_total;
+  int chunk0;
+};
+
 struct CrossAttnArgs {
   const __half* q;   // [R][d], rows of a chunk contiguous
-  const __half* xk;  // this layer: [b][h][T][64]
-  const __half* xv;
+  const DecBindings* bind;
+  int layer;
   __half* out;       // [R][d]
   float* partial;
   int* counters;
@@ -109,6 +117,7 @@ struct SearchState {
 
 struct SearchBuffers {
   SearchState* state;          // [1]
+  const SearchParams* params;  // [1] device copy of the options of the running generate() call
   RowInfo* rows;               // [B*K]
   int* tokens_in;              // [B*K] token fed at this step
   float* cum;                  // [2][B*K]
@@ -127,9 +136,10 @@ struct SearchBuffers {
   int n_ctx;
 };
 
-void search_rows(const float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s);
-void search_update(const SearchParams& p, const SearchBuffers& b, cudaStream_t s);
-void fake_logits(float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s);
+// `p` lives in device memory (SearchBuffers::params) so a captured step graph is independent of the options
+void search_rows(const float* logits, int R, int vpad, const SearchBuffers& b, cudaStream_t s);
+void search_update(int B, const SearchBuffers& b, cudaStream_t s);
+void fake_logits(float* logits, int R, const SearchBuffers& b, cudaStream_t s);
 void no_speech_from_logits(const float* logits, int row_stride, int R, int rows_per_chunk, int row_in_chunk, int n_vocab,
                            int no_speech_id, float* out, cudaStream_t s);
 void lang_probs_from_logits(const float* logits, int row_stride, int B, int lang_begin, int n_lang, float* out, cudaStream_t s);

@@ -63,7 +63,7 @@ Model::~Model() {
   if (stream) cudaStreamSynchronize(stream);
   for (void* p : allocs) cudaFree(p);
   void* ws[] = {e_feats, e_x0, e_x1, e_x, e_xn, e_qkv, e_ao, e_h, e_pcm, e_chunks, e_chunk_max, kcache, vcache, d_x, d_xn,
-                d_q, d_ao, d_h, d_logits, d_xpart, d_counters, d_suppress, sb_blob};
+                d_q, d_ao, d_h, d_logits, d_xpart, d_counters, d_suppress, sb_blob, d_bind};
   for (void* p : ws)
     if (p) cudaFree(p);
   if (h_pinned) cudaFreeHost(h_pinned);
@@ -323,6 +323,7 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   B2W_CUDA(cudaMemset(m->d_counters, 0, (64 + 16 * 20 * 64) * sizeof(int)));
   B2W_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->h_pinned), 4096));
   m->d_suppress = dalloc<uint8_t>(m->vpad);
+  m->d_bind = dalloc<DecBindings>(1);
   decode_configure();
   search_configure();
   B2W_CUDA(cudaStreamSynchronize(m->stream));
@@ -537,6 +538,7 @@ static void ensure_search_ws(Model* m, int B, int K) {
     return o;
   };
   const size_t Rr = std::max<size_t>(R, kMaxRows);
+  const size_t o_params = take(sizeof(SearchParams));
   const size_t o_state = take(sizeof(SearchState)), o_rows = take(Rr * sizeof(RowInfo)), o_tok = take(Rr * 4),
                o_cum = take(2 * R * 4), o_hist = take(2 * R * n_ctx * 4), o_anc = take(2 * R * n_ctx),
                o_cs = take(R * kMaxCand * 4), o_ct = take(R * kMaxCand * 4), o_done = take(B * 4), o_fc = take(B * 4),
@@ -546,6 +548,7 @@ static void ensure_search_ws(Model* m, int B, int K) {
   m->sb_blob = blob;
   SearchBuffers& sb = m->sb;
   sb.state = reinterpret_cast<SearchState*>(blob + o_state);
+  sb.params = reinterpret_cast<const SearchParams*>(blob + o_params);
   sb.rows = reinterpret_cast<RowInfo*>(blob + o_rows);
   sb.tokens_in = reinterpret_cast<int*>(blob + o_tok);
   sb.cum = reinterpret_cast<float*>(blob + o_cum);
@@ -606,14 +609,17 @@ static void gv(Model* m, GvArgs a) {
 }
 
 // all decoder layers for R rows described by sb.rows / sb.tokens_in; leaves LN_final(x) in d_xn
-static void decoder_layers(Model* m, const Encoded* e, int chunk0, int n_chunks, int rows_per_chunk, int slots, int splits,
-                           int step_base) {
+static void bind_encoded(Model* m, const Encoded* e, int chunk0) {
+  m->h_bind = DecBindings{e ? e->xkv : nullptr, e ? e->B : 0, chunk0};
+  B2W_CUDA(cudaMemcpyAsync(m->d_bind, &m->h_bind, sizeof(DecBindings), cudaMemcpyHostToDevice, m->stream));
+}
+
+static void decoder_layers(Model* m, int n_chunks, int rows_per_chunk, int slots, int splits, int step_base) {
   const b2w_config& c = m->cfg;
   const int dt = c.n_text_state, L = c.n_text_layer, H = c.n_text_head, R = n_chunks * rows_per_chunk;
   cudaStream_t s = m->stream;
   const SearchBuffers& sb = m->sb;
   embed_ln(sb.tokens_in, sb.rows, m->tok_emb, m->dec_pos, m->dec[0].ln1_g, m->dec[0].ln1_b, m->d_x, m->d_xn, R, dt, c.n_vocab, s);
-  const size_t xkv_layer = (size_t)e->B * H * 1500 * 64;  // per K or V
   const int qgroups = cross_attn_qgroups(rows_per_chunk);
   const size_t need_part = cross_attn_partial_floats(n_chunks, H, rows_per_chunk, splits);
   if (need_part > m->d_xpart_floats) {
@@ -643,8 +649,8 @@ static void decoder_layers(Model* m, const Encoded* e, int chunk0, int n_chunks,
     gv(m, q);
     CrossAttnArgs ca;
     ca.q = m->d_q;
-    ca.xk = e->xkv + ((size_t)l * 2 + 0) * xkv_layer + (size_t)chunk0 * H * 1500 * 64;
-    ca.xv = e->xkv + ((size_t)l * 2 + 1) * xkv_layer + (size_t)chunk0 * H * 1500 * 64;
+    ca.bind = m->d_bind;
+    ca.layer = l;
     ca.out = m->d_ao; ca.partial = m->d_xpart; ca.counters = m->d_counters + 64;
     ca.T = 1500; ca.H = H; ca.d = dt; ca.rows_per_chunk = rows_per_chunk; ca.splits = splits; ca.qgroups = qgroups;
     dec_cross_attn(ca, n_chunks, s);
@@ -693,7 +699,8 @@ static void prefill_pass(Model* m, const Encoded* e, int chunk0, int n, const in
   B2W_CUDA(cudaMemcpyAsync(m->sb.rows, rows.data(), R * sizeof(RowInfo), cudaMemcpyHostToDevice, m->stream));
   B2W_CUDA(cudaMemcpyAsync(m->sb.tokens_in, toks.data(), R * sizeof(int), cudaMemcpyHostToDevice, m->stream));
   B2W_CUDA(cudaStreamSynchronize(m->stream));  // host vectors go out of scope
-  decoder_layers(m, e, chunk0, n, rpc, slots, pick_splits(m, n, rpc), step_base);
+  bind_encoded(m, e, chunk0);
+  decoder_layers(m, n, rpc, slots, pick_splits(m, n, rpc), step_base);
 }
 
 struct HypOut {
@@ -800,26 +807,29 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     B2W_CUDA(cudaStreamSynchronize(s));
   }
   const int splits = pick_splits(m, n, K);
+  m->h_params = sp;
+  B2W_CUDA(cudaMemcpyAsync(const_cast<SearchParams*>(sb.params), &m->h_params, sizeof(SearchParams), cudaMemcpyHostToDevice, s));
+  bind_encoded(m, e, chunk0);
   auto record_step = [&]() {
     if (sp.fake_logits) {
-      fake_logits(m->d_logits, sp, sb, s);
+      fake_logits(m->d_logits, R, sb, s);
     } else {
-      decoder_layers(m, e, chunk0, n, K, K, splits, P - 1);
+      decoder_layers(m, n, K, K, splits, P - 1);
       logits_gemm(m, R);
     }
-    search_rows(m->d_logits, sp, sb, s);
-    search_update(sp, sb, s);
+    search_rows(m->d_logits, R, m->vpad, sb, s);
+    search_update(n, sb, s);
   };
 
   // one CUDA graph per (shape, options, buffers) — replayed every step, no per-step host parameters
-  std::vector<uint8_t> key(sizeof(SearchParams) + 6 * sizeof(void*) + 4 * sizeof(int));
+  // the graph depends only on shapes and workspace pointers: options and encoder-output bindings are read from
+  // device memory by the kernels, so one instantiated graph serves every window / chunk group of the same shape
+  std::vector<uint8_t> key(4 * sizeof(void*) + 8 * sizeof(int));
   {
     uint8_t* k = key.data();
-    memcpy(k, &sp, sizeof sp); k += sizeof sp;
-    const void* ptrs[6] = {e ? e->xkv : nullptr, m->kcache, m->sb_blob, m->d_xpart, (const void*)(uintptr_t)chunk0,
-                           (const void*)(uintptr_t)(e ? e->B : 0)};
+    const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[4] = {splits, m->use_ref_gemv ? 1 : 0, n, K};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, 0, 0, 0};
     memcpy(k, misc, sizeof misc);
   }
   if (sp.fake_logits == 0) {
@@ -830,7 +840,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       m->d_xpart = dalloc<float>(need_part);
       m->d_xpart_floats = need_part;
       const void* px = m->d_xpart;
-      memcpy(key.data() + sizeof sp + 3 * sizeof(void*), &px, sizeof px);
+      memcpy(key.data() + 2 * sizeof(void*), &px, sizeof px);
     }
   }
   const int64_t launches_before = g_launches;

@@ -97,6 +97,9 @@ struct Model {
   size_t d_xpart_floats = 0;
   int* d_counters = nullptr;  // [0]: GEMM ticket, [64..]: cross-attention groups
   uint8_t* d_suppress = nullptr;
+  DecBindings* d_bind = nullptr;
+  DecBindings h_bind{};
+  SearchParams h_params{};
   // search buffers
   SearchBuffers sb{};
   void* sb_blob = nullptr;

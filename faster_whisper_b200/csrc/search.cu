@@ -71,8 +71,8 @@ __device__ __forceinline__ float gumbel_u32(unsigned long long seed, int row, in
   return -logf(-logf(u));
 }
 
-__global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* __restrict__ logits, const SearchParams p,
-                                                                   const SearchBuffers bf) {
+__global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* __restrict__ logits, const SearchBuffers bf) {
+  const SearchParams p = *bf.params;
   extern __shared__ float s[];  // [vpad]
   __shared__ float red[32];
   __shared__ ArgMax wbest[32];
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
   const int V = p.n_vocab;
   const RowInfo ri = bf.rows[r];
   const int step = ri.pos - (p.prompt_len - 1);
-  const int cur = step & 1;
+  const int cur = ri.pos & 1;  // history double buffer is indexed by the parity of the absolute position
   const int* hist = bf.hist + ((long long)cur * p.B * p.K + r) * bf.n_ctx;
   const int len = step;  // tokens generated so far by this row
   const float* row = logits + (long long)r * p.vpad;
@@ -259,15 +259,16 @@ void search_configure() {
   B2W_CUDA(cudaFuncSetAttribute(search_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
 }
 
-void search_rows(const float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
-  const int smem = p.vpad * (int)sizeof(float);
+void search_rows(const float* logits, int R, int vpad, const SearchBuffers& b, cudaStream_t s) {
+  const int smem = vpad * (int)sizeof(float);
   B2W_CHECK(smem <= 210 * 1024, "vocabulary too large for the in-shared-memory row search");
-  search_rows_kernel<<<p.B * p.K, kRowThreads, smem, s>>>(logits, p, b);
+  search_rows_kernel<<<R, kRowThreads, smem, s>>>(logits, b);
   B2W_LAUNCHED();
 }
 
 // ---- beam / greedy bookkeeping ----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) search_update_kernel(const SearchParams p, const SearchBuffers bf) {
+__global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers bf) {
+  const SearchParams p = *bf.params;
   __shared__ float c_score[kMaxCand];
   __shared__ int c_tok[kMaxCand], c_beam[kMaxCand];
   __shared__ int parent[kMaxBeam], newtok[kMaxBeam];
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchParams p
   const int r0 = b * K;
   const int pos = bf.rows[r0].pos;
   const int step = pos - (p.prompt_len - 1);
-  const int cur = step & 1, nxt = cur ^ 1;
+  const int cur = pos & 1, nxt = cur ^ 1;
   const bool is_last = (step + 1 >= p.max_steps);
   const long long RB = (long long)p.B * K;
 
@@ -412,15 +413,16 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchParams p
   }
 }
 
-void search_update(const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
-  search_update_kernel<<<p.B, 128, 0, s>>>(p, b);
+void search_update(int B, const SearchBuffers& b, cudaStream_t s) {
+  search_update_kernel<<<B, 128, 0, s>>>(b);
   B2W_LAUNCHED();
 }
 
 // ---- deterministic stand-in for the decoder (tests of the search logic only) -------------------------------------------
 // logits[r][v] = u24(hash(token_in, step, v)) * 2^-20 - 8  (+3 for timestamps, +0.25*step for EOT); mirrored in
 // tests/test_search.py so the device search can be compared bit-for-bit with the oracle's search.
-__global__ void fake_logits_kernel(float* __restrict__ logits, const SearchParams p, const SearchBuffers bf) {
+__global__ void fake_logits_kernel(float* __restrict__ logits, const SearchBuffers bf) {
+  const SearchParams p = *bf.params;
   const int r = blockIdx.y;
   const int step = bf.rows[r].pos - (p.prompt_len - 1);
   const unsigned tok = (unsigned)bf.tokens_in[r];
@@ -437,8 +439,8 @@ __global__ void fake_logits_kernel(float* __restrict__ logits, const SearchParam
     logits[(long long)r * p.vpad + v] = x;
   }
 }
-void fake_logits(float* logits, const SearchParams& p, const SearchBuffers& b, cudaStream_t s) {
-  fake_logits_kernel<<<dim3(32, p.B * p.K), 256, 0, s>>>(logits, p, b);
+void fake_logits(float* logits, int R, const SearchBuffers& b, cudaStream_t s) {
+  fake_logits_kernel<<<dim3(32, R), 256, 0, s>>>(logits, b);
   B2W_LAUNCHED();
 }
 
