@@ -37,21 +37,44 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {  // weights: read o
 constexpr int kGvWarps = 8;
 constexpr int kGvPF = 4;  // weight chunks in flight per warp (x2 with the double buffer)
 
-// LayerNorm of all active rows by one CTA (called by the last CTA of a residual-producing GEMM)
+// LayerNorm of all active rows by one CTA (called by the last CTA of a residual-producing GEMM).
+// One warp per row, the whole row in registers: every L2 load is issued before the first use.
 __device__ void cta_layernorm_rows(const float* x, const float* g, const float* b, __half* xn, int R, int d) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int n4 = d >> 2;
   for (int r = warp; r < R; r += nw) {
-    const float* xr = x + (long long)r * d;
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * d);
+    float4 v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int idx = lane + 32 * i;
+      v[i] = (idx < n4) ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float s = 0.f;
-    for (int i = lane; i < d; i += 32) s += __ldcg(xr + i);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
     const float mean = warp_sum(s) / d;
     float q = 0.f;
-    for (int i = lane; i < d; i += 32) {
-      const float t = __ldcg(xr + i) - mean;
-      q += t * t;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      if (lane + 32 * i < n4) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+      }
     }
     const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
-    for (int i = lane; i < d; i += 32) xn[(long long)r * d + i] = __float2half_rn((__ldcg(xr + i) - mean) * rstd * __ldg(g + i) + __ldg(b + i));
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    uint2* o = reinterpret_cast<uint2*>(xn + (long long)r * d);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < n4) {
+        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+        o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
+                            pack_half2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
+      }
+    }
   }
 }
 
@@ -325,8 +348,12 @@ void dec_self_attn(const SelfAttnArgs& a, int R, int H, cudaStream_t s) {
 constexpr int kXQ = 8;        // queries (rows of one chunk) per CTA
 constexpr int kXThreads = 128;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAttnArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int T = a.T, S = a.splits;
   const int split = blockIdx.x % S, qg = blockIdx.x / S, h = blockIdx.y, b = blockIdx.z;
   const int row0 = b * a.rows_per_chunk + qg * kXQ;
@@ -335,29 +362,35 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
   const int k0 = (int)((long long)T * split / S), k1 = (int)((long long)T * (split + 1) / S);
   const int nk = k1 - k0;
   const int kmax = (T + S - 1) / S + 1;
-  float* qs = sm;                 // [kXQ][64]
-  float* sc = qs + kXQ * 64;      // [kXQ][kmax]
-  float* wred = sc + kXQ * kmax;  // [4][kXQ][64]
+  float* qs = sm;                     // [kXQ][64]
+  float* sc = qs + kXQ * 64;          // [kXQ][kmax]
+  float* wred = sc + kXQ * kmax;      // [4][kXQ][64]
   float* stat = wred + 4 * kXQ * 64;  // [kXQ][2]
+  __half* vt = reinterpret_cast<__half*>(stat + kXQ * 2);  // [kmax][64] V tile; float offset 512 + 8*kmax + 2048 + 16 is a multiple of 4 -> 16-byte aligned
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d;
+  const DecBindings bd = *a.bind;
+  const long long per = (long long)bd.B_total * a.H * T * 64;  // one layer's K (or V) block
+  const __half* Kb = bd.xkv + ((long long)a.layer * 2 + 0) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
+  const __half* Vb = bd.xkv + ((long long)a.layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
+  // V tile -> shared memory, asynchronously: its HBM latency hides behind the score phase
+  for (int i = tid; i < nk * 8; i += kXThreads) cp_async16(vt + i * 8, Vb + (long long)k0 * 64 + i * 8);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < kXQ * 64; i += kXThreads) {
     const int q = i >> 6, e = i & 63;
     qs[i] = (q < nq) ? __half2float(a.q[(long long)(row0 + q) * d + h * 64 + e]) * 0.125f : 0.f;
   }
   __syncthreads();
-  const DecBindings bd = *a.bind;
-  const long long per = (long long)bd.B_total * a.H * T * 64;  // one layer's K (or V) block
-  const __half* Kb = bd.xkv + ((long long)a.layer * 2 + 0) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
-  const __half* Vb = bd.xkv + ((long long)a.layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
-  // phase 1: scores, one key per thread
+  // phase 1: scores, one key per thread (8 x 16-byte loads in flight per thread)
   for (int j = tid; j < nk; j += kXThreads) {
     const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)(k0 + j) * 64);
+    uint4 kr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) kr[i] = ldg_stream(kp + i);
     float kf[64];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint4 kv = ldg_stream(kp + i);
-      const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+      const __half2* k2 = reinterpret_cast<const __half2*>(&kr[i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __half22float2(k2[e]);
@@ -381,30 +414,34 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
   }
   __syncthreads();
   // phase 2: per-query partial softmax statistics (warp per query)
-  for (int q = warp; q < nq; q += 4) {
-    float mx = -INFINITY;
-    for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kmax + j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < nk; j += 32) {
-      const float p = __expf(sc[q * kmax + j] - mx);
-      sc[q * kmax + j] = p;
-      sum += p;
-    }
-    sum = warp_sum(sum);
-    if (lane == 0) {
-      stat[q * 2] = mx;
-      stat[q * 2 + 1] = sum;
+  for (int q = warp; q < kXQ; q += 4) {
+    if (q < nq) {
+      float mx = -INFINITY;
+      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kmax + j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < nk; j += 32) {
+        const float p = __expf(sc[q * kmax + j] - mx);
+        sc[q * kmax + j] = p;
+        sum += p;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        stat[q * 2] = mx;
+        stat[q * 2 + 1] = sum;
+      }
+    } else {
+      for (int j = lane; j < nk; j += 32) sc[q * kmax + j] = 0.f;  // unused query slots contribute nothing
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // phase 3: P*V, lane owns 2 dims, warps split keys
+  // phase 3: P*V from shared memory, lane owns 2 dims, warps split keys
   float acc[kXQ][2];
 #pragma unroll
   for (int q = 0; q < kXQ; ++q) acc[q][0] = acc[q][1] = 0.f;
   for (int j = warp; j < nk; j += 4) {
-    const __half2 v2 = *reinterpret_cast<const __half2*>(Vb + (long long)(k0 + j) * 64 + 2 * lane);
-    const float2 vf = __half22float2(v2);
+    const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vt + j * 64 + 2 * lane));
 #pragma unroll
     for (int q = 0; q < kXQ; ++q) {
       const float p = sc[q * kmax + j];
@@ -440,16 +477,28 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // combine the S partials (S <= 8): all L2 loads are issued before they are consumed
   const float* pg = a.partial + group * S * (kXQ * 66);
   for (int i = tid; i < nq * 64; i += kXThreads) {
     const int q = i >> 6, e = i & 63;
-    float M = -INFINITY;
-    for (int s2 = 0; s2 < S; ++s2) M = fmaxf(M, __ldcg(pg + (s2 * kXQ + q) * 66 + 64));
+    float pm[8], pl[8], pa[8];
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const bool on = s2 < S;
+      const float* base = pg + ((on ? s2 : 0) * kXQ + q) * 66;
+      pm[s2] = on ? __ldcg(base + 64) : -INFINITY;
+      pl[s2] = on ? __ldcg(base + 65) : 0.f;
+      pa[s2] = on ? __ldcg(base + e) : 0.f;
+    }
+    float M = pm[0];
+#pragma unroll
+    for (int s2 = 1; s2 < 8; ++s2) M = fmaxf(M, pm[s2]);
     float num = 0.f, den = 0.f;
-    for (int s2 = 0; s2 < S; ++s2) {
-      const float w = __expf(__ldcg(pg + (s2 * kXQ + q) * 66 + 64) - M);
-      num = fmaf(w, __ldcg(pg + (s2 * kXQ + q) * 66 + e), num);
-      den = fmaf(w, __ldcg(pg + (s2 * kXQ + q) * 66 + 65), den);
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) {
+      const float w = (s2 < S) ? __expf(pm[s2] - M) : 0.f;
+      num = fmaf(w, pa[s2], num);
+      den = fmaf(w, pl[s2], den);
     }
     a.out[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
   }
@@ -457,7 +506,8 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
 
 int cross_attn_smem_bytes(int T, int splits) {
   const int kmax = (T + splits - 1) / splits + 1;
-  return (kXQ * 64 + kXQ * kmax + 4 * kXQ * 64 + kXQ * 2) * (int)sizeof(float);
+  const int floats = kXQ * 64 + kXQ * kmax + 4 * kXQ * 64 + kXQ * 2;
+  return floats * (int)sizeof(float) + kmax * 64 * (int)sizeof(__half);
 }
 int cross_attn_qgroups(int rows_per_chunk) { return ceil_div(rows_per_chunk, kXQ); }
 size_t cross_attn_partial_floats(int B, int H, int rows_per_chunk, int splits) {

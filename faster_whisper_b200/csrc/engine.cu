@@ -326,6 +326,7 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   m->d_bind = dalloc<DecBindings>(1);
   decode_configure();
   search_configure();
+  gemm_configure();
   B2W_CUDA(cudaStreamSynchronize(m->stream));
 }
 
@@ -600,15 +601,56 @@ static void ensure_cross_kv(Model* m, Encoded* e) {
   }
 }
 
+constexpr int kTcMinRows = 17;  // rows above which the decode GEMMs go through the tcgen05 path (activations reused from smem)
+
+// decode GEMM through the tensor-core GEMM: the plan (TMA maps) is cached per (weights, activations, rows)
+static const GemmPlan& dec_plan(Model* m, const GvArgs& a) {
+  const auto key = std::make_tuple((const void*)a.W, (const void*)a.x, a.R, a.mode);
+  auto it = m->dec_plans.find(key);
+  if (it != m->dec_plans.end()) return it->second;
+  GemmArgs g;
+  g.A = a.x;
+  g.a_batch = 1;
+  g.a_rows = a.R;
+  g.a_cols = a.K;
+  g.a_row_stride = a.K;
+  g.k_per_tap = a.K;
+  g.W = a.W;
+  g.N = a.N;
+  g.rows = a.R;
+  g.bias = a.bias;
+  switch (a.mode) {
+    case GV_QKV:
+      g.epilogue = EPI_QKV_CACHE;
+      g.out = a.out_h;
+      g.rowinfo = reinterpret_cast<const int4*>(a.rows);
+      g.kcache = a.kcache;
+      g.vcache = a.vcache;
+      g.qkv_d = a.d;
+      g.n_ctx = a.n_ctx;
+      g.slots = a.slots;
+      break;
+    case GV_F16: g.epilogue = EPI_F16; g.out = a.out_h; g.out_ld = a.N; break;
+    case GV_GELU_F16: g.epilogue = EPI_GELU_F16; g.out = a.out_h; g.out_ld = a.N; break;
+    case GV_RESID_LN: g.epilogue = EPI_RESID_F32; g.out = a.xres; g.resid = a.xres; g.out_ld = a.N; break;
+    case GV_F32: g.epilogue = EPI_F32; g.out = a.out_f; g.out_ld = a.ldo; break;
+  }
+  return m->dec_plans.emplace(key, gemm_plan(g, m->num_sms)).first->second;
+}
+
 static void gv(Model* m, GvArgs a) {
   if (m->use_ref_gemv && (a.mode == GV_F32)) {
     skinny_ref(a.x, a.W, a.bias, a.out_f, a.R, a.N, a.K, m->stream);
     return;
   }
+  if (a.R >= kTcMinRows && a.K % 64 == 0 && a.N % 32 == 0 && !m->use_ref_gemv) {
+    gemm_run(dec_plan(m, a), m->stream);
+    if (a.mode == GV_RESID_LN) layernorm_f32_f16(a.xres, a.ln_g, a.ln_b, a.xn_out, a.R, a.N, m->stream);
+    return;
+  }
   skinny_gemm(a, m->stream);
 }
 
-// all decoder layers for R rows described by sb.rows / sb.tokens_in; leaves LN_final(x) in d_xn
 static void bind_encoded(Model* m, const Encoded* e, int chunk0) {
   m->h_bind = DecBindings{e ? e->xkv : nullptr, e ? e->B : 0, chunk0};
   B2W_CUDA(cudaMemcpyAsync(m->d_bind, &m->h_bind, sizeof(DecBindings), cudaMemcpyHostToDevice, m->stream));
@@ -679,10 +721,9 @@ static void logits_gemm(Model* m, int R) {
 }
 
 static int pick_splits(const Model* m, int n_chunks, int rows_per_chunk) {
-  // enough CTAs to fill the SMs, but never fewer than ~180 keys per split
-  const int groups = n_chunks * m->cfg.n_text_head * cross_attn_qgroups(rows_per_chunk);
-  int s = ceil_div(2 * m->num_sms, groups);
-  return std::max(1, std::min(8, s));
+  // 8 key splits (~188 keys each): the V tile fits in shared memory next to the scores and even one chunk fills the SMs
+  (void)m; (void)n_chunks; (void)rows_per_chunk;
+  return 8;
 }
 
 // Forced decoding of tokens[chunk][i0..i1) for chunks [chunk0, chunk0+n): rows = n*(i1-i0) <= 80, slot 0.

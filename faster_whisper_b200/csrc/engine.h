@@ -35,6 +35,7 @@ enum Epilogue {
   EPI_GELU_POS_F32 = 3,  // out(f32) = gelu(acc + bias) + pos[row, n]
   EPI_F16_XKV = 4,       // cross-KV scatter: out[l][kv][b][h][t][64] (f16) = acc + bias
   EPI_F32 = 5,           // out(f32) = acc + bias
+  EPI_QKV_CACHE = 6,     // decoder fused QKV: q -> out(f16)[row][d]; k,v -> paged self-KV cache at (chunk,pos,slot) of the row
 };
 
 struct GemmArgs {
@@ -55,6 +56,10 @@ struct GemmArgs {
   const float* resid = nullptr;  // EPI_RESID_F32 (same indexing as out)
   const float* pos = nullptr;    // EPI_GELU_POS_F32: [rows][N]
   int xkv_d = 0, xkv_heads = 0, xkv_T = 0, xkv_B = 0;  // EPI_F16_XKV
+  const int4* rowinfo = nullptr;  // EPI_QKV_CACHE: (chunk, slot, pos, -) per row
+  __half* kcache = nullptr;
+  __half* vcache = nullptr;
+  int qkv_d = 0, n_ctx = 0, slots = 0;
   int epilogue = EPI_F16;
 };
 
@@ -67,6 +72,7 @@ struct GemmPlan {
 };
 GemmPlan gemm_plan(const GemmArgs& a, int num_sms);
 void gemm_run(const GemmPlan& p, cudaStream_t stream);
+void gemm_configure();  // per-device kernel attributes; call once per device outside stream capture
 void gemm_ref_run(const GemmArgs& a, cudaStream_t stream);  // plain SIMT reference of the same contract
 
 // ---- encoder attention on tcgen05 (attention.cu) ---------------------------------------------------------

@@ -28,6 +28,10 @@ struct GemmDev {
   const float* resid;
   const float* pos;
   int xkv_d, xkv_heads, xkv_T, xkv_B;
+  const int4* rowinfo;
+  __half* kcache;
+  __half* vcache;
+  int qkv_d, n_ctx, slots;
 };
 
 template <int EPI>
@@ -53,6 +57,21 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row,
   if constexpr (EPI == EPI_F16 || EPI == EPI_GELU_F16) {
     __half* o = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_batch_stride + (long long)row * p.out_ld + n0;
     uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o4[i] = make_uint4(pack_half2(v[8 * i], v[8 * i + 1]), pack_half2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_half2(v[8 * i + 4], v[8 * i + 5]), pack_half2(v[8 * i + 6], v[8 * i + 7]));
+  } else if constexpr (EPI == EPI_QKV_CACHE) {
+    const int d = p.qkv_d;
+    __half* dst;
+    if (n0 < d) {
+      dst = reinterpret_cast<__half*>(p.out) + (long long)row * d + n0;
+    } else {
+      const int4 ri = __ldg(p.rowinfo + row);  // (chunk, slot, pos, -)
+      const int which = n0 >= 2 * d ? 1 : 0;
+      dst = (which ? p.vcache : p.kcache) + (((long long)ri.x * p.n_ctx + ri.z) * p.slots + ri.y) * d + (n0 - d - which * d);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       o4[i] = make_uint4(pack_half2(v[8 * i], v[8 * i + 1]), pack_half2(v[8 * i + 2], v[8 * i + 3]),
@@ -260,14 +279,27 @@ GemmPlan gemm_plan(const GemmArgs& a, int num_sms) {
 
 template <int BN, int EPI>
 static void launch_tc(const GemmPlan& pl, const GemmDev& d, cudaStream_t stream) {
-  static bool configured = false;
-  const int smem = gemm_smem_bytes<BN>();
-  if (!configured) {
-    B2W_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  gemm_tc_kernel<BN, EPI><<<pl.grid, kGemmThreads, smem, stream>>>(pl.tmA, pl.tmB, d);
+  gemm_tc_kernel<BN, EPI><<<pl.grid, kGemmThreads, gemm_smem_bytes<BN>(), stream>>>(pl.tmA, pl.tmB, d);
   B2W_LAUNCHED();
+}
+
+template <int BN, int EPI>
+static void configure_one() {
+  B2W_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<BN>()));
+}
+template <int BN>
+static void configure_bn() {
+  configure_one<BN, EPI_F16>();
+  configure_one<BN, EPI_GELU_F16>();
+  configure_one<BN, EPI_RESID_F32>();
+  configure_one<BN, EPI_GELU_POS_F32>();
+  configure_one<BN, EPI_F16_XKV>();
+  configure_one<BN, EPI_F32>();
+  configure_one<BN, EPI_QKV_CACHE>();
+}
+void gemm_configure() {
+  configure_bn<128>();
+  configure_bn<256>();
 }
 
 template <int BN>
@@ -279,6 +311,7 @@ static void dispatch_epi(const GemmPlan& pl, const GemmDev& d, cudaStream_t s) {
     case EPI_GELU_POS_F32: launch_tc<BN, EPI_GELU_POS_F32>(pl, d, s); break;
     case EPI_F16_XKV: launch_tc<BN, EPI_F16_XKV>(pl, d, s); break;
     case EPI_F32: launch_tc<BN, EPI_F32>(pl, d, s); break;
+    case EPI_QKV_CACHE: launch_tc<BN, EPI_QKV_CACHE>(pl, d, s); break;
     default: throw Error("unknown GEMM epilogue");
   }
 }
@@ -306,6 +339,12 @@ static GemmDev make_dev(const GemmArgs& a, int tiles_m, int tiles_n, int num_kb)
   d.xkv_heads = a.xkv_heads;
   d.xkv_T = a.xkv_T;
   d.xkv_B = a.xkv_B;
+  d.rowinfo = a.rowinfo;
+  d.kcache = a.kcache;
+  d.vcache = a.vcache;
+  d.qkv_d = a.qkv_d;
+  d.n_ctx = a.n_ctx;
+  d.slots = a.slots;
   return d;
 }
 
@@ -347,6 +386,15 @@ __global__ void gemm_ref_kernel(const __half* __restrict__ A, int a_rows, int a_
     const int l = n / two_d, rem = n - l * two_d, kv = rem / p.xkv_d, c = rem - kv * p.xkv_d;
     long long o = ((((long long)(l * 2 + kv) * p.xkv_B + b) * p.xkv_heads + (c >> 6)) * p.xkv_T + row) * 64 + (c & 63);
     reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(acc);
+  } else if (epi == EPI_QKV_CACHE) {
+    const int d = p.qkv_d;
+    if (n < d) {
+      reinterpret_cast<__half*>(p.out)[(long long)row * d + n] = __float2half_rn(acc);
+    } else {
+      const int4 ri = p.rowinfo[row];
+      const int which = n >= 2 * d ? 1 : 0;
+      (which ? p.vcache : p.kcache)[(((long long)ri.x * p.n_ctx + ri.z) * p.slots + ri.y) * d + (n - d - which * d)] = __float2half_rn(acc);
+    }
   } else if (epi == EPI_RESID_F32) {
     reinterpret_cast<float*>(p.out)[idx] = p.resid[idx] + acc;
   } else if (epi == EPI_GELU_POS_F32) {

@@ -4,6 +4,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -84,6 +85,7 @@ struct Model {
   MelChunkDesc* e_chunks = nullptr;
   int* e_chunk_max = nullptr;
   std::map<int, EncPlan> enc_plans;
+  std::map<std::tuple<const void*, const void*, int, int>, GemmPlan> dec_plans;
 
   // decoder workspace
   int dw_rows = 0;

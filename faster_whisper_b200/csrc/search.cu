@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
   const SearchParams p = *bf.params;
   extern __shared__ float s[];  // [vpad]
   __shared__ float red[32];
-  __shared__ ArgMax wbest[32];
+  __shared__ float wl_v[32 * kMaxCand];
+  __shared__ int wl_i[32 * kMaxCand];
   __shared__ int sh_flags[4];
   const int r = blockIdx.x, tid = threadIdx.x;
   const int b = r / p.K, k = r % p.K;
@@ -98,8 +99,40 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
     if (tid == 0) bf.no_speech[b] = __expf(row[p.no_speech] - mx) / sm;
   }
 
-  // ---- load + static suppression ----
-  for (int v = tid; v < V; v += kRowThreads) s[v] = bf.suppress[v] ? B2W_LOWEST : row[v];
+  // ---- load + static suppression: 16-byte loads, all of a thread's loads in flight before the first store ----
+  {
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const uchar4* sup4 = reinterpret_cast<const uchar4*>(bf.suppress);
+    float4* s4 = reinterpret_cast<float4*>(s);
+    const int n4 = p.vpad >> 2;
+    float4 t[13];
+    uchar4 m[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      const int idx = tid + i * kRowThreads;
+      if (idx < n4) {
+        t[i] = __ldcs(row4 + idx);
+        m[i] = __ldg(sup4 + idx);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      const int idx = tid + i * kRowThreads;
+      if (idx < n4) {
+        float4 v = t[i];
+        if (m[i].x) v.x = B2W_LOWEST;
+        if (m[i].y) v.y = B2W_LOWEST;
+        if (m[i].z) v.z = B2W_LOWEST;
+        if (m[i].w) v.w = B2W_LOWEST;
+        s4[idx] = v;
+      }
+    }
+    for (int idx = tid + 13 * kRowThreads; idx < n4; idx += kRowThreads) {  // vocabularies above 53 248 (none today)
+      float4 v = row4[idx];
+      const uchar4 mm = sup4[idx];
+      s4[idx] = make_float4(mm.x ? B2W_LOWEST : v.x, mm.y ? B2W_LOWEST : v.y, mm.z ? B2W_LOWEST : v.z, mm.w ? B2W_LOWEST : v.w);
+    }
+  }
   __syncthreads();
   // repetition penalty on the raw value of every distinct generated token
   if (p.repetition_penalty != 1.0f) {
@@ -224,34 +257,47 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
     s[v] = x;
   }
   __syncthreads();
+  // ---- row top-ncand: every warp extracts the top-ncand of its own 1/32 slice with shuffles only, then warp 0
+  //      merges the 32 sorted lists (ties -> lower token id, as a stable top-k would) ----
+  const int ncand = p.ncand;
+  const int warp = tid >> 5, lane = tid & 31;
   ArgMax mine{-INFINITY, 0x7fffffff};
   for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
-  const int ncand = p.ncand;
+  if (mine.v == -INFINITY) mine.i = 0x7fffffff;
   for (int c = 0; c < ncand; ++c) {
-    ArgMax w = warp_argmax(mine);
-    if ((tid & 31) == 0) wbest[tid >> 5] = w;
-    __syncthreads();
-    ArgMax best = wbest[0];
-    for (int i = 1; i < kRowThreads / 32; ++i) best = better(best, wbest[i]);
-    if (tid == 0) {
-      float sc;
-      if (sampling) {
-        // score of a draw: tempered log-prob (what CTranslate2's RandomSampler gathers)
-        sc = (best.v == -INFINITY) ? B2W_LOWEST : (best.v - gumbel_u32(p.seed, r, step, best.i));
-      } else {
-        sc = best.v;
-      }
-      bf.cand_score[(long long)r * kMaxCand + c] = (p.mode == 0) ? cum + sc : sc;
-      bf.cand_tok[(long long)r * kMaxCand + c] = best.i;
+    const ArgMax w = warp_argmax(mine);
+    if (lane == 0) {
+      wl_v[warp * kMaxCand + c] = w.v;
+      wl_i[warp * kMaxCand + c] = w.i;
     }
-    if (best.i != 0x7fffffff && (best.i % kRowThreads) == tid) {
-      s[best.i] = -INFINITY;
+    if (w.i != 0x7fffffff && (w.i % kRowThreads) == tid) {
+      s[w.i] = -INFINITY;  // only this thread ever reads or writes this element again
       mine = ArgMax{-INFINITY, 0x7fffffff};
       for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
-      // entries already taken are -inf with a real index; never prefer them over the sentinel
       if (mine.v == -INFINITY) mine.i = 0x7fffffff;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int head = 0;  // lane l walks warp l's sorted list
+    for (int c = 0; c < ncand; ++c) {
+      ArgMax cur{-INFINITY, 0x7fffffff};
+      if (head < ncand) cur = ArgMax{wl_v[lane * kMaxCand + head], wl_i[lane * kMaxCand + head]};
+      if (cur.v == -INFINITY) cur.i = 0x7fffffff;
+      const ArgMax best = warp_argmax(cur);
+      if (best.i != 0x7fffffff && cur.i == best.i) ++head;
+      if (lane == 0) {
+        float sc;
+        if (sampling) {
+          // score of a draw: tempered log-prob (what CTranslate2's RandomSampler gathers)
+          sc = (best.i == 0x7fffffff) ? B2W_LOWEST : (best.v - gumbel_u32(p.seed, r, step, best.i));
+        } else {
+          sc = best.v;
+        }
+        bf.cand_score[(long long)r * kMaxCand + c] = (p.mode == 0) ? cum + sc : sc;
+        bf.cand_tok[(long long)r * kMaxCand + c] = (best.i == 0x7fffffff) ? 0 : best.i;
+      }
+    }
   }
 }
 
@@ -261,7 +307,7 @@ void search_configure() {
 
 void search_rows(const float* logits, int R, int vpad, const SearchBuffers& b, cudaStream_t s) {
   const int smem = vpad * (int)sizeof(float);
-  B2W_CHECK(smem <= 210 * 1024, "vocabulary too large for the in-shared-memory row search");
+  B2W_CHECK(smem <= 210 * 1024 && vpad % 4 == 0, "vocabulary too large for the in-shared-memory row search");
   search_rows_kernel<<<R, kRowThreads, smem, s>>>(logits, b);
   B2W_LAUNCHED();
 }
@@ -269,34 +315,46 @@ void search_rows(const float* logits, int R, int vpad, const SearchBuffers& b, c
 // ---- beam / greedy bookkeeping ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers bf) {
   const SearchParams p = *bf.params;
+  __shared__ float cs[kMaxBeam * kMaxCand];
+  __shared__ int ct[kMaxBeam * kMaxCand];
   __shared__ float c_score[kMaxCand];
   __shared__ int c_tok[kMaxCand], c_beam[kMaxCand];
   __shared__ int parent[kMaxBeam], newtok[kMaxBeam];
   __shared__ float newcum[kMaxBeam];
+  __shared__ int fin_src[kMaxBeam], fin_slot[kMaxBeam], fin_extra[kMaxBeam];  // hypotheses finishing at this step
+  __shared__ float fin_sc[kMaxBeam];
+  __shared__ int n_new_fin;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int K = p.K, V = p.n_vocab, n_ctx = bf.n_ctx;
+  const int K = p.K, V = p.n_vocab, n_ctx = bf.n_ctx, ncand = p.ncand;
   const int r0 = b * K;
   const int pos = bf.rows[r0].pos;
   const int step = pos - (p.prompt_len - 1);
   const int cur = pos & 1, nxt = cur ^ 1;
   const bool is_last = (step + 1 >= p.max_steps);
   const long long RB = (long long)p.B * K;
+  for (int i = tid; i < K * ncand; i += blockDim.x) {
+    const int k = i / ncand, c = i - k * ncand;
+    cs[k * kMaxCand + c] = bf.cand_score[(long long)(r0 + k) * kMaxCand + c];
+    ct[k * kMaxCand + c] = bf.cand_tok[(long long)(r0 + k) * kMaxCand + c];
+  }
+  __syncthreads();
 
   if (tid == 0) {
     const bool chunk_done = bf.done[b] != 0;
+    int nf = 0;
     if (p.mode == 0) {
       // ---- merge rows' sorted candidate lists (step 0: only the first row is live) ----
       const int nrows = (step == 0) ? 1 : K;
       int head[kMaxBeam];
       for (int i = 0; i < nrows; ++i) head[i] = 0;
-      for (int c = 0; c < p.ncand; ++c) {
+      for (int c = 0; c < ncand; ++c) {
         int bi = -1;
         float bs = 0.f;
         long long bflat = 0;
         for (int i = 0; i < nrows; ++i) {
-          if (head[i] >= p.ncand) continue;
-          const float sc = bf.cand_score[(long long)(r0 + i) * kMaxCand + head[i]];
-          const long long flat = (long long)i * V + bf.cand_tok[(long long)(r0 + i) * kMaxCand + head[i]];
+          if (head[i] >= ncand) continue;
+          const float sc = cs[i * kMaxCand + head[i]];
+          const long long flat = (long long)i * V + ct[i * kMaxCand + head[i]];
           if (bi < 0 || sc > bs || (sc == bs && flat < bflat)) {
             bi = i;
             bs = sc;
@@ -305,30 +363,27 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers 
         }
         c_score[c] = bs;
         c_beam[c] = bi;
-        c_tok[c] = bf.cand_tok[(long long)(r0 + bi) * kMaxCand + head[bi]];
+        c_tok[c] = ct[bi * kMaxCand + head[bi]];
         head[bi]++;
       }
       // ---- CTranslate2 beam step: finished hypotheses are replaced by secondary candidates ----
       int secondary = K;
       bool top_finished = false;
       int nfin = bf.fin_count[b];
-      const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
       for (int k = 0; k < K; ++k) {
         int nx = k;
         const int t = c_tok[k];
         if ((t == p.eot || is_last) && !chunk_done) {
           if (k == 0) top_finished = true;
           if (nfin < kMaxFinished) {
-            const int* src = hist_cur + (long long)(r0 + c_beam[k]) * n_ctx;
-            int* dst = bf.fin_tok + ((long long)b * kMaxFinished + nfin) * n_ctx;
-            for (int i = 0; i < step; ++i) dst[i] = src[i];
-            int len = step;
-            if (t != p.eot) dst[len++] = t;
-            bf.fin_len[b * kMaxFinished + nfin] = len;
-            bf.fin_score[b * kMaxFinished + nfin] = c_score[k];
+            fin_src[nf] = c_beam[k];
+            fin_slot[nf] = nfin;
+            fin_extra[nf] = (t != p.eot) ? t : -1;
+            fin_sc[nf] = c_score[k];
+            ++nf;
             ++nfin;
           }
-          for (int j = secondary; j < p.ncand; ++j)
+          for (int j = secondary; j < ncand; ++j)
             if (c_tok[j] != p.eot) {
               nx = j;
               secondary = j + 1;
@@ -356,11 +411,10 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers 
     } else {
       // ---- greedy / sampling: rows are independent hypotheses; fin slot k belongs to row k ----
       int ndone_rows = 0;
-      const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
       for (int k = 0; k < K; ++k) {
         const int r = r0 + k;
-        const int t = bf.cand_tok[(long long)r * kMaxCand];
-        const float sc = bf.cand_score[(long long)r * kMaxCand];
+        const int t = ct[k * kMaxCand];
+        const float sc = cs[k * kMaxCand];
         parent[k] = k;
         newtok[k] = t;
         const bool row_done = bf.fin_len[b * kMaxFinished + k] >= 0;
@@ -368,13 +422,11 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers 
         if (!row_done) {
           cumv += sc;
           if (t == p.eot || is_last) {
-            const int* src = hist_cur + (long long)r * n_ctx;
-            int* dst = bf.fin_tok + ((long long)b * kMaxFinished + k) * n_ctx;
-            for (int i = 0; i < step; ++i) dst[i] = src[i];
-            int len = step;
-            if (t != p.eot) dst[len++] = t;
-            bf.fin_len[b * kMaxFinished + k] = len;
-            bf.fin_score[b * kMaxFinished + k] = cumv;
+            fin_src[nf] = k;
+            fin_slot[nf] = k;
+            fin_extra[nf] = (t != p.eot) ? t : -1;
+            fin_sc[nf] = cumv;
+            ++nf;
             ++ndone_rows;
           }
         } else {
@@ -388,10 +440,23 @@ __global__ void __launch_bounds__(128) search_update_kernel(const SearchBuffers 
         atomicAdd(&bf.state->n_done, 1);
       }
     }
+    n_new_fin = nf;
   }
   __syncthreads();
-  // ---- re-link history and KV ancestry into the other buffer, append the new token ----
   const int* hist_cur = bf.hist + (long long)cur * RB * n_ctx;
+  // ---- store the hypotheses that finished at this step ----
+  for (int f = 0; f < n_new_fin; ++f) {
+    const int* src = hist_cur + (long long)(r0 + fin_src[f]) * n_ctx;
+    int* dst = bf.fin_tok + ((long long)b * kMaxFinished + fin_slot[f]) * n_ctx;
+    for (int i = tid; i < step; i += blockDim.x) dst[i] = src[i];
+    if (tid == 0) {
+      int len = step;
+      if (fin_extra[f] >= 0) dst[len++] = fin_extra[f];
+      bf.fin_len[b * kMaxFinished + fin_slot[f]] = len;
+      bf.fin_score[b * kMaxFinished + fin_slot[f]] = fin_sc[f];
+    }
+  }
+  // ---- re-link history and KV ancestry into the other buffer, append the new token ----
   int* hist_nxt = bf.hist + (long long)nxt * RB * n_ctx;
   const uint8_t* anc_cur = bf.anc + (long long)cur * RB * n_ctx;
   uint8_t* anc_nxt = bf.anc + (long long)nxt * RB * n_ctx;
