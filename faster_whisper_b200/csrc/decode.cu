@@ -35,7 +35,7 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {  // weights: read o
 }
 
 constexpr int kGvWarps = 8;
-constexpr int kGvPF = 4;  // weight chunks in flight per warp (x2 with the double buffer)
+constexpr int kGvPF = 5;  // weight chunks in flight per warp (x2 with the double buffer): K = 1280 is one round trip
 
 // LayerNorm of all active rows by one CTA (called by the last CTA of a residual-producing GEMM).
 // One warp per row, the whole row in registers: every L2 load is issued before the first use.
@@ -367,30 +367,33 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
   float* wred = sc + kXQ * kmax;      // [4][kXQ][64]
   float* stat = wred + 4 * kXQ * 64;  // [kXQ][2]
   __half* vt = reinterpret_cast<__half*>(stat + kXQ * 2);  // [kmax][64] V tile; float offset 512 + 8*kmax + 2048 + 16 is a multiple of 4 -> 16-byte aligned
+  __half* kt = vt + kmax * 64;                             // [kmax][72] K tile, rows padded to 144 B: conflict-free 16-byte reads by one thread per key
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d;
   const DecBindings bd = *a.bind;
   const long long per = (long long)bd.B_total * a.H * T * 64;  // one layer's K (or V) block
   const __half* Kb = bd.xkv + ((long long)a.layer * 2 + 0) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
   const __half* Vb = bd.xkv + ((long long)a.layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
-  // V tile -> shared memory, asynchronously: its HBM latency hides behind the score phase
+  // K and V tiles -> shared memory with fully coalesced 16-byte async copies (every byte of the beam-shared
+  // cross-KV cache crosses HBM once per chunk and step); V's latency hides behind the score phase
+  for (int i = tid; i < nk * 8; i += kXThreads) cp_async16(kt + (i >> 3) * 72 + (i & 7) * 8, Kb + (long long)k0 * 64 + i * 8);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < nk * 8; i += kXThreads) cp_async16(vt + i * 8, Vb + (long long)k0 * 64 + i * 8);
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < kXQ * 64; i += kXThreads) {
     const int q = i >> 6, e = i & 63;
     qs[i] = (q < nq) ? __half2float(a.q[(long long)(row0 + q) * d + h * 64 + e]) * 0.125f : 0.f;
   }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
   __syncthreads();
-  // phase 1: scores, one key per thread (8 x 16-byte loads in flight per thread)
+  // phase 1: scores, one key per thread
   for (int j = tid; j < nk; j += kXThreads) {
-    const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)(k0 + j) * 64);
-    uint4 kr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) kr[i] = ldg_stream(kp + i);
+    const uint4* kp = reinterpret_cast<const uint4*>(kt + j * 72);
     float kf[64];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const __half2* k2 = reinterpret_cast<const __half2*>(&kr[i]);
+      const uint4 kr = kp[i];
+      const __half2* k2 = reinterpret_cast<const __half2*>(&kr);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __half22float2(k2[e]);
@@ -507,7 +510,7 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
 int cross_attn_smem_bytes(int T, int splits) {
   const int kmax = (T + splits - 1) / splits + 1;
   const int floats = kXQ * 64 + kXQ * kmax + 4 * kXQ * 64 + kXQ * 2;
-  return floats * (int)sizeof(float) + kmax * 64 * (int)sizeof(__half);
+  return floats * (int)sizeof(float) + kmax * (64 + 72) * (int)sizeof(__half);
 }
 int cross_attn_qgroups(int rows_per_chunk) { return ceil_div(rows_per_chunk, kXQ); }
 size_t cross_attn_partial_floats(int B, int H, int rows_per_chunk, int splits) {

@@ -62,6 +62,7 @@ Model::~Model() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
   for (void* p : allocs) cudaFree(p);
+  for (auto& it : pool) cudaFree(it.second);
   void* ws[] = {e_feats, e_x0, e_x1, e_x, e_xn, e_qkv, e_ao, e_h, e_pcm, e_chunks, e_chunk_max, kcache, vcache, d_x, d_xn,
                 d_q, d_ao, d_h, d_logits, d_xpart, d_counters, d_suppress, sb_blob, d_bind};
   for (void* p : ws)
@@ -75,10 +76,40 @@ Model::~Model() {
   if (stream) cudaStreamDestroy(stream);
 }
 
+void* Model::pool_get(size_t bytes) {
+  for (size_t i = 0; i < pool.size(); ++i)
+    if (pool[i].first == bytes) {
+      void* p = pool[i].second;
+      pool_bytes -= bytes;
+      pool.erase(pool.begin() + i);
+      return p;
+    }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 1));
+  if (e != cudaSuccess) {  // release the cache and retry once
+    cudaGetLastError();
+    for (auto& it : pool) cudaFree(it.second);
+    pool.clear();
+    pool_bytes = 0;
+    B2W_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 1)));
+  }
+  return p;
+}
+void Model::pool_put(void* p, size_t bytes) {
+  if (!p) return;
+  if (pool_bytes + bytes > (size_t)24 << 30 || pool.size() >= 16) {
+    cudaFree(p);
+    return;
+  }
+  pool.emplace_back(bytes, p);
+  pool_bytes += bytes;
+}
+
 Encoded::~Encoded() {
-  if (owner) cudaSetDevice(owner->device);
-  if (enc_out) cudaFree(enc_out);
-  if (xkv) cudaFree(xkv);
+  if (!owner) return;
+  cudaSetDevice(owner->device);
+  owner->pool_put(enc_out, enc_bytes);
+  owner->pool_put(xkv, xkv_bytes);
 }
 
 // ---- timing -----------------------------------------------------------------------------------------------------
@@ -470,7 +501,8 @@ static Encoded* encode_features(Model* m, const float* feats_host, const float* 
   e->owner = m;
   e->B = B;
   const size_t d = m->cfg.n_audio_state;
-  e->enc_out = dalloc<__half>((size_t)B * 1500 * d);
+  e->enc_bytes = (size_t)B * 1500 * d * sizeof(__half);
+  e->enc_out = reinterpret_cast<__half*>(m->pool_get(e->enc_bytes));
   const size_t per = (size_t)m->cfg.n_mels * 3000;
   for (int b0 = 0; b0 < B; b0 += kEncSub) {
     const int b = std::min(kEncSub, B - b0);
@@ -572,9 +604,10 @@ static void ensure_search_ws(Model* m, int B, int K) {
 
 static void ensure_cross_kv(Model* m, Encoded* e) {
   if (e->xkv) return;
-  ScopedStage st(m, B2W_T_CROSSKV);
   const int d = m->cfg.n_audio_state, dt = m->cfg.n_text_state, L = m->cfg.n_text_layer, H = m->cfg.n_text_head;
-  e->xkv = dalloc<__half>((size_t)L * 2 * e->B * 1500 * dt);
+  e->xkv_bytes = (size_t)L * 2 * e->B * 1500 * dt * sizeof(__half);
+  e->xkv = reinterpret_cast<__half*>(m->pool_get(e->xkv_bytes));
+  ScopedStage st(m, B2W_T_CROSSKV);
   GemmArgs a;
   a.A = e->enc_out;
   a.a_batch = e->B;
@@ -1130,7 +1163,8 @@ int b2w_encode_audio(b2w_model* h, const float* const* pcm, const int64_t* n_sam
     std::unique_ptr<Encoded> e(new Encoded);
     e->owner = m;
     e->B = batch;
-    e->enc_out = dalloc<__half>((size_t)batch * 1500 * d);
+    e->enc_bytes = (size_t)batch * 1500 * d * sizeof(__half);
+    e->enc_out = reinterpret_cast<__half*>(m->pool_get(e->enc_bytes));
     for (int b0 = 0; b0 < batch; b0 += kEncSub) {
       const int b = std::min(kEncSub, batch - b0);
       ensure_encoder_ws(m, std::min(kEncSub, (int)batch));

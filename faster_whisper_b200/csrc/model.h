@@ -41,6 +41,7 @@ struct Model;
 struct Encoded {
   Model* owner = nullptr;
   int B = 0;
+  size_t enc_bytes = 0, xkv_bytes = 0;
   __half* enc_out = nullptr;  // [B][1500][d] fp16
   __half* xkv = nullptr;      // lazily: [L][2][B][H][T][64] fp16
   ~Encoded();
@@ -55,6 +56,11 @@ struct Model {
   cudaStream_t stream = nullptr;
   std::mutex mu;
   std::vector<void*> allocs;  // weights
+  // size-keyed free list for encoder outputs / cross-KV caches: a 3.9 GB cudaMalloc+cudaFree per call costs ~100s of ms
+  std::vector<std::pair<size_t, void*>> pool;
+  size_t pool_bytes = 0;
+  void* pool_get(size_t bytes);
+  void pool_put(void* p, size_t bytes);
 
   // encoder weights
   __half *conv1_w = nullptr, *conv2_w = nullptr;
