@@ -64,7 +64,7 @@ Model::~Model() {
   for (void* p : allocs) cudaFree(p);
   for (auto& it : pool) cudaFree(it.second);
   void* ws[] = {e_feats, e_x0, e_x1, e_x, e_xn, e_qkv, e_ao, e_h, e_pcm, e_chunks, e_chunk_max, kcache, vcache, d_x, d_xn,
-                d_q, d_ao, d_h, d_logits, d_xpart, d_counters, d_suppress, sb_blob, d_bind};
+                d_q, d_ao, d_h, d_logits, d_xpart, d_counters, d_suppress, sb_blob, d_bind, d_layers, d_bar};
   for (void* p : ws)
     if (p) cudaFree(p);
   if (h_pinned) cudaFreeHost(h_pinned);
@@ -358,6 +358,19 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   decode_configure();
   search_configure();
   gemm_configure();
+  dstep_configure();
+  {
+    std::vector<DLayer> hl(L);
+    for (int i = 0; i < L; ++i) {
+      const DecLayerW& D = m->dec[i];
+      hl[i] = DLayer{D.wqkv, D.wo, D.wq_x, D.wo_x, D.w1, D.w2, D.bqkv, D.bo, D.bq_x, D.bo_x, D.b1, D.b2,
+                     D.ln1_g, D.ln1_b, D.ln2_g, D.ln2_b, D.ln3_g, D.ln3_b};
+    }
+    m->d_layers = dalloc<DLayer>(L);
+    B2W_CUDA(cudaMemcpy(m->d_layers, hl.data(), L * sizeof(DLayer), cudaMemcpyHostToDevice));
+    m->d_bar = dalloc<unsigned>(4);
+    B2W_CUDA(cudaMemset(m->d_bar, 0, 4 * sizeof(unsigned)));
+  }
   B2W_CUDA(cudaStreamSynchronize(m->stream));
 }
 
@@ -881,6 +894,28 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     B2W_CUDA(cudaStreamSynchronize(s));
   }
   const int splits = pick_splits(m, n, K);
+  // persistent single-kernel step for <= 8 rows
+  DStepArgs ds{};
+  bool use_dstep = m->use_dstep && !sp.fake_logits && R <= 8 && !m->use_ref_gemv && c.n_text_layer <= 32;
+  if (use_dstep) {
+    ds.layers = m->d_layers; ds.L = c.n_text_layer; ds.tok_emb = m->tok_emb; ds.pos_emb = m->dec_pos;
+    ds.lnf_g = m->dec_ln_g; ds.lnf_b = m->dec_ln_b;
+    ds.R = R; ds.d = c.n_text_state; ds.H = c.n_text_head; ds.n_ctx = c.n_text_ctx; ds.slots = K; ds.T = 1500;
+    ds.vpad = m->vpad; ds.n_vocab = c.n_vocab; ds.n_chunks = n; ds.rows_per_chunk = K;
+    ds.xsplits = std::max(1, std::min(8, m->num_sms / (c.n_text_head * n)));
+    ds.rows = sb.rows; ds.tokens_in = sb.tokens_in;
+    ds.x = m->d_x; ds.q = m->d_q; ds.ao = m->d_ao; ds.h = m->d_h; ds.logits = m->d_logits;
+    ds.kcache = m->kcache; ds.vcache = m->vcache; ds.kv_layer_stride = (long long)m->kv_elems;
+    ds.anc = sb.anc; ds.anc_buf_stride = (long long)n * K * c.n_text_ctx;
+    ds.bind = m->d_bind; ds.xpart = m->d_xpart; ds.xcounters = m->d_counters + 64; ds.bar = m->d_bar;
+    ds.prof = m->d_prof;
+    if (m->dstep_grid == 0) {
+      const size_t smem = dstep_smem_bytes(ds, nullptr);
+      m->dstep_grid = dstep_max_grid(m->num_sms, smem);
+      if (m->dstep_grid == 0) m->dstep_grid = -1;
+    }
+    if (m->dstep_grid <= 0) use_dstep = false;
+  }
   m->h_params = sp;
   B2W_CUDA(cudaMemcpyAsync(const_cast<SearchParams*>(sb.params), &m->h_params, sizeof(SearchParams), cudaMemcpyHostToDevice, s));
   bind_encoded(m, e, chunk0);
@@ -888,8 +923,12 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     if (sp.fake_logits) {
       fake_logits(m->d_logits, R, sb, s);
     } else {
-      decoder_layers(m, n, K, K, splits, P - 1);
-      logits_gemm(m, R);
+      if (use_dstep) {
+        dstep_launch(ds, m->dstep_grid, s);
+      } else {
+        decoder_layers(m, n, K, K, splits, P - 1);
+        logits_gemm(m, R);
+      }
     }
     search_rows(m->d_logits, R, m->vpad, sb, s);
     search_update(n, sb, s);
@@ -903,7 +942,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, 0, 0, 0};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : 0, 0, 0};
     memcpy(k, misc, sizeof misc);
   }
   if (sp.fake_logits == 0) {
@@ -965,6 +1004,38 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       }
     }
     m->decode_steps += steps_run;
+    if (m->d_prof && use_dstep) {
+      B2W_CUDA(cudaStreamSynchronize(s));
+      const int L = c.n_text_layer, nstamps = 1 + 2 * (1 + 8 * L) + 1;
+      std::vector<unsigned long long> t(nstamps);
+      B2W_CUDA(cudaMemcpy(t.data(), m->d_prof, nstamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      // stamps: [0]=start, then (arrive, release) per barrier, then end.  work(p) = arrive_p - release_{p-1}; wait(p) = release_p - arrive_p
+      static const char* names[8] = {"qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "ffn2"};
+      double work[8] = {0}, wait[8] = {0};
+      unsigned long long prev = t[2];  // release of the embed barrier
+      for (int l = 0; l < L; ++l)
+        for (int ph = 0; ph < 8; ++ph) {
+          const int bi = 1 + 2 * (1 + l * 8 + ph);
+          work[ph] += double(t[bi] - prev);
+          wait[ph] += double(t[bi + 1] - t[bi]);
+          prev = t[bi + 1];
+        }
+      fprintf(stderr, "[dstep prof] last step: total %.1f us; embed %.1f us; logits %.1f us\n", (t[nstamps - 1] - t[0]) / 1e3,
+              (t[2] - t[0]) / 1e3, (t[nstamps - 1] - prev) / 1e3);
+      {
+        std::vector<unsigned long long> f(96);
+        B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, 96 * sizeof(unsigned long long)));
+        for (int k = 0; k < 10; ++k)
+          if (f[k * 8 + 4])
+            fprintf(stderr, "[dstep prof]   gemv mode %d K%s: stage %.0f  tile-wait %.0f  mma+reduce %.0f  epilogue %.0f cycles (first item, mean of %llu)\n", k / 2,
+                    (k & 1) ? ">2048" : "<=2048", double(f[k * 8]) / f[k * 8 + 4], double(f[k * 8 + 1]) / f[k * 8 + 4],
+                    double(f[k * 8 + 2]) / f[k * 8 + 4], double(f[k * 8 + 3]) / f[k * 8 + 4], f[k * 8 + 4]);
+      }
+      for (int ph = 0; ph < 8; ++ph)
+        fprintf(stderr, "[dstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
+                wait[ph] / L / 1e3, L);
+    }
   }
 
   // ---- collect hypotheses ----
@@ -1073,6 +1144,13 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     if (const char* v = getenv("B2W_ATTN_IMPL")) m->use_ref_attn = !strcmp(v, "ref");
     if (const char* v = getenv("B2W_GEMV_IMPL")) m->use_ref_gemv = !strcmp(v, "ref");
     if (const char* v = getenv("B2W_GRAPH")) m->use_graph = strcmp(v, "0") != 0;
+    if (const char* v = getenv("B2W_DSTEP")) m->use_dstep = strcmp(v, "0") != 0;
+    if (const char* v = getenv("B2W_DSTEP_PROF")) {
+      if (strcmp(v, "0") != 0) {
+        m->d_prof = dalloc<unsigned long long>(4096);
+        B2W_CUDA(cudaMemset(m->d_prof, 0, 4096 * sizeof(unsigned long long)));
+      }
+    }
     TensorTable tt{tensors, n_tensors};
     build_model(m, *cfg, tt);
     *out = h.release();

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "decode.h"
+#include "dstep.h"
 #include "engine.h"
 
 namespace b2w {
@@ -106,6 +107,11 @@ struct Model {
   int* d_counters = nullptr;  // [0]: GEMM ticket, [64..]: cross-attention groups
   uint8_t* d_suppress = nullptr;
   DecBindings* d_bind = nullptr;
+  DLayer* d_layers = nullptr;   // device copy of the decoder layer pointer table (persistent step kernel)
+  unsigned* d_bar = nullptr;
+  unsigned long long* d_prof = nullptr;  // B2W_DSTEP_PROF=1: per-phase timestamps of the persistent step kernel
+  int dstep_grid = 0;
+  bool use_dstep = true;
   DecBindings h_bind{};
   SearchParams h_params{};
   // search buffers
