@@ -70,7 +70,11 @@ __device__ void cta_layernorm_rows(const float* x, const float* g, const float* 
     for (int i = 0; i < 10; ++i) {
       const int idx = lane + 32 * i;
       if (idx < n4) {
-        const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+        float4 gg = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g) {  // decoder LayerNorm affines are folded into the consuming weights at load time (engine.cu:fold_ln)
+          gg = __ldg(g4 + idx);
+          bb = __ldg(b4 + idx);
+        }
         o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y),
                             pack_half2((v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w));
       }
@@ -263,7 +267,7 @@ __global__ void embed_ln_kernel(const int* __restrict__ tokens, const RowInfo* _
   cnt = 0;
   for (int i = threadIdx.x; i < d; i += blockDim.x, ++cnt) {
     x[(long long)r * d + i] = v[cnt];
-    xn[(long long)r * d + i] = __float2half_rn((v[cnt] - mean) * rstd * g[i] + b[i]);
+    xn[(long long)r * d + i] = __float2half_rn(g ? (v[cnt] - mean) * rstd * g[i] + b[i] : (v[cnt] - mean) * rstd);
   }
 }
 

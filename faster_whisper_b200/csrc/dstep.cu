@@ -31,6 +31,8 @@ namespace b2w {
 constexpr int kDsThreads = 256;
 constexpr int kDsWarps = 8;
 constexpr int kDsXQ = 8;
+constexpr int kDsNBuf = 3;      // weight-tile ring: the tile being consumed + two in flight
+constexpr int kDsSelfKeys = 224;  // keys staged per self-attention pass
 
 __device__ __forceinline__ void ds_mma(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -40,6 +42,13 @@ __device__ __forceinline__ void ds_mma(float* c, uint32_t a0, uint32_t a1, uint3
 }
 __device__ __forceinline__ void ds_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier.  Unlike cp.async (LDGSTS), whose issue stalls once
+// the SM's miss queue is full (measured: ~4400 cycles to issue one 40 KB tile), the issuing thread returns immediately.
+__device__ __forceinline__ void ds_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void ds_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ds_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -55,6 +64,16 @@ __device__ __forceinline__ unsigned long long ds_globaltimer() {
   return t;
 }
 
+// fine-grained cycle accounting for CTA 0 (B2W_DSTEP_PROF): slot = 3000 + kind*16 + point
+#define DS_TICK(a, kind, point, tprev)                                                      \
+  do {                                                                                      \
+    if ((a).prof && blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+      const long long _now = clock64();                                                     \
+      (a).prof[3000 + (kind) * 16 + (point)] += (unsigned long long)(_now - (tprev));       \
+      (tprev) = _now;                                                                       \
+    }                                                                                       \
+  } while (0)
+
 // per-CTA state that lives in shared memory (pointers/tables are never re-fetched from L2 inside the layer loop)
 struct DsShared {
   DLayer lay[32];
@@ -63,20 +82,28 @@ struct DsShared {
   int prof_i;
   int flag;
   // weight pipeline: the next item to issue (sequence index, item index, buffer) and the buffer to consume next
-  int p_s, p_item, p_buf, c_buf;
+  int p_s, p_item, p_buf, c_buf, ahead;  // ahead = tiles issued and not yet consumed
+  int consumed;    // tiles consumed so far (buffer = consumed % kDsNBuf, mbarrier parity = (consumed / kDsNBuf) & 1)
+  int x_parity;    // parity of the input-staging mbarrier
+  uint64_t wbar[kDsNBuf];
+  uint64_t xbar;
 };
 
 // Grid barrier: every CTA arrives once; sh.epoch is the running arrival target (host zeroes *bar before the launch).
 // Arrive = red.release (orders the CTA's earlier writes, cumulative through bar.sync); wait = relaxed polling.  No acquire
 // fence on purpose: it would invalidate the SM's L1 (CCTL.IVALL) and with it the stack, and every read of data produced by
 // other CTAs in this kernel already bypasses L1 (ld.global.cg / cp.async.cg / atomics).
-__device__ __noinline__ void ds_grid_barrier(const DStepArgs& a, DsShared& sh) {
+__device__ __forceinline__ void ds_barrier_arrive(const DStepArgs& a, DsShared& sh) {
   __syncthreads();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
-    const unsigned target = sh.epoch;
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();  // arrival of CTA 0
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+  }
+}
+__device__ __forceinline__ void ds_barrier_wait(const DStepArgs& a, DsShared& sh) {
+  if (threadIdx.x == 0) {
+    const unsigned target = sh.epoch;
     unsigned v;
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
@@ -95,26 +122,25 @@ struct GemvDesc {
   const __half* W;
   const float* bias;
   int N, K, ksplit, mode;
-  const float* ln_g;   // LayerNorm(x) input when non-null, else the fp16 activation `src16`
-  const float* ln_b;
+  int ln;              // input = normalised x (LayerNorm affine is folded into W/bias at load) when set, else `src16`
   const __half* src16;
 };
 
 __device__ __forceinline__ GemvDesc ds_desc(const DStepArgs& a, const DsShared& sh, int s) {
   GemvDesc g;
   const int d = a.d;
-  g.bias = nullptr; g.ln_g = nullptr; g.ln_b = nullptr; g.src16 = nullptr; g.ksplit = 1; g.K = d; g.N = d;
+  g.bias = nullptr; g.ln = 0; g.src16 = nullptr; g.ksplit = 1; g.K = d; g.N = d;
   if (s >= 6 * a.L) {
-    g.W = a.tok_emb; g.N = a.vpad; g.mode = DS_F32; g.ln_g = a.lnf_g; g.ln_b = a.lnf_b;
+    g.W = a.logit_w; g.bias = a.logit_b; g.N = a.vpad; g.mode = DS_F32; g.ln = 1;
     return g;
   }
   const DLayer& W = sh.lay[s / 6];
   switch (s % 6) {
-    case 0: g.W = W.wqkv; g.bias = W.bqkv; g.N = 3 * d; g.mode = DS_QKV; g.ln_g = W.ln1_g; g.ln_b = W.ln1_b; break;
+    case 0: g.W = W.wqkv; g.bias = W.bqkv; g.N = 3 * d; g.mode = DS_QKV; g.ln = 1; break;
     case 1: g.W = W.wo; g.bias = W.bo; g.mode = DS_RESID; g.src16 = a.ao; break;
-    case 2: g.W = W.wq_x; g.bias = W.bq_x; g.mode = DS_F16; g.ln_g = W.ln2_g; g.ln_b = W.ln2_b; break;
+    case 2: g.W = W.wq_x; g.bias = W.bq_x; g.mode = DS_F16; g.ln = 1; break;
     case 3: g.W = W.wo_x; g.bias = W.bo_x; g.mode = DS_RESID; g.src16 = a.ao; break;
-    case 4: g.W = W.w1; g.bias = W.b1; g.N = 4 * d; g.mode = DS_GELU; g.ln_g = W.ln3_g; g.ln_b = W.ln3_b; break;
+    case 4: g.W = W.w1; g.bias = W.b1; g.N = 4 * d; g.mode = DS_GELU; g.ln = 1; break;
     default: g.W = W.w2; g.bias = W.b2; g.K = 4 * d; g.ksplit = 4; g.mode = DS_RESID; g.src16 = a.h; break;
   }
   return g;
@@ -124,6 +150,7 @@ __device__ __forceinline__ GemvDesc ds_desc(const DStepArgs& a, const DsShared& 
 // Buffers: [16 rows][kr + 32 halves] + 16 floats  (row stride kr*2 + 64 bytes -> conflict-free 16-byte fragment reads)
 __device__ __noinline__ bool ds_issue_next(const DStepArgs& a, DsShared& sh, __half* wbuf, int wbuf_halves) {
   const int last = 6 * a.L;
+  long long tq = clock64();
   int s = sh.p_s, item = sh.p_item;
   const int buf = sh.p_buf;
   GemvDesc g;
@@ -137,115 +164,94 @@ __device__ __noinline__ bool ds_issue_next(const DStepArgs& a, DsShared& sh, __h
   const int kr = g.K / g.ksplit, tl = item / g.ksplit, ks = item - tl * g.ksplit;
   const __half* src = g.W + (long long)tl * 16 * g.K + ks * kr;
   __half* dst = wbuf + (long long)buf * wbuf_halves;
-  const int per_row = kr >> 3, ld = kr + 32;
-#pragma unroll 1
-  for (int r = 0; r < 16; ++r)
-    for (int c = threadIdx.x; c < per_row; c += kDsThreads) ds_cp_async16(dst + r * ld + c * 8, src + (long long)r * g.K + c * 8);
-  if (g.bias && ks == 0 && threadIdx.x < 4) ds_cp_async16(dst + 16 * ld + threadIdx.x * 8, g.bias + tl * 16 + threadIdx.x * 4);
-  ds_cp_commit();
+  const int ld = kr + 32;
+  if (threadIdx.x < 32) {  // warp 0: one bulk copy per weight row (+ the item's 16 bias values)
+    const bool with_bias = g.bias && ks == 0;
+    DS_TICK(a, 7, 0, tq);
+    if (threadIdx.x == 0) {
+      fence_proxy_async();  // the buffer was last read through the generic proxy
+      DS_TICK(a, 7, 1, tq);
+      mbar_expect_tx(&sh.wbar[buf], 16u * (uint32_t)kr * 2u + (with_bias ? 64u : 0u));
+      DS_TICK(a, 7, 2, tq);
+    }
+    __syncwarp();
+    if (threadIdx.x < 16) ds_bulk_g2s(dst + threadIdx.x * ld, src + (long long)threadIdx.x * g.K, (uint32_t)kr * 2u, &sh.wbar[buf]);
+    if (threadIdx.x == 16 && with_bias) ds_bulk_g2s(dst + 16 * ld, g.bias + tl * 16, 64u, &sh.wbar[buf]);
+    DS_TICK(a, 7, 3, tq);
+  }
   __syncthreads();  // every thread has read p_* before thread 0 advances them
+  DS_TICK(a, 7, 4, tq);
   if (threadIdx.x == 0) {
     sh.p_s = s;
     sh.p_item = item + gridDim.x;
-    sh.p_buf = buf ^ 1;
+    sh.p_buf = (buf + 1 == kDsNBuf) ? 0 : buf + 1;
+    sh.ahead += 1;
   }
   __syncthreads();
+  DS_TICK(a, 7, 5, tq);
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[3000 + 7 * 16 + 15] += 1;
   return true;
 }
 
-// GEMV input -> xs [8][K + 32] halves (row stride K*2 + 64 bytes).  LayerNorm inputs go through an fp32 staging area
-// (raw rows + gamma + beta fetched with one batch of async copies), fp16 activations are copied straight in.
-__device__ __noinline__ void ds_stage_input(const DStepArgs& a, const float* ln_g, const float* ln_b, const __half* src16, int K, __half* xs,
-                                            float* stage32) {
+// keep the ring full (called between a barrier's arrive and wait, and after every consumed tile)
+__device__ __noinline__ void ds_fill_pipeline(const DStepArgs& a, DsShared& sh, __half* wbuf, int wbuf_halves) {
+  while (sh.ahead < kDsNBuf) {
+    if (!ds_issue_next(a, sh, wbuf, wbuf_halves)) break;
+  }
+}
+
+// GEMV input -> xs [8][K + 32] halves (row stride K*2 + 64 bytes).  Rows arrive by TMA bulk copies (one per row) on an
+// mbarrier; LayerNorm inputs land as fp32 in a staging area and are normalised one warp per row in a single pass
+// (sum and sum of squares from registers); fp16 activations are copied straight into xs.
+__device__ __noinline__ void ds_stage_input(const DStepArgs& a, DsShared& sh, int ln, const __half* src16, int K, __half* xs, float* stage32,
+                                            int kind) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = K + 32;
-  if (ln_g) {
-    const int n16 = K >> 2;  // 16-byte pieces per fp32 row
-    float* gam = stage32 + 8 * K;
-    float* bet = gam + K;
-#pragma unroll 1
-    for (int r = 0; r < a.R; ++r)
-      for (int c = threadIdx.x; c < n16; c += kDsThreads) ds_cp_async16(stage32 + r * K + c * 4, a.x + (long long)r * K + c * 4);
-    for (int c = threadIdx.x; c < n16; c += kDsThreads) {
-      ds_cp_async16(gam + c * 4, ln_g + c * 4);
-      ds_cp_async16(bet + c * 4, ln_b + c * 4);
+  long long tp = clock64();
+  if (warp == 0) {
+    const uint32_t row_bytes = ln ? (uint32_t)K * 4u : (uint32_t)K * 2u;
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&sh.xbar, row_bytes * (uint32_t)a.R);
     }
-    ds_cp_commit();
-    ds_cp_wait_all();
-    __syncthreads();
-    // All 8 warps work on all rows: thread t owns float4 columns t and t+256 of every row (K <= 2048), single-pass
-    // statistics (sum, sum of squares), one cross-warp exchange, then normalise from registers.
+    __syncwarp();
+    if (lane < a.R) {
+      if (ln)
+        ds_bulk_g2s(stage32 + lane * K, a.x + (long long)lane * K, row_bytes, &sh.xbar);
+      else
+        ds_bulk_g2s(xs + lane * ld, src16 + (long long)lane * K, row_bytes, &sh.xbar);
+    }
+  }
+  DS_TICK(a, kind, 0, tp);  // copies issued
+  mbar_wait(&sh.xbar, (uint32_t)sh.x_parity);
+  DS_TICK(a, kind, 1, tp);  // input landed
+  if (ln && warp < a.R) {
+    const float4* xr = reinterpret_cast<const float4*>(stage32 + warp * K);
     const int n4 = K >> 2;
-    float* part = bet + K;  // [8 warps][8 rows][2]
-    float4 v[8][2];
-    float su[8], sq[8];
+    float4 v[10];
+    float su = 0.f, sq = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      su[r] = 0.f;
-      sq[r] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int idx = threadIdx.x + k * kDsThreads;
-        v[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < a.R && idx < n4) v[r][k] = reinterpret_cast<const float4*>(stage32 + r * K)[idx];
-        su[r] += v[r][k].x + v[r][k].y + v[r][k].z + v[r][k].w;
-        sq[r] += v[r][k].x * v[r][k].x + v[r][k].y * v[r][k].y + v[r][k].z * v[r][k].z + v[r][k].w * v[r][k].w;
-      }
+    for (int i = 0; i < 10; ++i) {
+      const int idx = lane + 32 * i;
+      v[i] = idx < n4 ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      su += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
+    su = warp_sum(su);
+    sq = warp_sum(sq);
+    const float mean = su / K;
+    const float rstd = rsqrtf(fmaxf(sq / K - mean * mean, 0.f) + 1e-5f);
+    uint2* o = reinterpret_cast<uint2*>(xs + warp * ld);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      su[r] = warp_sum(su[r]);
-      sq[r] = warp_sum(sq[r]);
+    for (int i = 0; i < 10; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < n4)
+        o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd, (v[i].y - mean) * rstd), pack_half2((v[i].z - mean) * rstd, (v[i].w - mean) * rstd));
     }
-    if (lane < 8) {
-      float s_l = 0.f, q_l = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (lane == r) {
-          s_l = su[r];
-          q_l = sq[r];
-        }
-      part[(warp * 8 + lane) * 2] = s_l;
-      part[(warp * 8 + lane) * 2 + 1] = q_l;
-    }
-    __syncthreads();
-    float mean[8], rstd[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float s_t = 0.f, q_t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kDsWarps; ++w) {
-        const float2 p2 = *reinterpret_cast<const float2*>(part + (w * 8 + r) * 2);
-        s_t += p2.x;
-        q_t += p2.y;
-      }
-      mean[r] = s_t / K;
-      rstd[r] = rsqrtf(fmaxf(q_t / K - mean[r] * mean[r], 0.f) + 1e-5f);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int idx = threadIdx.x + k * kDsThreads;
-      if (idx < n4) {
-        const float4 gg = reinterpret_cast<const float4*>(gam)[idx], bb = reinterpret_cast<const float4*>(bet)[idx];
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-          if (r < a.R) {
-            const float4 x4 = v[r][k];
-            *reinterpret_cast<uint2*>(xs + r * ld + idx * 4) =
-                make_uint2(pack_half2((x4.x - mean[r]) * rstd[r] * gg.x + bb.x, (x4.y - mean[r]) * rstd[r] * gg.y + bb.y),
-                           pack_half2((x4.z - mean[r]) * rstd[r] * gg.z + bb.z, (x4.w - mean[r]) * rstd[r] * gg.w + bb.w));
-          }
-      }
-    }
-  } else {
-    const int n16 = K >> 3;
-#pragma unroll 1
-    for (int r = 0; r < a.R; ++r)
-      for (int c = threadIdx.x; c < n16; c += kDsThreads) ds_cp_async16(xs + r * ld + c * 8, src16 + (long long)r * K + c * 8);
-    ds_cp_commit();
-    ds_cp_wait_all();
   }
   __syncthreads();
+  if (threadIdx.x == 0) sh.x_parity ^= 1;
+  DS_TICK(a, kind, 2, tp);  // normalised / copied input ready
 }
 
 // One GEMV phase: y[R,N] = in[R,K] W[N,K]^T for this CTA's items, weights consumed from the shared-memory pipeline.
@@ -259,18 +265,18 @@ __device__ __noinline__ void ds_gemv_phase(const DStepArgs& a, DsShared& sh, int
   const int ldx = K + 32, ldw = kr + 32;
   int item = blockIdx.x;
   if (item >= nitems) return;
-  ds_stage_input(a, gd.ln_g, gd.ln_b, gd.src16, K, xs, stage32);
+  const int kind = s >= 6 * a.L ? 6 : s % 6;
+  ds_stage_input(a, sh, gd.ln, gd.src16, K, xs, stage32, kind);
+  long long tp = clock64();
+  bool first = true;
 #pragma unroll 1
   for (; item < nitems; item += gridDim.x) {
     const int tl = item / ksplit, ks = item - tl * ksplit;
     const int n0 = tl * 16, kbase = ks * kr;
     const int cbuf = sh.c_buf;
-    // keep the pipeline one item ahead, then wait for this item's tile
-    if (ds_issue_next(a, sh, wbuf, wbuf_halves))
-      ds_cp_wait_1();
-    else
-      ds_cp_wait_all();
-    __syncthreads();
+    // this item's tile was issued earlier (possibly phases ago); wait for its mbarrier
+    mbar_wait(&sh.wbar[cbuf], (uint32_t)((sh.consumed / kDsNBuf) & 1));
+    if (first) DS_TICK(a, kind, 3, tp);  // weight tile landed
     const __half* wt = wbuf + (long long)cbuf * wbuf_halves;
     const __half* w_lo = wt + g * ldw + 8 * t;
     const __half* w_hi = w_lo + 8 * ldw;
@@ -290,6 +296,7 @@ __device__ __noinline__ void ds_gemv_phase(const DStepArgs& a, DsShared& sh, int
     my[(g + 8) * 8 + 2 * t] = acc[2];
     my[(g + 8) * 8 + 2 * t + 1] = acc[3];
     __syncthreads();
+    if (first) DS_TICK(a, kind, 4, tp);  // MMAs + partials stored
     if (threadIdx.x < 128) {
       const int ch = threadIdx.x & 15, r = threadIdx.x >> 4;
       if (r < a.R) {
@@ -318,78 +325,103 @@ __device__ __noinline__ void ds_gemv_phase(const DStepArgs& a, DsShared& sh, int
         }
       }
     }
-    if (threadIdx.x == 0) sh.c_buf = cbuf ^ 1;
+    if (threadIdx.x == 0) {
+      sh.c_buf = (cbuf + 1 == kDsNBuf) ? 0 : cbuf + 1;
+      sh.ahead -= 1;
+      sh.consumed += 1;
+    }
     __syncthreads();
+    if (first) DS_TICK(a, kind, 5, tp);  // epilogue
+    ds_fill_pipeline(a, sh, wbuf, wbuf_halves);
+    if (first) {
+      DS_TICK(a, kind, 6, tp);  // ring topped up
+      if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[3000 + kind * 16 + 15] += 1;
+    }
+    first = false;
   }
 }
 
 // masked self-attention for one (head, row) task: the row's K/V history is gathered through the ancestry table into
-// shared memory with async copies (one L2/HBM round trip), then scored from there
+// shared memory with async copies (one L2/HBM round trip per pass of kDsSelfKeys keys), then scored from there with an
+// online softmax across passes
 __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShared& sh, int h, int r, const __half* kc, const __half* vc, float* sm) {
-  float* sc = sm;                      // [n_ctx]
-  float* red = sm + B2W_MAX_TEXT_CTX;  // [16]
+  float* sc = sm;                      // [kDsSelfKeys]
+  float* red = sm + kDsSelfKeys;       // [16]
   float* oacc = red + 16;              // [4][64]
   float* qf = oacc + 256;              // [64]
-  __half* kt = reinterpret_cast<__half*>(qf + 64);  // [nk][72]  (offset 784 floats: 16-byte aligned)
+  __half* kt = reinterpret_cast<__half*>(qf + 64);  // [kDsSelfKeys][72]  (offset 560 floats: 16-byte aligned)
+  __half* vt = kt + kDsSelfKeys * 72;               // [kDsSelfKeys][64]
   const RowInfo ri = sh.rows[r];
   const int d = a.d, nk = ri.pos + 1, tid = threadIdx.x;
-  __half* vt = kt + (long long)a.n_ctx * 72;        // [nk][64]
   const uint8_t* anc = a.anc + (ri.pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * a.n_ctx;
-#pragma unroll 1
-  for (int j = tid; j < nk; j += kDsThreads) {
-    const int slot = (j == ri.pos) ? ri.slot : anc[j];
-    const long long off = (((long long)ri.chunk * a.n_ctx + j) * a.slots + slot) * d + h * 64;
-#pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-      ds_cp_async16(kt + j * 72 + i * 8, kc + off + i * 8);
-      ds_cp_async16(vt + j * 64 + i * 8, vc + off + i * 8);
-    }
-  }
-  ds_cp_commit();
   if (tid < 64) qf[tid] = __half2float(__ldcg(a.q + (long long)r * d + h * 64 + tid)) * 0.125f;
-  ds_cp_wait_all();
-  __syncthreads();
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int j = tid; j < nk; j += kDsThreads) {
-    const __half2* kp = reinterpret_cast<const __half2*>(kt + j * 72);
-    float s = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-      const float2 kf = __half22float2(kp[i]);
-      s = fmaf(kf.x, qf[2 * i], s);
-      s = fmaf(kf.y, qf[2 * i + 1], s);
-    }
-    sc[j] = s;
-    mx = fmaxf(mx, s);
-  }
-  mx = warp_max(mx);
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
-  __syncthreads();
-  mx = red[0];
-#pragma unroll
-  for (int i = 1; i < kDsWarps; ++i) mx = fmaxf(mx, red[i]);
-  float sum = 0.f;
-#pragma unroll 1
-  for (int j = tid; j < nk; j += kDsThreads) {
-    const float p = __expf(sc[j] - mx);
-    sc[j] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  __syncthreads();
-  if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
-  __syncthreads();
-  sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < kDsWarps; ++i) sum += red[8 + i];
   const int e = tid & 63, part = tid >> 6;
-  float acc = 0.f;
+  float m_run = -INFINITY, l_run = 0.f, acc = 0.f;
+#pragma unroll 1
+  for (int base = 0; base < nk; base += kDsSelfKeys) {
+    const int n = min(kDsSelfKeys, nk - base);
+    if (tid < n) {
+      const int j = base + tid;
+      const int slot = (j == ri.pos) ? ri.slot : anc[j];
+      const long long off = (((long long)ri.chunk * a.n_ctx + j) * a.slots + slot) * d + h * 64;
 #pragma unroll 2
-  for (int j = part; j < nk; j += 4) acc = fmaf(sc[j], __half2float(vt[j * 64 + e]), acc);
+      for (int i = 0; i < 8; ++i) {
+        ds_cp_async16(kt + tid * 72 + i * 8, kc + off + i * 8);
+        ds_cp_async16(vt + tid * 64 + i * 8, vc + off + i * 8);
+      }
+    }
+    ds_cp_commit();
+    ds_cp_wait_all();
+    __syncthreads();
+    float mx = -INFINITY;
+    if (tid < n) {
+      const __half2* kp = reinterpret_cast<const __half2*>(kt + tid * 72);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < 32; i += 2) {
+        const float2 k0 = __half22float2(kp[i]), k1 = __half22float2(kp[i + 1]);
+        s0 = fmaf(k0.x, qf[2 * i], fmaf(k0.y, qf[2 * i + 1], s0));
+        s1 = fmaf(k1.x, qf[2 * i + 2], fmaf(k1.y, qf[2 * i + 3], s1));
+      }
+      mx = s0 + s1;
+      sc[tid] = mx;
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < kDsWarps; ++i) mx = fmaxf(mx, red[i]);
+    const float m_new = fmaxf(m_run, mx);
+    float sum = 0.f;
+    if (tid < n) {
+      const float p = __expf(sc[tid] - m_new);
+      sc[tid] = p;
+      sum = p;
+    }
+    sum = warp_sum(sum);
+    if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kDsWarps; ++i) sum += red[8 + i];
+    const float alpha = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+    float a0 = 0.f, a1 = 0.f;
+    int j = part;  // this thread's keys: part, part + 4, ...; two independent chains
+#pragma unroll 2
+    for (; j + 4 < n; j += 8) {
+      a0 = fmaf(sc[j], __half2float(vt[j * 64 + e]), a0);
+      a1 = fmaf(sc[j + 4], __half2float(vt[(j + 4) * 64 + e]), a1);
+    }
+    if (j < n) a0 = fmaf(sc[j], __half2float(vt[j * 64 + e]), a0);
+    acc = fmaf(acc, alpha, a0 + a1);
+    l_run = fmaf(l_run, alpha, sum);
+    m_run = m_new;
+    __syncthreads();  // the staging buffers are reused by the next pass
+  }
   oacc[part * 64 + e] = acc;
   __syncthreads();
-  if (tid < 64) a.ao[(long long)r * d + h * 64 + tid] = __float2half_rn((oacc[tid] + oacc[64 + tid] + oacc[128 + tid] + oacc[192 + tid]) / sum);
+  if (tid < 64) a.ao[(long long)r * d + h * 64 + tid] = __float2half_rn((oacc[tid] + oacc[64 + tid] + oacc[128 + tid] + oacc[192 + tid]) / l_run);
   __syncthreads();
 }
 
@@ -540,10 +572,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
   if (threadIdx.x == 0) a_sh = a_param;
   __syncthreads();
   const DStepArgs& a = a_sh;
-  // [weight buffer 0][weight buffer 1][union: GEMV input xs (+ fp32 LayerNorm staging) | attention scratch][red]
+  // [weight ring: kDsNBuf buffers][union: GEMV input xs (+ fp32 LayerNorm staging) | attention scratch][red]
   const int wbuf_halves = 16 * (a.d + 32) + 32;  // 16 padded rows + 16 fp32 bias values
   __half* wbuf = reinterpret_cast<__half*>(ds_smem);
-  unsigned char* uni = ds_smem + 2 * (size_t)wbuf_halves * sizeof(__half);
+  unsigned char* uni = ds_smem + kDsNBuf * (size_t)wbuf_halves * sizeof(__half);
   __half* xs = reinterpret_cast<__half*>(uni);
   float* stage32 = reinterpret_cast<float*>(uni + (size_t)8 * (a.d + 32) * sizeof(__half));  // only used by LayerNorm inputs (K = d)
   float* att = reinterpret_cast<float*>(uni);
@@ -562,11 +594,17 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
       sh.p_item = blockIdx.x;
       sh.p_buf = 0;
       sh.c_buf = 0;
+      sh.ahead = 0;
+      sh.consumed = 0;
+      sh.x_parity = 0;
+      for (int i = 0; i < kDsNBuf; ++i) mbar_init(&sh.wbar[i], 1);
+      mbar_init(&sh.xbar, 1);
+      fence_mbar_init();
       if (a.prof && blockIdx.x == 0) a.prof[0] = ds_globaltimer();
     }
   }
   __syncthreads();
-  ds_issue_next(a, sh, wbuf, wbuf_halves);  // the first weight tile is in flight before anything else happens
+  ds_fill_pipeline(a, sh, wbuf, wbuf_halves);  // the first weight tiles are in flight before anything else happens
 
   // ---- embed: x = tok_emb[token] + pos_emb[pos] (CTA r owns row r) ----
   if ((int)blockIdx.x < a.R) {
@@ -578,7 +616,8 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
     for (int i = threadIdx.x; i < d; i += kDsThreads)
       __stcg(a.x + (long long)r * d + i, __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
   }
-  ds_grid_barrier(a, sh);
+  ds_barrier_arrive(a, sh);
+  ds_barrier_wait(a, sh);
 
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
@@ -600,7 +639,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
         const int j = ph == 0 ? 0 : (ph < 4 ? ph - 1 : ph - 2);
         ds_gemv_phase(a, sh, 6 * l + j, wbuf, wbuf_halves, xs, stage32, red, kc, vc);
       }
-      ds_grid_barrier(a, sh);
+      // arrive, then use the barrier latency to top up the weight ring, then wait
+      ds_barrier_arrive(a, sh);
+      ds_fill_pipeline(a, sh, wbuf, wbuf_halves);
+      ds_barrier_wait(a, sh);
     }
   }
   // ---- logits = LN_f(x) E^T ----
@@ -609,12 +651,12 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
 }
 
 size_t dstep_smem_bytes(const DStepArgs& a, size_t* xs_bytes) {
-  const size_t wbufs = 2 * ((size_t)16 * (a.d + 32) + 32) * sizeof(__half);
+  const size_t wbufs = kDsNBuf * ((size_t)16 * (a.d + 32) + 32) * sizeof(__half);
   const size_t xs_ffn2 = (size_t)8 * (4 * a.d + 32) * sizeof(__half);
-  const size_t xs_ln = (size_t)8 * (a.d + 32) * sizeof(__half) + ((size_t)10 * a.d + 128) * sizeof(float);  // fp16 rows + fp32 rows, gamma, beta
+  const size_t xs_ln = (size_t)8 * (a.d + 32) * sizeof(__half) + (size_t)8 * a.d * sizeof(float);  // fp16 rows + fp32 rows, gamma, beta
   const int kmax = (a.T + a.xsplits - 1) / a.xsplits + 1;
   const size_t xat = (size_t)(kDsXQ * 64 + kDsXQ * kmax + kDsWarps * kDsXQ * 64 + kDsXQ * 2) * sizeof(float) + (size_t)kmax * (64 + 72) * sizeof(__half);
-  const size_t sat = (size_t)(B2W_MAX_TEXT_CTX + 16 + 256 + 64) * sizeof(float) + (size_t)a.n_ctx * (72 + 64) * sizeof(__half);
+  const size_t sat = (size_t)(kDsSelfKeys + 16 + 256 + 64) * sizeof(float) + (size_t)kDsSelfKeys * (72 + 64) * sizeof(__half);
   size_t region = xs_ffn2;
   if (xs_ln > region) region = xs_ln;
   if (xat > region) region = xat;

@@ -14,6 +14,8 @@ struct DStepArgs {
   const DLayer* layers;  // device array [L]
   int L;
   const __half* tok_emb;
+  const __half* logit_w;
+  const float* logit_b;
   const float* pos_emb;
   const float* lnf_g;
   const float* lnf_b;

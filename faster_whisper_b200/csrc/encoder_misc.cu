@@ -42,7 +42,11 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   for (int i = 0; i < 10; ++i) {
     const int idx = lane + 32 * i;
     if (idx < n4) {
-      const float4 gg = __ldg(g4 + idx), bb = __ldg(b4 + idx);
+      float4 gg = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g) {
+        gg = __ldg(g4 + idx);
+        bb = __ldg(b4 + idx);
+      }
       const float a = (v[i].x - mean) * rstd * gg.x + bb.x, b = (v[i].y - mean) * rstd * gg.y + bb.y;
       const float c = (v[i].z - mean) * rstd * gg.z + bb.z, e = (v[i].w - mean) * rstd * gg.w + bb.w;
       if constexpr (sizeof(OutT) == 2) {

@@ -212,6 +212,19 @@ struct Uploader {
     }
     B2W_CUDA(cudaStreamSynchronize(m->stream));
   }
+  void vec_to_f16(const std::vector<float>& v, __half* dst) {
+    b2w_tensor t{};
+    t.name = "folded";
+    t.data = v.data();
+    t.dtype = B2W_F32;
+    t.ndim = 1;
+    t.shape[0] = (int64_t)v.size();
+    to_f16(t, dst);
+  }
+  void vec_to_f32(const std::vector<float>& v, float* dst) {
+    B2W_CUDA(cudaMemcpyAsync(dst, v.data(), v.size() * 4, cudaMemcpyHostToDevice, m->stream));
+    B2W_CUDA(cudaStreamSynchronize(m->stream));
+  }
   template <typename T>
   T* alloc(size_t n, bool zero = false) {
     T* p = dalloc<T>(n);
@@ -234,6 +247,33 @@ struct Uploader {
     return p;
   }
 };
+
+static std::vector<float> host_f32(const b2w_tensor& t) {
+  const int64_t n = numel(t);
+  std::vector<float> v((size_t)n);
+  if (t.dtype == B2W_F32) {
+    memcpy(v.data(), t.data, (size_t)n * 4);
+  } else {
+    const __half* h = reinterpret_cast<const __half*>(t.data);
+    for (int64_t i = 0; i < n; ++i) v[(size_t)i] = __half2float(h[i]);
+  }
+  return v;
+}
+
+// LayerNorm affine folded into the consuming linear layer (exact algebra):
+//   LN(x) W^T + b = ((x - mu) rstd) (W diag(gamma))^T + (W beta + b)
+// so the decode kernels only normalise, and no gamma/beta fetch sits on the per-phase critical path.
+static void fold_ln(std::vector<float>& W, std::vector<float>& bias, int N, int K, const std::vector<float>& gamma, const std::vector<float>& beta) {
+  for (int n = 0; n < N; ++n) {
+    float* w = W.data() + (size_t)n * K;
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+      acc += (double)w[k] * beta[k];
+      w[k] *= gamma[k];
+    }
+    bias[n] += (float)acc;
+  }
+}
 
 static float host_value(const b2w_tensor& t, int64_t i) {
   if (t.dtype == B2W_F32) return reinterpret_cast<const float*>(t.data)[i];
@@ -318,15 +358,37 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   for (int i = 0; i < L; ++i) {
     const std::string p = "decoder.blocks." + std::to_string(i);
     DecLayerW& D = m->dec[i];
-    D.ln1_g = up.f32(tt, p + ".attn_ln.weight", {dt});
-    D.ln1_b = up.f32(tt, p + ".attn_ln.bias", {dt});
-    fused_qkv(p + ".attn", dt, D.wqkv, D.bqkv);
+    // LayerNorm affines are folded into the consuming projections (fold_ln); the kernels normalise only
+    D.ln1_g = D.ln1_b = D.ln2_g = D.ln2_b = D.ln3_g = D.ln3_b = nullptr;
+    {
+      const std::vector<float> g1 = host_f32(tt.get(p + ".attn_ln.weight")), b1 = host_f32(tt.get(p + ".attn_ln.bias"));
+      expect_shape(tt.get(p + ".attn_ln.weight"), {dt});
+      D.wqkv = up.alloc<__half>((size_t)3 * dt * dt);
+      D.bqkv = up.alloc<float>((size_t)3 * dt, true);
+      const char* parts[3] = {".query", ".key", ".value"};
+      for (int j = 0; j < 3; ++j) {
+        const b2w_tensor& tw = tt.get(p + ".attn" + parts[j] + ".weight");
+        expect_shape(tw, {dt, dt});
+        std::vector<float> W = host_f32(tw), bias((size_t)dt, 0.f);
+        if (const b2w_tensor* tb = tt.find(p + ".attn" + parts[j] + ".bias")) bias = host_f32(*tb);
+        fold_ln(W, bias, dt, dt, g1, b1);
+        up.vec_to_f16(W, D.wqkv + (size_t)j * dt * dt);
+        up.vec_to_f32(bias, D.bqkv + (size_t)j * dt);
+      }
+    }
     D.wo = up.f16(tt, p + ".attn.out.weight", {dt, dt});
     D.bo = up.f32(tt, p + ".attn.out.bias", {dt});
-    D.ln2_g = up.f32(tt, p + ".cross_attn_ln.weight", {dt});
-    D.ln2_b = up.f32(tt, p + ".cross_attn_ln.bias", {dt});
-    D.wq_x = up.f16(tt, p + ".cross_attn.query.weight", {dt, dt});
-    D.bq_x = up.f32(tt, p + ".cross_attn.query.bias", {dt});
+    {
+      const std::vector<float> g2 = host_f32(tt.get(p + ".cross_attn_ln.weight")), b2 = host_f32(tt.get(p + ".cross_attn_ln.bias"));
+      const b2w_tensor& tw = tt.get(p + ".cross_attn.query.weight");
+      expect_shape(tw, {dt, dt});
+      std::vector<float> W = host_f32(tw), bias = host_f32(tt.get(p + ".cross_attn.query.bias"));
+      fold_ln(W, bias, dt, dt, g2, b2);
+      D.wq_x = up.alloc<__half>((size_t)dt * dt);
+      D.bq_x = up.alloc<float>((size_t)dt);
+      up.vec_to_f16(W, D.wq_x);
+      up.vec_to_f32(bias, D.bq_x);
+    }
     {
       const b2w_tensor& tk = tt.get(p + ".cross_attn.key.weight");
       const b2w_tensor& tv = tt.get(p + ".cross_attn.value.weight");
@@ -338,16 +400,33 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
     }
     D.wo_x = up.f16(tt, p + ".cross_attn.out.weight", {dt, dt});
     D.bo_x = up.f32(tt, p + ".cross_attn.out.bias", {dt});
-    D.ln3_g = up.f32(tt, p + ".mlp_ln.weight", {dt});
-    D.ln3_b = up.f32(tt, p + ".mlp_ln.bias", {dt});
-    D.w1 = up.f16(tt, p + ".mlp.0.weight", {4 * dt, dt});
-    D.b1 = up.f32(tt, p + ".mlp.0.bias", {4 * dt});
+    {
+      const std::vector<float> g3 = host_f32(tt.get(p + ".mlp_ln.weight")), b3 = host_f32(tt.get(p + ".mlp_ln.bias"));
+      const b2w_tensor& tw = tt.get(p + ".mlp.0.weight");
+      expect_shape(tw, {4 * dt, dt});
+      std::vector<float> W = host_f32(tw), bias = host_f32(tt.get(p + ".mlp.0.bias"));
+      fold_ln(W, bias, 4 * dt, dt, g3, b3);
+      D.w1 = up.alloc<__half>((size_t)4 * dt * dt);
+      D.b1 = up.alloc<float>((size_t)4 * dt);
+      up.vec_to_f16(W, D.w1);
+      up.vec_to_f32(bias, D.b1);
+    }
     D.w2 = up.f16(tt, p + ".mlp.2.weight", {dt, 4 * dt});
     D.b2 = up.f32(tt, p + ".mlp.2.bias", {dt});
     wbytes += 2.0 * ((double)3 * dt * dt + (double)dt * dt * 3 + 8.0 * dt * dt);
   }
-  m->dec_ln_g = up.f32(tt, "decoder.ln.weight", {dt});
-  m->dec_ln_b = up.f32(tt, "decoder.ln.bias", {dt});
+  {
+    // logits = LN_f(x) E^T with the final LayerNorm folded: a gamma-scaled copy of the tied embedding + a per-token bias
+    const std::vector<float> gf = host_f32(tt.get("decoder.ln.weight")), bf = host_f32(tt.get("decoder.ln.bias"));
+    std::vector<float> E = host_f32(tt.get("decoder.token_embedding.weight")), lb((size_t)m->vpad, 0.f);
+    E.resize((size_t)m->vpad * dt, 0.f);
+    fold_ln(E, lb, m->vpad, dt, gf, bf);
+    m->logit_w = up.alloc<__half>((size_t)m->vpad * dt);
+    m->logit_b = up.alloc<float>((size_t)m->vpad);
+    up.vec_to_f16(E, m->logit_w);
+    up.vec_to_f32(lb, m->logit_b);
+    m->dec_ln_g = m->dec_ln_b = nullptr;
+  }
   m->dec_weight_bytes = wbytes;
   m->mel.reset(new MelPlan(cfg.n_mels));
   m->d_counters = dalloc<int>(64 + 16 * 20 * 64);
@@ -761,7 +840,7 @@ static void decoder_layers(Model* m, int n_chunks, int rows_per_chunk, int slots
 
 static void logits_gemm(Model* m, int R) {
   GvArgs a;
-  a.x = m->d_xn; a.W = m->tok_emb; a.bias = nullptr; a.R = R; a.N = m->vpad; a.K = m->cfg.n_text_state; a.mode = GV_F32;
+  a.x = m->d_xn; a.W = m->logit_w; a.bias = m->logit_b; a.R = R; a.N = m->vpad; a.K = m->cfg.n_text_state; a.mode = GV_F32;
   a.out_f = m->d_logits; a.ldo = m->vpad;
   gv(m, a);
 }
@@ -899,6 +978,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
   bool use_dstep = m->use_dstep && !sp.fake_logits && R <= 8 && !m->use_ref_gemv && c.n_text_layer <= 32;
   if (use_dstep) {
     ds.layers = m->d_layers; ds.L = c.n_text_layer; ds.tok_emb = m->tok_emb; ds.pos_emb = m->dec_pos;
+    ds.logit_w = m->logit_w; ds.logit_b = m->logit_b;
     ds.lnf_g = m->dec_ln_g; ds.lnf_b = m->dec_ln_b;
     ds.R = R; ds.d = c.n_text_state; ds.H = c.n_text_head; ds.n_ctx = c.n_text_ctx; ds.slots = K; ds.T = 1500;
     ds.vpad = m->vpad; ds.n_vocab = c.n_vocab; ds.n_chunks = n; ds.rows_per_chunk = K;
@@ -1023,14 +1103,21 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       fprintf(stderr, "[dstep prof] last step: total %.1f us; embed %.1f us; logits %.1f us\n", (t[nstamps - 1] - t[0]) / 1e3,
               (t[2] - t[0]) / 1e3, (t[nstamps - 1] - prev) / 1e3);
       {
-        std::vector<unsigned long long> f(96);
-        B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, 96 * sizeof(unsigned long long)));
-        for (int k = 0; k < 10; ++k)
-          if (f[k * 8 + 4])
-            fprintf(stderr, "[dstep prof]   gemv mode %d K%s: stage %.0f  tile-wait %.0f  mma+reduce %.0f  epilogue %.0f cycles (first item, mean of %llu)\n", k / 2,
-                    (k & 1) ? ">2048" : "<=2048", double(f[k * 8]) / f[k * 8 + 4], double(f[k * 8 + 1]) / f[k * 8 + 4],
-                    double(f[k * 8 + 2]) / f[k * 8 + 4], double(f[k * 8 + 3]) / f[k * 8 + 4], f[k * 8 + 4]);
+        std::vector<unsigned long long> f(8 * 16);
+        B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
+        static const char* kinds[7] = {"qkv", "out", "cross_q", "cross_out", "ffn1", "ffn2", "logits"};
+        for (int k = 0; k < 7; ++k) {
+          const double n = (double)f[k * 16 + 15];
+          if (n > 0)
+            fprintf(stderr, "[dstep prof]   %-9s cycles: issue-x %.0f  x-landed %.0f  LN/copy %.0f  tile-wait %.0f  mma %.0f  epilogue %.0f  refill %.0f\n",
+                    kinds[k], f[k * 16] / n, f[k * 16 + 1] / n, f[k * 16 + 2] / n, f[k * 16 + 3] / n, f[k * 16 + 4] / n, f[k * 16 + 5] / n, f[k * 16 + 6] / n);
+        }
+        if (f[7 * 16 + 15] > 0) {
+          const double n = (double)f[7 * 16 + 15];
+          fprintf(stderr, "[dstep prof]   issue_next cycles: find %.0f  fence %.0f  expect_tx %.0f  bulk %.0f  sync1 %.0f  sync2 %.0f (mean of %.0f)\n", f[112] / n,
+                  f[113] / n, f[114] / n, f[115] / n, f[116] / n, f[117] / n, n);
+        }
       }
       for (int ph = 0; ph < 8; ++ph)
         fprintf(stderr, "[dstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,

@@ -69,6 +69,8 @@ struct Model {
   std::vector<EncLayerW> enc;
   // decoder weights
   __half* tok_emb = nullptr;  // [vpad][d]
+  __half* logit_w = nullptr;  // [vpad][d]  tied embedding scaled by the final LayerNorm's gamma
+  float* logit_b = nullptr;   // [vpad]     E . beta_f
   float *dec_pos = nullptr, *dec_ln_g = nullptr, *dec_ln_b = nullptr;
   std::vector<DecLayerW> dec;
   __half* wxkv = nullptr;  // [L*2d][d]
