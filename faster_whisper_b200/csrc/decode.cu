@@ -380,9 +380,16 @@ __global__ void __launch_bounds__(kXThreads) dec_cross_attn_kernel(const CrossAt
   const __half* Vb = bd.xkv + ((long long)a.layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T) * 64;
   // K and V tiles -> shared memory with fully coalesced 16-byte async copies (every byte of the beam-shared
   // cross-KV cache crosses HBM once per chunk and step); V's latency hides behind the score phase
-  for (int i = tid; i < nk * 8; i += kXThreads) cp_async16(kt + (i >> 3) * 72 + (i & 7) * 8, Kb + (long long)k0 * 64 + i * 8);
+  // (the cache stores each 128-byte row with its 16-byte chunks at chunk ^ (t & 7), gemm.cu EPI_F16_XKV: undo it here)
+  for (int i = tid; i < nk * 8; i += kXThreads) {
+    const int key = k0 + (i >> 3);
+    cp_async16(kt + (i >> 3) * 72 + (i & 7) * 8, Kb + (long long)key * 64 + (((i & 7) ^ (key & 7)) << 3));
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = tid; i < nk * 8; i += kXThreads) cp_async16(vt + i * 8, Vb + (long long)k0 * 64 + i * 8);
+  for (int i = tid; i < nk * 8; i += kXThreads) {
+    const int key = k0 + (i >> 3);
+    cp_async16(vt + i * 8, Vb + (long long)key * 64 + (((i & 7) ^ (key & 7)) << 3));
+  }
   asm volatile("cp.async.commit_group;" ::: "memory");
   for (int i = tid; i < kXQ * 64; i += kXThreads) {
     const int q = i >> 6, e = i & 63;

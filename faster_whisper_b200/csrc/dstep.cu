@@ -3,19 +3,26 @@
 // With so few rows every sub-layer streams 3-13 MB of weights: as separate launches each costs 6-15 us, and a large-v3
 // step is 257 of them.  Here one CTA per SM stays resident for the whole step and walks the phases
 //   embed | L x { QKV, self-attn, out-proj, cross-q, cross-attn, cross-out, FFN1, FFN2 } | logits
-// separated by grid barriers.  Three things matter on B200 (measured, tools/bench/*.cu and profiles/r1_dstep_*.txt):
-//   * a dependent hop through L2 costs ~0.6 us and a grid barrier ~1.4 us, so a phase has a ~2.4 us floor: every load a
-//     phase needs that does not depend on the previous phase (weight tiles, biases, pointers) is issued earlier — the
-//     weight tile of the *next* work item, whichever phase it belongs to, is always in flight into the other shared-memory
-//     buffer (cp.async) while the CTA computes, waits at a barrier or runs an attention phase;
-//   * the instruction cache: the first version of this kernel was 105 KB of SASS and every phase ran at instruction-fetch
-//     speed (~10x slower than its arithmetic).  The per-layer loop is therefore written for code size: rolled loops,
-//     cp.async staging instead of register batches, out-of-line phase functions;
-//   * LayerNorms are recomputed by each consumer CTA from the fp32 residual stream instead of being phases of their own,
-//     and the residual adds are fire-and-forget fp32 reductions (no read-modify-write hop).
+// separated by grid barriers.  What shapes it (measured on B200: tools/bench/*.cu, profiles/r1_dstep_*.txt):
+//   * a dependent hop through L2 costs ~0.6 us and a grid barrier ~1.4 us, so a phase has a ~2.4 us floor.  Everything a
+//     phase needs that does not depend on the previous phase is therefore fetched ahead of time: the weights are stored as
+//     a stream of per-work-item tiles (dstep_pack_tiles) and a three-deep shared-memory ring is kept full across phase
+//     boundaries by one producer thread, one TMA bulk copy (cp.async.bulk + mbarrier) per 42 KB tile; the cross-attention
+//     K/V tile of a layer is prefetched the same way as soon as the layer's self-attention has released the buffer;
+//   * LDGSTS (cp.async) is not fire-and-forget: issuing one 40 KB tile as 16-byte copies stalls the issuing warps for
+//     ~4400 cycles once the SM's miss queue is full, and every bulk-copy instruction costs ~65 cycles of issue — hence one
+//     contiguous block per tile instead of 16 row copies;
+//   * the instruction cache: the first version of this kernel was 105 KB of SASS and ran at instruction-fetch speed.
+//     The per-layer loop is written for code size: rolled loops, out-of-line phase functions;
+//   * acquire fences invalidate L1 (CCTL.IVALL) and with it the stack: the barrier is red.release + relaxed polling, data
+//     produced by other CTAs is read with ld.global.cg / TMA, and no phase function keeps state on the stack;
+//   * LayerNorms are recomputed by each consumer CTA from the fp32 residual stream (their affine part is folded into the
+//     consuming weights at load), and the residual adds are fire-and-forget fp32 reductions.
 //
-// Work units and math are those of decode.cu (16-channel weight tiles feeding mma.sync fragments, 8 warps splitting K;
-// self-attention through the beam ancestry table; beam-shared cross attention with flash-decoding splits).
+// Math: 16-channel weight tiles feed mma.sync.m16n8k16 fragments (rows = output channels, columns = the <= 8 token rows,
+// 8 warps split K); self-attention walks the beam ancestry table; beam-shared cross attention runs QK^T and PV on
+// mma.sync from a K/V cache whose 16-byte chunks are XOR-swizzled by the key index (conflict-free fragment loads without
+// padding), with 7 flash-decoding key splits per (chunk, head) and a last-arriver combine.
 //
 // Replaces the per-token body of CTranslate2's Whisper.generate loop (reference call sites
 // faster_whisper/transcribe.py:222-236, 1446-1459) — the "single persistent kernel per
@@ -31,8 +38,14 @@ namespace b2w {
 constexpr int kDsThreads = 256;
 constexpr int kDsWarps = 8;
 constexpr int kDsXQ = 8;
-constexpr int kDsNBuf = 3;      // weight-tile ring: the tile being consumed + two in flight
-constexpr int kDsSelfKeys = 224;  // keys staged per self-attention pass
+constexpr int kDsNBuf = 3;         // weight-tile ring: the tile being consumed + two in flight
+constexpr int kDsSelfKeys = 192;   // keys staged per self-attention pass
+constexpr int kDsProducer = 128;   // the thread that owns the TMA issue state (first thread outside the epilogue warps)
+constexpr int kDsKvBytes = 2 * kDsXKeysMax * 64 * 2;  // cross-attention K + V tile
+constexpr int kDsScLd = kDsXKeysMax + 4;   // fp32 score rows
+constexpr int kDsPLd = kDsXKeysMax + 8;    // fp16 probability rows
+constexpr int kDsQLd = 96;                 // fp16 query rows
+constexpr int kDsXScratch = kDsXQ * kDsQLd * 2 + kDsXQ * kDsScLd * 4 + kDsXQ * kDsPLd * 2 + 2 * kDsXQ * 64 * 4 + 64;
 
 __device__ __forceinline__ void ds_mma(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -40,11 +53,15 @@ __device__ __forceinline__ void ds_mma(float* c, uint32_t a0, uint32_t a1, uint3
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ds_ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(smem_u32(smem_row)));
+}
 __device__ __forceinline__ void ds_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier.  Unlike cp.async (LDGSTS), whose issue stalls once
-// the SM's miss queue is full (measured: ~4400 cycles to issue one 40 KB tile), the issuing thread returns immediately.
+// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
 __device__ __forceinline__ void ds_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
                "r"(bytes), "r"(smem_u32(bar))
@@ -52,12 +69,6 @@ __device__ __forceinline__ void ds_bulk_g2s(void* smem_dst, const void* gsrc, ui
 }
 __device__ __forceinline__ void ds_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ds_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void ds_cp_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ unsigned ds_ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long ds_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -81,28 +92,19 @@ struct DsShared {
   unsigned epoch;
   int prof_i;
   int flag;
-  // weight pipeline: the next item to issue (sequence index, item index, buffer) and the buffer to consume next
-  int p_s, p_item, p_buf, c_buf, ahead;  // ahead = tiles issued and not yet consumed
-  int consumed;    // tiles consumed so far (buffer = consumed % kDsNBuf, mbarrier parity = (consumed / kDsNBuf) & 1)
-  int x_parity;    // parity of the input-staging mbarrier
+  int p_s, p_j, p_issued;  // producer-thread state: next (phase, item ordinal) to fetch, tiles issued so far
   uint64_t wbar[kDsNBuf];
-  uint64_t xbar;
+  uint64_t kvbar;
 };
 
-// Grid barrier: every CTA arrives once; sh.epoch is the running arrival target (host zeroes *bar before the launch).
-// Arrive = red.release (orders the CTA's earlier writes, cumulative through bar.sync); wait = relaxed polling.  No acquire
-// fence on purpose: it would invalidate the SM's L1 (CCTL.IVALL) and with it the stack, and every read of data produced by
-// other CTAs in this kernel already bypasses L1 (ld.global.cg / cp.async.cg / atomics).
-__device__ __forceinline__ void ds_barrier_arrive(const DStepArgs& a, DsShared& sh) {
+// Grid barrier: every CTA arrives once; sh.epoch is the running arrival target (the host zeroes *bar before the launch).
+// Arrive = red.release (orders the CTA's earlier writes, cumulative through bar.sync); wait = relaxed polling.
+__device__ __forceinline__ void ds_grid_barrier(const DStepArgs& a, DsShared& sh) {
   __syncthreads();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();  // arrival of CTA 0
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
-  }
-}
-__device__ __forceinline__ void ds_barrier_wait(const DStepArgs& a, DsShared& sh) {
-  if (threadIdx.x == 0) {
     const unsigned target = sh.epoch;
     unsigned v;
     do {
@@ -117,228 +119,183 @@ __device__ __forceinline__ void ds_barrier_wait(const DStepArgs& a, DsShared& sh
 enum { DS_QKV = 0, DS_F16 = 1, DS_GELU = 2, DS_RESID = 3, DS_F32 = 4 };
 
 // The GEMVs of a step form a static sequence s = 0 .. 6L (per layer: qkv, out, cross_q, cross_out, ffn1, ffn2; then logits).
-// A work item is (16 output channels, one of `ksplit` K ranges of width kr <= d).
-struct GemvDesc {
-  const __half* W;
-  const float* bias;
-  int N, K, ksplit, mode;
-  int ln;              // input = normalised x (LayerNorm affine is folded into W/bias at load) when set, else `src16`
-  const __half* src16;
-};
-
-__device__ __forceinline__ GemvDesc ds_desc(const DStepArgs& a, const DsShared& sh, int s) {
-  GemvDesc g;
-  const int d = a.d;
-  g.bias = nullptr; g.ln = 0; g.src16 = nullptr; g.ksplit = 1; g.K = d; g.N = d;
+// A work item is (16 output channels, one K range of width d): every GEMV has K = d except ffn2 (K = 4d, four ranges).
+__device__ __forceinline__ void ds_geom(const DStepArgs& a, int s, int& ntiles, int& ksplit) {
+  ksplit = 1;
   if (s >= 6 * a.L) {
-    g.W = a.logit_w; g.bias = a.logit_b; g.N = a.vpad; g.mode = DS_F32; g.ln = 1;
-    return g;
+    ntiles = a.vpad >> 4;
+    return;
   }
-  const DLayer& W = sh.lay[s / 6];
-  switch (s % 6) {
-    case 0: g.W = W.wqkv; g.bias = W.bqkv; g.N = 3 * d; g.mode = DS_QKV; g.ln = 1; break;
-    case 1: g.W = W.wo; g.bias = W.bo; g.mode = DS_RESID; g.src16 = a.ao; break;
-    case 2: g.W = W.wq_x; g.bias = W.bq_x; g.mode = DS_F16; g.ln = 1; break;
-    case 3: g.W = W.wo_x; g.bias = W.bo_x; g.mode = DS_RESID; g.src16 = a.ao; break;
-    case 4: g.W = W.w1; g.bias = W.b1; g.N = 4 * d; g.mode = DS_GELU; g.ln = 1; break;
-    default: g.W = W.w2; g.bias = W.b2; g.K = 4 * d; g.ksplit = 4; g.mode = DS_RESID; g.src16 = a.h; break;
-  }
-  return g;
+  const int sub = s % 6, dt = a.d >> 4;
+  ntiles = sub == 0 ? 3 * dt : (sub == 4 ? 4 * dt : dt);
+  if (sub == 5) ksplit = 4;
 }
+// j-th work item of this CTA in a phase, or -1.  With four K ranges the CTAs are grouped in fours so that all items of a
+// CTA share one range (it stages only that quarter of the FFN activations).
+__device__ __forceinline__ int ds_item(int ntiles, int ksplit, int j) {
+  if (ksplit == 1) {
+    const int it = blockIdx.x + j * gridDim.x;
+    return it < ntiles ? it : -1;
+  }
+  const int g4 = gridDim.x >> 2;
+  if ((int)blockIdx.x >= 4 * g4) return -1;
+  const int tl = (int)(blockIdx.x >> 2) + j * g4;
+  return tl < ntiles ? tl * 4 + (int)(blockIdx.x & 3) : -1;
+}
+__device__ __forceinline__ uint32_t ds_tile_bytes(int d) { return (uint32_t)(16 * (d + 32) + 32) * 2u; }
 
-// Issues the cp.async copies of the next work item's weight tile (+ its 16 bias values) into buffer sh.p_buf.
-// Buffers: [16 rows][kr + 32 halves] + 16 floats  (row stride kr*2 + 64 bytes -> conflict-free 16-byte fragment reads)
-__device__ __noinline__ bool ds_issue_next(const DStepArgs& a, DsShared& sh, __half* wbuf, int wbuf_halves) {
+// Producer thread only: keep the ring full.  `consumed` tiles have been released so far.
+__device__ __noinline__ void ds_produce(const DStepArgs& a, DsShared& sh, unsigned char* ring, int tile_stride, int consumed) {
   const int last = 6 * a.L;
-  long long tq = clock64();
-  int s = sh.p_s, item = sh.p_item;
-  const int buf = sh.p_buf;
-  GemvDesc g;
-  for (;;) {
-    if (s > last) return false;
-    g = ds_desc(a, sh, s);
-    if (item < (g.N >> 4) * g.ksplit) break;
-    s += 1;
-    item = blockIdx.x;
-  }
-  const int kr = g.K / g.ksplit, tl = item / g.ksplit, ks = item - tl * g.ksplit;
-  const __half* src = g.W + (long long)tl * 16 * g.K + ks * kr;
-  __half* dst = wbuf + (long long)buf * wbuf_halves;
-  const int ld = kr + 32;
-  if (threadIdx.x < 32) {  // warp 0: one bulk copy per weight row (+ the item's 16 bias values)
-    const bool with_bias = g.bias && ks == 0;
-    DS_TICK(a, 7, 0, tq);
-    if (threadIdx.x == 0) {
-      fence_proxy_async();  // the buffer was last read through the generic proxy
-      DS_TICK(a, 7, 1, tq);
-      mbar_expect_tx(&sh.wbar[buf], 16u * (uint32_t)kr * 2u + (with_bias ? 64u : 0u));
-      DS_TICK(a, 7, 2, tq);
+  const uint32_t bytes = ds_tile_bytes(a.d);
+#pragma unroll 1
+  while (sh.p_issued < consumed + kDsNBuf) {
+    int s = sh.p_s, j = sh.p_j, item = -1;
+#pragma unroll 1
+    for (; s <= last; ++s, j = 0) {
+      int ntiles, ksplit;
+      ds_geom(a, s, ntiles, ksplit);
+      item = ds_item(ntiles, ksplit, j);
+      if (item >= 0) break;
     }
-    __syncwarp();
-    if (threadIdx.x < 16) ds_bulk_g2s(dst + threadIdx.x * ld, src + (long long)threadIdx.x * g.K, (uint32_t)kr * 2u, &sh.wbar[buf]);
-    if (threadIdx.x == 16 && with_bias) ds_bulk_g2s(dst + 16 * ld, g.bias + tl * 16, 64u, &sh.wbar[buf]);
-    DS_TICK(a, 7, 3, tq);
-  }
-  __syncthreads();  // every thread has read p_* before thread 0 advances them
-  DS_TICK(a, 7, 4, tq);
-  if (threadIdx.x == 0) {
     sh.p_s = s;
-    sh.p_item = item + gridDim.x;
-    sh.p_buf = (buf + 1 == kDsNBuf) ? 0 : buf + 1;
-    sh.ahead += 1;
-  }
-  __syncthreads();
-  DS_TICK(a, 7, 5, tq);
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[3000 + 7 * 16 + 15] += 1;
-  return true;
-}
-
-// keep the ring full (called between a barrier's arrive and wait, and after every consumed tile)
-__device__ __noinline__ void ds_fill_pipeline(const DStepArgs& a, DsShared& sh, __half* wbuf, int wbuf_halves) {
-  while (sh.ahead < kDsNBuf) {
-    if (!ds_issue_next(a, sh, wbuf, wbuf_halves)) break;
+    if (item < 0) return;
+    const __half* base = s >= last ? a.logit_tiles : sh.lay[s / 6].wt[s % 6];
+    const int buf = sh.p_issued % kDsNBuf;
+    fence_proxy_async();  // the buffer was last read through the generic proxy
+    mbar_expect_tx(&sh.wbar[buf], bytes);
+    ds_bulk_g2s(ring + (size_t)buf * tile_stride, base + (long long)item * (bytes >> 1), bytes, &sh.wbar[buf]);
+    sh.p_j = j + 1;
+    sh.p_issued += 1;
   }
 }
 
-// GEMV input -> xs [8][K + 32] halves (row stride K*2 + 64 bytes).  Rows arrive by TMA bulk copies (one per row) on an
-// mbarrier; LayerNorm inputs land as fp32 in a staging area and are normalised one warp per row in a single pass
-// (sum and sum of squares from registers); fp16 activations are copied straight into xs.
-__device__ __noinline__ void ds_stage_input(const DStepArgs& a, DsShared& sh, int ln, const __half* src16, int K, __half* xs, float* stage32,
-                                            int kind) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ld = K + 32;
-  long long tp = clock64();
-  if (warp == 0) {
-    const uint32_t row_bytes = ln ? (uint32_t)K * 4u : (uint32_t)K * 2u;
-    if (lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&sh.xbar, row_bytes * (uint32_t)a.R);
-    }
-    __syncwarp();
-    if (lane < a.R) {
-      if (ln)
-        ds_bulk_g2s(stage32 + lane * K, a.x + (long long)lane * K, row_bytes, &sh.xbar);
-      else
-        ds_bulk_g2s(xs + lane * ld, src16 + (long long)lane * K, row_bytes, &sh.xbar);
-    }
-  }
-  DS_TICK(a, kind, 0, tp);  // copies issued
-  mbar_wait(&sh.xbar, (uint32_t)sh.x_parity);
-  DS_TICK(a, kind, 1, tp);  // input landed
-  if (ln && warp < a.R) {
-    const float4* xr = reinterpret_cast<const float4*>(stage32 + warp * K);
-    const int n4 = K >> 2;
-    float4 v[10];
-    float su = 0.f, sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const int idx = lane + 32 * i;
-      v[i] = idx < n4 ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-      su += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-    }
-    su = warp_sum(su);
-    sq = warp_sum(sq);
-    const float mean = su / K;
-    const float rstd = rsqrtf(fmaxf(sq / K - mean * mean, 0.f) + 1e-5f);
-    uint2* o = reinterpret_cast<uint2*>(xs + warp * ld);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < n4)
-        o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd, (v[i].y - mean) * rstd), pack_half2((v[i].z - mean) * rstd, (v[i].w - mean) * rstd));
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) sh.x_parity ^= 1;
-  DS_TICK(a, kind, 2, tp);  // normalised / copied input ready
-}
-
-// One GEMV phase: y[R,N] = in[R,K] W[N,K]^T for this CTA's items, weights consumed from the shared-memory pipeline.
-__device__ __noinline__ void ds_gemv_phase(const DStepArgs& a, DsShared& sh, int s, __half* wbuf, int wbuf_halves, __half* xs, float* stage32,
-                                           float* red, __half* kc, __half* vc) {
-  const GemvDesc gd = ds_desc(a, sh, s);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One GEMV phase: y[R,N] = in[R,K] W[N,K]^T for this CTA's items, weights consumed from the shared-memory ring.
+// Returns the updated count of consumed tiles (a warp-uniform register value; the ring index and mbarrier parity follow
+// from it).
+__device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int s, int consumed, unsigned char* ring, int tile_stride, __half* xs,
+                                          float* red, __half* kc, __half* vc) {
+  int ntiles, ksplit;
+  ds_geom(a, s, ntiles, ksplit);
+  if (ds_item(ntiles, ksplit, 0) < 0) return consumed;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int N = gd.N, K = gd.K, ksplit = gd.ksplit;
-  const int nitems = (N >> 4) * ksplit, kr = K / ksplit, kchunks = kr >> 5;
-  const int ldx = K + 32, ldw = kr + 32;
-  int item = blockIdx.x;
-  if (item >= nitems) return;
-  const int kind = s >= 6 * a.L ? 6 : s % 6;
-  ds_stage_input(a, sh, gd.ln, gd.src16, K, xs, stage32, kind);
+  const int d = a.d, ld = d + 32, kchunks = d >> 5;
+  const bool is_logits = s >= 6 * a.L;
+  const int sub = is_logits ? 6 : s % 6;
+  const int N = ntiles << 4;
+  int mode, ln = 0, src_ld = d;
+  const __half* src16 = nullptr;
+  switch (sub) {
+    case 0: mode = DS_QKV; ln = 1; break;
+    case 1: mode = DS_RESID; src16 = a.ao; break;
+    case 2: mode = DS_F16; ln = 1; break;
+    case 3: mode = DS_RESID; src16 = a.ao; break;
+    case 4: mode = DS_GELU; ln = 1; break;
+    case 5: mode = DS_RESID; src16 = a.h + (blockIdx.x & 3) * d; src_ld = 4 * d; break;
+    default: mode = DS_F32; ln = 1; break;
+  }
   long long tp = clock64();
+  // ---- input rows -> xs [8][d + 32] halves, straight from L2 (one round trip) ----
+  if (ln) {
+    if (warp < a.R) {  // one warp per row: single-pass LayerNorm from registers (affine part folded into the weights)
+      const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)warp * d);
+      const int n4 = d >> 2;
+      float4 v[10];
+      float su = 0.f, sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int idx = lane + 32 * i;
+        v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        su += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+      su = warp_sum(su);
+      sq = warp_sum(sq);
+      const float mean = su / d;
+      const float rstd = rsqrtf(fmaxf(sq / d - mean * mean, 0.f) + 1e-5f);
+      uint2* o = reinterpret_cast<uint2*>(xs + warp * ld);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n4)
+          o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd, (v[i].y - mean) * rstd), pack_half2((v[i].z - mean) * rstd, (v[i].w - mean) * rstd));
+      }
+    }
+  } else {
+    const int c8 = d >> 3;
+#pragma unroll 2
+    for (int i = tid; i < a.R * c8; i += kDsThreads) {
+      const int r = i / c8, c = i - r * c8;
+      *reinterpret_cast<uint4*>(xs + r * ld + c * 8) = __ldcg(reinterpret_cast<const uint4*>(src16 + (long long)r * src_ld) + c);
+    }
+  }
+  __syncthreads();
+  DS_TICK(a, sub, 0, tp);  // input staged
   bool first = true;
 #pragma unroll 1
-  for (; item < nitems; item += gridDim.x) {
-    const int tl = item / ksplit, ks = item - tl * ksplit;
-    const int n0 = tl * 16, kbase = ks * kr;
-    const int cbuf = sh.c_buf;
-    // this item's tile was issued earlier (possibly phases ago); wait for its mbarrier
-    mbar_wait(&sh.wbar[cbuf], (uint32_t)((sh.consumed / kDsNBuf) & 1));
-    if (first) DS_TICK(a, kind, 3, tp);  // weight tile landed
-    const __half* wt = wbuf + (long long)cbuf * wbuf_halves;
-    const __half* w_lo = wt + g * ldw + 8 * t;
-    const __half* w_hi = w_lo + 8 * ldw;
-    const __half* xb = xs + g * ldx + kbase + 8 * t;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+  for (int j = 0;; ++j) {
+    const int item = ds_item(ntiles, ksplit, j);
+    if (item < 0) break;
+    const int tl = ksplit == 1 ? item : item >> 2;
+    const int buf = consumed % kDsNBuf;
+    mbar_wait(&sh.wbar[buf], (uint32_t)((consumed / kDsNBuf) & 1));
+    if (first) DS_TICK(a, sub, 1, tp);  // weight tile landed
+    const __half* wt = reinterpret_cast<const __half*>(ring + (size_t)buf * tile_stride);
+    const __half* w_lo = wt + g * ld + 8 * t;
+    const __half* w_hi = w_lo + 8 * ld;
+    const __half* xb = xs + g * ld + 8 * t;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
     for (int c = warp; c < kchunks; c += kDsWarps) {
       const uint4 wa = *reinterpret_cast<const uint4*>(w_lo + c * 32);
       const uint4 wb = *reinterpret_cast<const uint4*>(w_hi + c * 32);
       const uint4 xv = *reinterpret_cast<const uint4*>(xb + c * 32);
       ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
-      ds_mma(acc, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+      ds_mma(acc2, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
     }
-    float* my = red + warp * 128;  // [16 ch][8 rows]
-    my[g * 8 + 2 * t] = acc[0];
-    my[g * 8 + 2 * t + 1] = acc[1];
-    my[(g + 8) * 8 + 2 * t] = acc[2];
-    my[(g + 8) * 8 + 2 * t + 1] = acc[3];
-    __syncthreads();
-    if (first) DS_TICK(a, kind, 4, tp);  // MMAs + partials stored
-    if (threadIdx.x < 128) {
-      const int ch = threadIdx.x & 15, r = threadIdx.x >> 4;
-      if (r < a.R) {
-        float v = 0.f;
+    float* rj = red + (j & 1) * (kDsWarps * 128);
+    float* my = rj + warp * 128;  // [16 ch][8 rows]
+    *reinterpret_cast<float2*>(my + g * 8 + 2 * t) = make_float2(acc[0] + acc2[0], acc[1] + acc2[1]);
+    *reinterpret_cast<float2*>(my + (g + 8) * 8 + 2 * t) = make_float2(acc[2] + acc2[2], acc[3] + acc2[3]);
+    const int ch = tid & 15, r = tid >> 4;
+    float v = (tid < 128) ? reinterpret_cast<const float*>(wt + 16 * ld)[ch] : 0.f;  // bias (zero for ks > 0)
+    __syncthreads();  // partials visible; the weight buffer is free
+    consumed += 1;
+    if (tid == kDsProducer) ds_produce(a, sh, ring, tile_stride, consumed);
+    if (first) DS_TICK(a, sub, 2, tp);  // MMAs + partials
+    if (tid < 128 && r < a.R) {
 #pragma unroll
-        for (int w = 0; w < kDsWarps; ++w) v += red[w * 128 + ch * 8 + r];
-        const int n = n0 + ch;
-        if (gd.bias && ks == 0) v += reinterpret_cast<const float*>(wt + 16 * ldw)[ch];
-        if (gd.mode == DS_QKV) {
-          const int d = a.d;
-          if (n < d) {
-            a.q[(long long)r * d + n] = __float2half_rn(v);
-          } else {
-            const RowInfo ri = sh.rows[r];
-            const int which = (n >= 2 * d) ? 1 : 0;
-            (which ? vc : kc)[(((long long)ri.chunk * a.n_ctx + ri.pos) * a.slots + ri.slot) * d + (n - d - which * d)] = __float2half_rn(v);
-          }
-        } else if (gd.mode == DS_F16) {
-          a.q[(long long)r * N + n] = __float2half_rn(v);
-        } else if (gd.mode == DS_GELU) {
-          a.h[(long long)r * N + n] = __float2half_rn(gelu_erf(v));
-        } else if (gd.mode == DS_RESID) {
-          atomicAdd(a.x + (long long)r * N + n, v);  // fire-and-forget reduction into the fp32 residual stream
+      for (int w = 0; w < kDsWarps; ++w) v += rj[w * 128 + ch * 8 + r];
+      const int n = tl * 16 + ch;
+      if (mode == DS_QKV) {
+        if (n < d) {
+          a.q[(long long)r * d + n] = __float2half_rn(v);
         } else {
-          a.logits[(long long)r * a.vpad + n] = v;
+          const RowInfo ri = sh.rows[r];
+          const int which = (n >= 2 * d) ? 1 : 0;
+          (which ? vc : kc)[(((long long)ri.chunk * a.n_ctx + ri.pos) * a.slots + ri.slot) * d + (n - d - which * d)] = __float2half_rn(v);
         }
+      } else if (mode == DS_F16) {
+        a.q[(long long)r * N + n] = __float2half_rn(v);
+      } else if (mode == DS_GELU) {
+        a.h[(long long)r * N + n] = __float2half_rn(gelu_erf(v));
+      } else if (mode == DS_RESID) {
+        atomicAdd(a.x + (long long)r * N + n, v);  // fire-and-forget reduction into the fp32 residual stream
+      } else {
+        a.logits[(long long)r * a.vpad + n] = v;
       }
     }
-    if (threadIdx.x == 0) {
-      sh.c_buf = (cbuf + 1 == kDsNBuf) ? 0 : cbuf + 1;
-      sh.ahead -= 1;
-      sh.consumed += 1;
-    }
-    __syncthreads();
-    if (first) DS_TICK(a, kind, 5, tp);  // epilogue
-    ds_fill_pipeline(a, sh, wbuf, wbuf_halves);
     if (first) {
-      DS_TICK(a, kind, 6, tp);  // ring topped up
-      if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[3000 + kind * 16 + 15] += 1;
+      DS_TICK(a, sub, 3, tp);  // epilogue
+      if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[3000 + sub * 16 + 15] += 1;
     }
     first = false;
   }
+  return consumed;
 }
 
 // masked self-attention for one (head, row) task: the row's K/V history is gathered through the ancestry table into
@@ -425,65 +382,91 @@ __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShare
   __syncthreads();
 }
 
-// beam-shared cross attention: one (key split, head, chunk) task; the last split of a (chunk, head) group combines
-__device__ __noinline__ void ds_cross_attn_task(const DStepArgs& a, DsShared& sh, int layer, int split, int h, int b, float* sm) {
-  const int T = a.T, S = a.xsplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nq = a.rows_per_chunk, row0 = b * a.rows_per_chunk, d = a.d;
-  const int k0 = (int)((long long)T * split / S), k1 = (int)((long long)T * (split + 1) / S), nk = k1 - k0;
-  const int kmax = (T + S - 1) / S + 1;
-  float* qs = sm;                              // [8][64]
-  float* sc = qs + kDsXQ * 64;                 // [8][kmax]
-  float* wred = sc + kDsXQ * kmax;             // [8 warps][8][64]
-  float* stat = wred + kDsWarps * kDsXQ * 64;  // [8][2]
-  __half* vt = reinterpret_cast<__half*>(stat + kDsXQ * 2);  // [kmax][64]
-  __half* kt = vt + kmax * 64;                 // [kmax][72]
+// Producer thread only: TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf.
+__device__ __noinline__ void ds_issue_cross_kv(const DStepArgs& a, DsShared& sh, int layer, int task, unsigned char* kvbuf) {
+  const int split = task % kDsXSplits, rest = task / kDsXSplits;
+  const int h = rest % a.H, b = rest / a.H, T = a.T;
+  const int k0 = (int)((long long)T * split / kDsXSplits), k1 = (int)((long long)T * (split + 1) / kDsXSplits), nk = k1 - k0;
   const DecBindings bd = *a.bind;
   const long long per = (long long)bd.B_total * a.H * T * 64;
-  const __half* Kb = bd.xkv + ((long long)layer * 2 + 0) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
-  const __half* Vb = bd.xkv + ((long long)layer * 2 + 1) * per + (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
-#pragma unroll 1
-  for (int i = tid; i < nk * 8; i += kDsThreads) ds_cp_async16(kt + (i >> 3) * 72 + (i & 7) * 8, Kb + i * 8);
-  ds_cp_commit();
-#pragma unroll 1
-  for (int i = tid; i < nk * 8; i += kDsThreads) ds_cp_async16(vt + i * 8, Vb + i * 8);
-  ds_cp_commit();
-  for (int i = tid; i < kDsXQ * 64; i += kDsThreads) {
-    const int q = i >> 6, e = i & 63;
-    qs[i] = (q < nq) ? __half2float(__ldcg(a.q + (long long)(row0 + q) * d + h * 64 + e)) * 0.125f : 0.f;
-  }
-  ds_cp_wait_1();
-  __syncthreads();
-  // scores: one key per thread, eight queries at a time in registers
-#pragma unroll 1
-  for (int j = tid; j < nk; j += kDsThreads) {
-    const __half2* kp = reinterpret_cast<const __half2*>(kt + j * 72);
-    float s[kDsXQ];
+  const long long off = (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
+  const __half* Kb = bd.xkv + ((long long)layer * 2 + 0) * per + off;
+  const __half* Vb = bd.xkv + ((long long)layer * 2 + 1) * per + off;
+  fence_proxy_async();
+  mbar_expect_tx(&sh.kvbar, (uint32_t)nk * 256u);
+  ds_bulk_g2s(kvbuf, Kb, (uint32_t)nk * 128u, &sh.kvbar);
+  ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, &sh.kvbar);
+}
+
+// Beam-shared cross attention: one (key split, head, chunk) task for all rows of the chunk; the last split of a
+// (chunk, head) group to finish combines.  K/V rows are 128 bytes whose 16-byte chunks are XOR-swizzled by (key & 7) in the
+// cache itself (gemm.cu EPI_F16_XKV), so the tile arrives conflict-free with two bulk copies.
+//   S[key][q]  = K Q^T      : mma A = K rows (keys), B = Q rows; 16-byte fragment loads, k-permuted like the GEMVs
+//   O^T[e][q]  = V^T P^T    : mma A = V^T via ldmatrix.trans, B = P rows (fp16 probabilities)
+__device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh, int layer, int task, bool prefetched, int kv_uses,
+                                               unsigned char* kvbuf, unsigned char* scratch) {
+  const int T = a.T, S = kDsXSplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int split = task % S, rest = task / S, h = rest % a.H, b = rest / a.H;
+  const int nq = a.rows_per_chunk, row0 = b * a.rows_per_chunk, d = a.d;
+  const int k0 = (int)((long long)T * split / S), k1 = (int)((long long)T * (split + 1) / S), nk = k1 - k0;
+  const int nkp = (nk + 15) & ~15;
+  __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
+  __half* vt = kt + kDsXKeysMax * 64;
+  __half* qs = reinterpret_cast<__half*>(scratch);                 // [8][96], pre-scaled by 1/8
+  float* sc = reinterpret_cast<float*>(qs + kDsXQ * kDsQLd);      // [8][kDsScLd]
+  __half* pr = reinterpret_cast<__half*>(sc + kDsXQ * kDsScLd);   // [8][kDsPLd]
+  float* wred = reinterpret_cast<float*>(pr + kDsXQ * kDsPLd);    // [2][8][64]
+  float* stat = wred + 2 * kDsXQ * 64;                            // [8][2]
+  if (!prefetched && tid == kDsProducer) ds_issue_cross_kv(a, sh, layer, task, kvbuf);
+  if (tid < 64) {
+    const int q = tid >> 3, c = tid & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (q < nq) {
+      v = __ldcg(reinterpret_cast<const uint4*>(a.q + (long long)(row0 + q) * d + h * 64) + c);
+      __half2* h2 = reinterpret_cast<__half2*>(&v);
+      const __half2 sc8 = __floats2half2_rn(0.125f, 0.125f);
 #pragma unroll
-    for (int q = 0; q < kDsXQ; ++q) s[q] = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
-      const float2 kf = __half22float2(kp[i]);
-#pragma unroll
-      for (int q = 0; q < kDsXQ; ++q) {
-        const float2 qq = *reinterpret_cast<const float2*>(qs + q * 64 + 2 * i);
-        s[q] = fmaf(kf.x, qq.x, fmaf(kf.y, qq.y, s[q]));
-      }
+      for (int i = 0; i < 4; ++i) h2[i] = __hmul2(h2[i], sc8);
     }
+    *reinterpret_cast<uint4*>(qs + q * kDsQLd + c * 8) = v;
+  }
+  // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite
+  for (int i = tid; i < (nkp - nk) * 8; i += kDsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  mbar_wait(&sh.kvbar, (uint32_t)(kv_uses & 1));
+  __syncthreads();
+  // ---- scores ----
+#pragma unroll 1
+  for (int tile = warp; tile * 16 < nkp; tile += kDsWarps) {
+    const int rg = tile * 16 + g, swz = (k0 + rg) & 7;  // rows rg and rg + 8 share the swizzle
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < kDsXQ; ++q) sc[q * kmax + j] = s[q];
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int pc = ((4 * c2 + t) ^ swz) << 3;
+      const uint4 wa = *reinterpret_cast<const uint4*>(kt + rg * 64 + pc);
+      const uint4 wb = *reinterpret_cast<const uint4*>(kt + (rg + 8) * 64 + pc);
+      const uint4 xv = *reinterpret_cast<const uint4*>(qs + g * kDsQLd + 32 * c2 + 8 * t);
+      ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
+      ds_mma(acc, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+    }
+    sc[(2 * t) * kDsScLd + rg] = acc[0];
+    sc[(2 * t + 1) * kDsScLd + rg] = acc[1];
+    sc[(2 * t) * kDsScLd + rg + 8] = acc[2];
+    sc[(2 * t + 1) * kDsScLd + rg + 8] = acc[3];
   }
   __syncthreads();
-  {  // one warp per query: partial softmax statistics
+  {  // one warp per query: partial softmax statistics, probabilities as fp16
     const int q = warp;
     if (q < nq) {
       float mx = -INFINITY;
-      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kmax + j]);
+      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kDsScLd + j]);
       mx = warp_max(mx);
       float sum = 0.f;
-      for (int j = lane; j < nk; j += 32) {
-        const float p = __expf(sc[q * kmax + j] - mx);
-        sc[q * kmax + j] = p;
-        sum += p;
+      for (int j = lane; j < nkp; j += 32) {
+        const float p = j < nk ? __expf(sc[q * kDsScLd + j] - mx) : 0.f;
+        const __half ph = __float2half_rn(p);
+        pr[q * kDsPLd + j] = ph;
+        sum += __half2float(ph);
       }
       sum = warp_sum(sum);
       if (lane == 0) {
@@ -491,36 +474,37 @@ __device__ __noinline__ void ds_cross_attn_task(const DStepArgs& a, DsShared& sh
         stat[q * 2 + 1] = sum;
       }
     } else {
-      for (int j = lane; j < nk; j += 32) sc[q * kmax + j] = 0.f;
+      for (int j = lane; j < nkp; j += 32) pr[q * kDsPLd + j] = __float2half_rn(0.f);
     }
   }
-  ds_cp_wait_all();
   __syncthreads();
-  float acc[kDsXQ][2];
-#pragma unroll
-  for (int q = 0; q < kDsXQ; ++q) acc[q][0] = acc[q][1] = 0.f;
+  {  // ---- O^T = V^T P^T: warp -> (16 output dims, half of the key tiles) ----
+    const int dtile = warp & 3, khalf = warp >> 2;
+    const int mi = lane >> 3, r8 = lane & 7;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-  for (int j = warp; j < nk; j += kDsWarps) {
-    const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vt + j * 64 + 2 * lane));
-#pragma unroll
-    for (int q = 0; q < kDsXQ; ++q) {
-      const float p = sc[q * kmax + j];
-      acc[q][0] = fmaf(p, vf.x, acc[q][0]);
-      acc[q][1] = fmaf(p, vf.y, acc[q][1]);
+    for (int tile = khalf; tile * 16 < nkp; tile += 2) {
+      const int row = tile * 16 + 8 * (mi >> 1) + r8;
+      const int pc = ((2 * dtile + (mi & 1)) ^ ((k0 + row) & 7)) << 3;
+      uint32_t a0, a1, a2, a3;
+      ds_ldmatrix_x4_trans(a0, a1, a2, a3, vt + row * 64 + pc);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr + g * kDsPLd + tile * 16 + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pr + g * kDsPLd + tile * 16 + 2 * t + 8);
+      ds_mma(acc, a0, a1, a2, a3, b0, b1);
     }
+    float* w = wred + khalf * (kDsXQ * 64);
+    w[(2 * t) * 64 + 16 * dtile + g] = acc[0];
+    w[(2 * t + 1) * 64 + 16 * dtile + g] = acc[1];
+    w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
+    w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
   }
-#pragma unroll
-  for (int q = 0; q < kDsXQ; ++q) *reinterpret_cast<float2*>(wred + (warp * kDsXQ + q) * 64 + 2 * lane) = make_float2(acc[q][0], acc[q][1]);
   __syncthreads();
   const long long group = (long long)b * a.H + h;
   float* part = a.xpart + (group * S + split) * (kDsXQ * 66);
 #pragma unroll 1
   for (int i = tid; i < nq * 64; i += kDsThreads) {
     const int q = i >> 6, e = i & 63;
-    float v = 0.f;
-#pragma unroll
-    for (int w = 0; w < kDsWarps; ++w) v += wred[(w * kDsXQ + q) * 64 + e];
-    __stcg(part + q * 66 + e, v);
+    __stcg(part + q * 66 + e, wred[q * 64 + e] + wred[(kDsXQ + q) * 64 + e]);
   }
   if (tid < nq) {
     __stcg(part + tid * 66 + 64, stat[tid * 2]);
@@ -562,26 +546,28 @@ __device__ __noinline__ void ds_cross_attn_task(const DStepArgs& a, DsShared& sh
     }
   }
   __syncthreads();
+  return kv_uses + 1;
 }
 
 __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_param) {
-  extern __shared__ __align__(16) unsigned char ds_smem[];
+  extern __shared__ __align__(128) unsigned char ds_smem[];
   // the argument block is copied to shared memory: the out-of-line phase functions take it by reference, and a reference
   // to a kernel parameter would otherwise be materialised on the (L1-cached, local-memory) stack
   __shared__ DStepArgs a_sh;
+  __shared__ DsShared sh;
   if (threadIdx.x == 0) a_sh = a_param;
   __syncthreads();
   const DStepArgs& a = a_sh;
-  // [weight ring: kDsNBuf buffers][union: GEMV input xs (+ fp32 LayerNorm staging) | attention scratch][red]
-  const int wbuf_halves = 16 * (a.d + 32) + 32;  // 16 padded rows + 16 fp32 bias values
-  __half* wbuf = reinterpret_cast<__half*>(ds_smem);
-  unsigned char* uni = ds_smem + kDsNBuf * (size_t)wbuf_halves * sizeof(__half);
-  __half* xs = reinterpret_cast<__half*>(uni);
-  float* stage32 = reinterpret_cast<float*>(uni + (size_t)8 * (a.d + 32) * sizeof(__half));  // only used by LayerNorm inputs (K = d)
-  float* att = reinterpret_cast<float*>(uni);
-  float* red = reinterpret_cast<float*>(uni + a.smem_xs_bytes);
-  __shared__ DsShared sh;
+  // [weight ring: kDsNBuf tiles][cross-attention K/V tile | self-attention scratch][GEMV input xs | cross-attention scratch][red x2]
   const int d = a.d, L = a.L;
+  const int tile_stride = (int)((ds_tile_bytes(d) + 127u) & ~127u);
+  unsigned char* ring = ds_smem;
+  unsigned char* kvbuf = ring + (size_t)kDsNBuf * tile_stride;
+  unsigned char* scr = kvbuf + kDsKvBytes;
+  const int xs_bytes = 8 * (d + 32) * 2;
+  const int scr_bytes = ((xs_bytes > kDsXScratch ? xs_bytes : kDsXScratch) + 127) & ~127;
+  float* red = reinterpret_cast<float*>(scr + scr_bytes);
+  __half* xs = reinterpret_cast<__half*>(scr);
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.layers);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh.lay);
@@ -591,20 +577,17 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
       sh.epoch = 0;
       sh.prof_i = 1;
       sh.p_s = 0;
-      sh.p_item = blockIdx.x;
-      sh.p_buf = 0;
-      sh.c_buf = 0;
-      sh.ahead = 0;
-      sh.consumed = 0;
-      sh.x_parity = 0;
+      sh.p_j = 0;
+      sh.p_issued = 0;
       for (int i = 0; i < kDsNBuf; ++i) mbar_init(&sh.wbar[i], 1);
-      mbar_init(&sh.xbar, 1);
+      mbar_init(&sh.kvbar, 1);
       fence_mbar_init();
       if (a.prof && blockIdx.x == 0) a.prof[0] = ds_globaltimer();
     }
   }
   __syncthreads();
-  ds_fill_pipeline(a, sh, wbuf, wbuf_halves);  // the first weight tiles are in flight before anything else happens
+  if (threadIdx.x == kDsProducer) ds_produce(a, sh, ring, tile_stride, 0);  // the first weight tiles are in flight before anything else happens
+  int consumed = 0, kv_uses = 0;
 
   // ---- embed: x = tok_emb[token] + pos_emb[pos] (CTA r owns row r) ----
   if ((int)blockIdx.x < a.R) {
@@ -616,9 +599,9 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
     for (int i = threadIdx.x; i < d; i += kDsThreads)
       __stcg(a.x + (long long)r * d + i, __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
   }
-  ds_barrier_arrive(a, sh);
-  ds_barrier_wait(a, sh);
+  ds_grid_barrier(a, sh);
 
+  const int xtasks = kDsXSplits * a.H * a.n_chunks;
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
@@ -627,62 +610,79 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
     for (int ph = 0; ph < 8; ++ph) {
       if (ph == 1) {  // masked self-attention
 #pragma unroll 1
-        for (int task = blockIdx.x; task < a.H * a.R; task += gridDim.x) ds_self_attn_task(a, sh, task % a.H, task / a.H, kc, vc, att);
+        for (int task = blockIdx.x; task < a.H * a.R; task += gridDim.x)
+          ds_self_attn_task(a, sh, task % a.H, task / a.H, kc, vc, reinterpret_cast<float*>(kvbuf));
+        // the buffer is free until this layer's cross attention: fetch its K/V tile now (it does not depend on the step)
+        if (threadIdx.x == kDsProducer && (int)blockIdx.x < xtasks) ds_issue_cross_kv(a, sh, l, blockIdx.x, kvbuf);
       } else if (ph == 4) {  // beam-shared cross attention
+        bool pre = true;
 #pragma unroll 1
-        for (int task = blockIdx.x; task < a.xsplits * a.H * a.n_chunks; task += gridDim.x) {
-          const int split = task % a.xsplits, rest = task / a.xsplits;
-          ds_cross_attn_task(a, sh, l, split, rest % a.H, rest / a.H, att);
+        for (int task = blockIdx.x; task < xtasks; task += gridDim.x) {
+          kv_uses = ds_cross_attn_task(a, sh, l, task, pre, kv_uses, kvbuf, scr);
+          pre = false;
         }
       } else {
         // GEMV sequence index inside the layer: ph 0 -> qkv(0), 2 -> out(1), 3 -> cross_q(2), 5 -> cross_out(3), 6 -> ffn1(4), 7 -> ffn2(5)
         const int j = ph == 0 ? 0 : (ph < 4 ? ph - 1 : ph - 2);
-        ds_gemv_phase(a, sh, 6 * l + j, wbuf, wbuf_halves, xs, stage32, red, kc, vc);
+        consumed = ds_gemv_phase(a, sh, 6 * l + j, consumed, ring, tile_stride, xs, red, kc, vc);
       }
-      // arrive, then use the barrier latency to top up the weight ring, then wait
-      ds_barrier_arrive(a, sh);
-      ds_fill_pipeline(a, sh, wbuf, wbuf_halves);
-      ds_barrier_wait(a, sh);
+      ds_grid_barrier(a, sh);
     }
   }
   // ---- logits = LN_f(x) E^T ----
-  ds_gemv_phase(a, sh, 6 * L, wbuf, wbuf_halves, xs, stage32, red, nullptr, nullptr);
+  consumed = ds_gemv_phase(a, sh, 6 * L, consumed, ring, tile_stride, xs, red, nullptr, nullptr);
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
 }
 
-size_t dstep_smem_bytes(const DStepArgs& a, size_t* xs_bytes) {
-  const size_t wbufs = kDsNBuf * ((size_t)16 * (a.d + 32) + 32) * sizeof(__half);
-  const size_t xs_ffn2 = (size_t)8 * (4 * a.d + 32) * sizeof(__half);
-  const size_t xs_ln = (size_t)8 * (a.d + 32) * sizeof(__half) + (size_t)8 * a.d * sizeof(float);  // fp16 rows + fp32 rows, gamma, beta
-  const int kmax = (a.T + a.xsplits - 1) / a.xsplits + 1;
-  const size_t xat = (size_t)(kDsXQ * 64 + kDsXQ * kmax + kDsWarps * kDsXQ * 64 + kDsXQ * 2) * sizeof(float) + (size_t)kmax * (64 + 72) * sizeof(__half);
-  const size_t sat = (size_t)(kDsSelfKeys + 16 + 256 + 64) * sizeof(float) + (size_t)kDsSelfKeys * (72 + 64) * sizeof(__half);
-  size_t region = xs_ffn2;
-  if (xs_ln > region) region = xs_ln;
-  if (xat > region) region = xat;
-  if (sat > region) region = sat;
-  region = (region + 127) & ~size_t(127);
-  if (xs_bytes) *xs_bytes = region;
-  return wbufs + region + kDsWarps * 128 * sizeof(float);
+// ---- weight re-layout: row-major [N][K] -> stream of work-item tiles -------------------------------------------------------
+__global__ void ds_pack_kernel(const __half* __restrict__ W, const float* __restrict__ bias, int K, int ksplit, __half* __restrict__ out) {
+  const int item = blockIdx.x, tl = item / ksplit, ks = item - tl * ksplit;
+  const int kr = K / ksplit, ld = kr + 32;
+  __half* o = out + (size_t)item * (16 * ld + 32);
+  for (int i = threadIdx.x; i < 16 * ld; i += blockDim.x) {
+    const int r = i / ld, c = i - r * ld;
+    o[i] = c < kr ? W[(size_t)(tl * 16 + r) * K + ks * kr + c] : __float2half(0.f);
+  }
+  float* ob = reinterpret_cast<float*>(o + 16 * ld);
+  if (threadIdx.x < 16) ob[threadIdx.x] = (bias && ks == 0) ? bias[tl * 16 + threadIdx.x] : 0.f;
+}
+
+size_t dstep_tile_halves(int kr) { return (size_t)16 * (kr + 32) + 32; }
+size_t dstep_packed_halves(int N, int K, int ksplit) { return (size_t)(N / 16) * ksplit * dstep_tile_halves(K / ksplit); }
+
+void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int ksplit, __half* out, cudaStream_t s) {
+  B2W_CHECK(N % 16 == 0 && K % (32 * ksplit) == 0, "dstep_pack_tiles: shape");
+  ds_pack_kernel<<<(N / 16) * ksplit, 256, 0, s>>>(W, bias, K, ksplit, out);
+  B2W_LAUNCHED();
+}
+
+size_t dstep_smem_bytes(const DStepArgs& a) {
+  const size_t tile_stride = ((size_t)dstep_tile_halves(a.d) * 2 + 127) & ~size_t(127);
+  const size_t xs_bytes = (size_t)8 * (a.d + 32) * 2;
+  const size_t scr = ((xs_bytes > (size_t)kDsXScratch ? xs_bytes : (size_t)kDsXScratch) + 127) & ~size_t(127);
+  return kDsNBuf * tile_stride + kDsKvBytes + scr + 2 * kDsWarps * 128 * sizeof(float);
 }
 
 void dstep_configure() {
   B2W_CUDA(cudaFuncSetAttribute(dstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 }
 
-int dstep_max_grid(int num_sms, size_t smem) {
-  if (smem > 220 * 1024) return 0;
+// 0 when the shape is not supported by the persistent kernel (the caller falls back to the multi-kernel step)
+int dstep_max_grid(int num_sms, const DStepArgs& a) {
+  const size_t smem = dstep_smem_bytes(a);
+  const size_t self_scratch = (size_t)(kDsSelfKeys + 16 + 256 + 64) * sizeof(float) + (size_t)kDsSelfKeys * (72 + 64) * sizeof(__half);
+  if (smem > 220 * 1024 || self_scratch > (size_t)kDsKvBytes) return 0;
+  if (a.d % 64 != 0 || a.d > 1280 || a.L > 32 || a.R > 8 || (a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || num_sms < 4) return 0;
   int per_sm = 0;
   B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel, kDsThreads, smem));
   return per_sm >= 1 ? num_sms : 0;
 }
 
-void dstep_launch(DStepArgs a, int grid, cudaStream_t s) {
-  size_t xs = 0;
-  const size_t smem = dstep_smem_bytes(a, &xs);
-  a.smem_xs_bytes = (int)xs;
+void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s) {
+  const size_t smem = dstep_smem_bytes(a);
   B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
-  void* args[] = {&a};
+  DStepArgs copy = a;
+  void* args[] = {&copy};
   B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dstep_kernel), dim3(grid), dim3(kDsThreads), args, smem, s));
   count_launch();
 }

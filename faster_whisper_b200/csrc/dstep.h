@@ -4,22 +4,22 @@
 
 namespace b2w {
 
+constexpr int kDsXSplits = 7;    // key splits of the beam-shared cross attention (20 heads x 7 = 140 tasks for 148 SMs)
+constexpr int kDsXKeysMax = 224;  // keys per cross-attention tile (multiple of 16, >= ceil(T / kDsXSplits) + 1)
+
+// Per layer: the six weight matrices of the step re-laid out as a stream of work-item tiles (dstep_pack_tiles), in the order
+// qkv, out, cross_q, cross_out, ffn1, ffn2.
 struct DLayer {
-  const __half *wqkv, *wo, *wq_x, *wo_x, *w1, *w2;
-  const float *bqkv, *bo, *bq_x, *bo_x, *b1, *b2;
-  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  const __half* wt[6];
 };
 
 struct DStepArgs {
   const DLayer* layers;  // device array [L]
   int L;
   const __half* tok_emb;
-  const __half* logit_w;
-  const float* logit_b;
+  const __half* logit_tiles;  // packed tiles of the (LayerNorm-folded) output embedding
   const float* pos_emb;
-  const float* lnf_g;
-  const float* lnf_b;
-  int R, d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk, xsplits;
+  int R, d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk;
   const RowInfo* rows;
   const int* tokens_in;
   float* x;        // [8][d] fp32 residual stream
@@ -36,13 +36,19 @@ struct DStepArgs {
   float* xpart;
   int* xcounters;
   unsigned* bar;
-  int smem_xs_bytes;  // filled by dstep_launch
-  unsigned long long* prof;  // optional: %globaltimer at every barrier exit (CTA 0), [1 + 8 L + 1]
+  unsigned long long* prof;  // optional: %globaltimer at every barrier (CTA 0) + cycle counters
 };
 
-size_t dstep_smem_bytes(const DStepArgs& a, size_t* xs_bytes);
+// Tile stream of one matrix W[N][K] (+ bias[N] or null) split `ksplit` ways along K: item = tile * ksplit + ks holds
+// 16 rows x (K/ksplit) halves, rows padded by 32 halves (bank-conflict-free 16-byte fragment reads), then 16 fp32 bias
+// values (zero unless ks == 0).  One item = one contiguous block = one TMA bulk copy.
+size_t dstep_tile_halves(int kr);
+size_t dstep_packed_halves(int N, int K, int ksplit);
+void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int ksplit, __half* out, cudaStream_t s);
+
+size_t dstep_smem_bytes(const DStepArgs& a);
 void dstep_configure();
-int dstep_max_grid(int num_sms, size_t smem);
-void dstep_launch(DStepArgs a, int grid, cudaStream_t s);
+int dstep_max_grid(int num_sms, const DStepArgs& a);
+void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s);
 
 }  // namespace b2w

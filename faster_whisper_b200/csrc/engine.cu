@@ -439,12 +439,25 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   gemm_configure();
   dstep_configure();
   {
+    // decoder weights re-laid out as the persistent step kernel's tile stream (a second copy: ~1.6 GB for large-v3)
     std::vector<DLayer> hl(L);
-    for (int i = 0; i < L; ++i) {
+    auto pack = [&](const __half* W, const float* bias, int N, int K, int ksplit) {
+      __half* out = up.alloc<__half>(dstep_packed_halves(N, K, ksplit));
+      dstep_pack_tiles(W, bias, N, K, ksplit, out, m->stream);
+      return out;
+    };
+    const bool packable = dt % 64 == 0 && m->vpad % 16 == 0;
+    for (int i = 0; i < L && packable; ++i) {
       const DecLayerW& D = m->dec[i];
-      hl[i] = DLayer{D.wqkv, D.wo, D.wq_x, D.wo_x, D.w1, D.w2, D.bqkv, D.bo, D.bq_x, D.bo_x, D.b1, D.b2,
-                     D.ln1_g, D.ln1_b, D.ln2_g, D.ln2_b, D.ln3_g, D.ln3_b};
+      hl[i].wt[0] = pack(D.wqkv, D.bqkv, 3 * dt, dt, 1);
+      hl[i].wt[1] = pack(D.wo, D.bo, dt, dt, 1);
+      hl[i].wt[2] = pack(D.wq_x, D.bq_x, dt, dt, 1);
+      hl[i].wt[3] = pack(D.wo_x, D.bo_x, dt, dt, 1);
+      hl[i].wt[4] = pack(D.w1, D.b1, 4 * dt, dt, 1);
+      hl[i].wt[5] = pack(D.w2, D.b2, dt, 4 * dt, 4);
     }
+    if (packable) m->logit_tiles = pack(m->logit_w, m->logit_b, m->vpad, dt, 1);
+    else m->use_dstep = false;
     m->d_layers = dalloc<DLayer>(L);
     B2W_CUDA(cudaMemcpy(m->d_layers, hl.data(), L * sizeof(DLayer), cudaMemcpyHostToDevice));
     m->d_bar = dalloc<unsigned>(4);
@@ -978,11 +991,9 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
   bool use_dstep = m->use_dstep && !sp.fake_logits && R <= 8 && !m->use_ref_gemv && c.n_text_layer <= 32;
   if (use_dstep) {
     ds.layers = m->d_layers; ds.L = c.n_text_layer; ds.tok_emb = m->tok_emb; ds.pos_emb = m->dec_pos;
-    ds.logit_w = m->logit_w; ds.logit_b = m->logit_b;
-    ds.lnf_g = m->dec_ln_g; ds.lnf_b = m->dec_ln_b;
+    ds.logit_tiles = m->logit_tiles;
     ds.R = R; ds.d = c.n_text_state; ds.H = c.n_text_head; ds.n_ctx = c.n_text_ctx; ds.slots = K; ds.T = 1500;
     ds.vpad = m->vpad; ds.n_vocab = c.n_vocab; ds.n_chunks = n; ds.rows_per_chunk = K;
-    ds.xsplits = std::max(1, std::min(8, m->num_sms / (c.n_text_head * n)));
     ds.rows = sb.rows; ds.tokens_in = sb.tokens_in;
     ds.x = m->d_x; ds.q = m->d_q; ds.ao = m->d_ao; ds.h = m->d_h; ds.logits = m->d_logits;
     ds.kcache = m->kcache; ds.vcache = m->vcache; ds.kv_layer_stride = (long long)m->kv_elems;
@@ -990,8 +1001,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     ds.bind = m->d_bind; ds.xpart = m->d_xpart; ds.xcounters = m->d_counters + 64; ds.bar = m->d_bar;
     ds.prof = m->d_prof;
     if (m->dstep_grid == 0) {
-      const size_t smem = dstep_smem_bytes(ds, nullptr);
-      m->dstep_grid = dstep_max_grid(m->num_sms, smem);
+      m->dstep_grid = dstep_max_grid(m->num_sms, ds);
       if (m->dstep_grid == 0) m->dstep_grid = -1;
     }
     if (m->dstep_grid <= 0) use_dstep = false;
@@ -1110,13 +1120,8 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         for (int k = 0; k < 7; ++k) {
           const double n = (double)f[k * 16 + 15];
           if (n > 0)
-            fprintf(stderr, "[dstep prof]   %-9s cycles: issue-x %.0f  x-landed %.0f  LN/copy %.0f  tile-wait %.0f  mma %.0f  epilogue %.0f  refill %.0f\n",
-                    kinds[k], f[k * 16] / n, f[k * 16 + 1] / n, f[k * 16 + 2] / n, f[k * 16 + 3] / n, f[k * 16 + 4] / n, f[k * 16 + 5] / n, f[k * 16 + 6] / n);
-        }
-        if (f[7 * 16 + 15] > 0) {
-          const double n = (double)f[7 * 16 + 15];
-          fprintf(stderr, "[dstep prof]   issue_next cycles: find %.0f  fence %.0f  expect_tx %.0f  bulk %.0f  sync1 %.0f  sync2 %.0f (mean of %.0f)\n", f[112] / n,
-                  f[113] / n, f[114] / n, f[115] / n, f[116] / n, f[117] / n, n);
+            fprintf(stderr, "[dstep prof]   %-9s cycles (first item): stage-input %.0f  tile-wait %.0f  mma %.0f  epilogue %.0f\n", kinds[k], f[k * 16] / n,
+                    f[k * 16 + 1] / n, f[k * 16 + 2] / n, f[k * 16 + 3] / n);
         }
       }
       for (int ph = 0; ph < 8; ++ph)

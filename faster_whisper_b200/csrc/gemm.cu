@@ -82,11 +82,14 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row,
     const int l = n0 / two_d, rem = n0 - l * two_d;
     const int kv = rem / p.xkv_d, c = rem - kv * p.xkv_d;
     const int h = c >> 6, e = c & 63;
-    long long idx = ((((long long)(l * 2 + kv) * p.xkv_B + b) * p.xkv_heads + h) * p.xkv_T + row) * 64 + e;
+    // a (t, head) row is 128 bytes = eight 16-byte chunks stored at chunk ^ (t & 7): the decode kernels copy K/V tiles
+    // to shared memory verbatim and read them bank-conflict-free (dstep.cu, decode.cu)
+    long long idx = ((((long long)(l * 2 + kv) * p.xkv_B + b) * p.xkv_heads + h) * p.xkv_T + row) * 64;
     uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + idx);
+    const int cb = e >> 3, sw = row & 7;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      o4[i] = make_uint4(pack_half2(v[8 * i], v[8 * i + 1]), pack_half2(v[8 * i + 2], v[8 * i + 3]),
+      o4[(cb + i) ^ sw] = make_uint4(pack_half2(v[8 * i], v[8 * i + 1]), pack_half2(v[8 * i + 2], v[8 * i + 3]),
                          pack_half2(v[8 * i + 4], v[8 * i + 5]), pack_half2(v[8 * i + 6], v[8 * i + 7]));
   } else {
     const long long idx = (long long)b * p.out_batch_stride + (long long)row * p.out_ld + n0;
@@ -384,7 +387,8 @@ __global__ void gemm_ref_kernel(const __half* __restrict__ A, int a_rows, int a_
   } else if (epi == EPI_F16_XKV) {
     const int two_d = 2 * p.xkv_d;
     const int l = n / two_d, rem = n - l * two_d, kv = rem / p.xkv_d, c = rem - kv * p.xkv_d;
-    long long o = ((((long long)(l * 2 + kv) * p.xkv_B + b) * p.xkv_heads + (c >> 6)) * p.xkv_T + row) * 64 + (c & 63);
+    const int e = c & 63;
+    long long o = ((((long long)(l * 2 + kv) * p.xkv_B + b) * p.xkv_heads + (c >> 6)) * p.xkv_T + row) * 64 + ((((e >> 3) ^ (row & 7)) << 3) | (e & 7));
     reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(acc);
   } else if (epi == EPI_QKV_CACHE) {
     const int d = p.qkv_d;

@@ -109,6 +109,7 @@ struct Model {
   int* d_counters = nullptr;  // [0]: GEMM ticket, [64..]: cross-attention groups
   uint8_t* d_suppress = nullptr;
   DecBindings* d_bind = nullptr;
+  __half* logit_tiles = nullptr;  // output embedding as the persistent step kernel's tile stream
   DLayer* d_layers = nullptr;   // device copy of the decoder layer pointer table (persistent step kernel)
   unsigned* d_bar = nullptr;
   unsigned long long* d_prof = nullptr;  // B2W_DSTEP_PROF=1: per-phase timestamps of the persistent step kernel
