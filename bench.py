@@ -94,53 +94,96 @@ def dist_env():
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (a port of the reference path; CTranslate2 itself is not installable here)
 # ----------------------------------------------------------------------------------------------------------------
+def host_threads(cap: int = 16) -> int:
+    """Threads the CPU arm uses: the cores this process may actually run on (affinity and cgroup quota), capped — on a
+    128-core box an uncapped torch thread pool ran this path 10x slower than 8 threads do."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]))))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        n = min(n, max(1, q // int(f2.read().split()[0])))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, min(n, cap))
+
+
+class CpuPath:
+    """The oracle's restatement of the reference path on the host cores (weights and model built once)."""
+
+    def __init__(self, model_name: str, beam: int, sample_tokens: int, seed: int, threads: int):
+        import torch
+
+        from faster_whisper_b200.config import MODEL_DIMS, special_tokens
+        from faster_whisper_b200.synthetic import make_weights, synthetic_audio
+        from oracle.whisper_oracle import WhisperOracle
+
+        torch.set_num_threads(threads)
+        self.threads, self.beam, self.sample_tokens = threads, beam, sample_tokens
+        self.dims = MODEL_DIMS[model_name]
+        self.st = special_tokens(self.dims.n_vocab)
+        self.orc = WhisperOracle(self.dims.to_dict(), make_weights(self.dims, seed=seed), self.st.to_dict())
+        self.audio = synthetic_audio(0, 30.0)
+
+    def run(self):
+        from oracle.whisper_oracle import log_mel, pad_or_trim
+
+        st, dims, beam, sample_tokens = self.st, self.dims, self.beam, self.sample_tokens
+        t0 = time.perf_counter()
+        feats = pad_or_trim(log_mel(self.audio, dims.n_mels)[:, :-1])[None]
+        t1 = time.perf_counter()
+        enc = self.orc.encode(feats)
+        t2 = time.perf_counter()
+        prompt = [st.sot, st.lang_begin, st.transcribe, st.no_timestamps] if dims.is_multilingual else [st.sot, st.no_timestamps]
+        sup = [st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech]
+        self.orc.generate(enc, [prompt], beam_size=beam, max_length=len(prompt) + sample_tokens, suppress_tokens=sup)
+        t3 = time.perf_counter()
+        per_tok = (t3 - t2) / (sample_tokens + len(prompt) - 1)
+        total = (t1 - t0) + (t2 - t1) + per_tok * (NEW_TOKENS + len(prompt) - 1)
+        return dict(value=30.0 / total, unit="audio-s/s", cores=self.threads, kind="port",
+                    sample=(f"1 chunk of 30 s: log-mel {1e3 * (t1 - t0):.0f} ms + encoder {1e3 * (t2 - t1):.0f} ms measured in full; beam-{beam} "
+                            f"decode measured for {sample_tokens} new tokens ({1e3 * per_tok:.0f} ms/position) and extrapolated to {NEW_TOKENS}; "
+                            "fp32 torch CPU restatement of the reference path, not CTranslate2 int8"))
+
+
 def cpu_baseline(model_name: str, beam: int, sample_tokens: int, seed: int, threads: int):
-    import torch
-
-    from faster_whisper_b200.config import MODEL_DIMS, special_tokens
-    from faster_whisper_b200.synthetic import make_weights, synthetic_audio
-    from oracle.whisper_oracle import WhisperOracle, log_mel, pad_or_trim
-
-    torch.set_num_threads(threads)
-    dims = MODEL_DIMS[model_name]
-    st = special_tokens(dims.n_vocab)
-    w = make_weights(dims, seed=seed)
-    orc = WhisperOracle(dims.to_dict(), w, st.to_dict())
-    audio = synthetic_audio(0, 30.0)
-    t0 = time.perf_counter()
-    feats = pad_or_trim(log_mel(audio, dims.n_mels)[:, :-1])[None]
-    t1 = time.perf_counter()
-    enc = orc.encode(feats)
-    t2 = time.perf_counter()
-    prompt = [st.sot, st.lang_begin, st.transcribe, st.no_timestamps] if dims.is_multilingual else [st.sot, st.no_timestamps]
-    sup = [st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech]
-    orc.generate(enc, [prompt], beam_size=beam, max_length=len(prompt) + sample_tokens, suppress_tokens=sup)
-    t3 = time.perf_counter()
-    per_tok = (t3 - t2) / (sample_tokens + len(prompt) - 1)
-    total = (t1 - t0) + (t2 - t1) + per_tok * (NEW_TOKENS + len(prompt) - 1)
-    return dict(value=30.0 / total, unit="audio-s/s", cores=threads, kind="port",
-                sample=(f"1 chunk of 30 s: log-mel {1e3 * (t1 - t0):.0f} ms + encoder {1e3 * (t2 - t1):.0f} ms measured in full; beam-{beam} decode "
-                        f"measured for {sample_tokens} new tokens ({1e3 * per_tok:.0f} ms/position) and extrapolated to {NEW_TOKENS}; "
-                        "fp32 torch CPU restatement of the reference path, not CTranslate2 int8"))
+    return CpuPath(model_name, beam, sample_tokens, seed, threads).run()
 
 
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     t0 = time.perf_counter()
+    path = CpuPath(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, threads)
+    for _ in range(min(args.warmup, 1)):
+        path.run()
     vals = []
     cb = None
-    for _ in range(max(1, min(args.steps, 2))):
-        cb = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, threads)
+    # every step is the same bounded sample (one 30 s chunk, short decode extrapolated); at most 3 are timed so the arm ends in minutes
+    for _ in range(max(1, min(args.steps, 3))):
+        cb = path.run()
         vals.append(cb["value"])
     v = float(np.mean(vals))
     cb["value"] = v
     line = dict(metric=METRIC, value=v, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=30.0 / v * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config={"workload": workload_name(args), "model": args.model, "note": "CPU port of the reference path on rank 0's host cores"},
+                config={"workload": workload_name(args), "model": args.model, "timed_samples": len(vals),
+                        "note": "CPU port of the reference path on rank 0's host cores"},
                 cpu_baseline=cb, e2e={"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 wall_s=time.perf_counter() - t0)
     print(json.dumps(line), flush=True)
@@ -248,16 +291,20 @@ def run_engine(args):
         gpu_launches=int(stats["launches"]),
         clocks=clocks,
         stages_ms={k[:-3]: round(v / args.steps, 3) for k, v in stats.items() if k.endswith("_ms") and v > 0},
-        roofline={"bound": "hbm", "kernel": "decode step (CUDA graph: skinny_gemm weight stream + self/cross attention + search)",
+        device_ms_per_step=round(sum(v for k, v in stats.items() if k.endswith("_ms")) / args.steps, 3),
+        timing="value/e2e: host clock around K steps bracketed by stream sync (+ barrier, max over ranks); stages_ms/roofline: CUDA events on the engine stream",
+        roofline={"bound": "hbm", "kernel": ("decode step = dstep_kernel (persistent: weight stream + self/cross attention + logits) + search kernels"
+                                             if B * args.beam_size <= 8 else
+                                             "decode step (CUDA graph: gemm_tc/skinny_gemm weight stream + self/cross attention + search)"),
                   "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "peak_source": pk["source"],
-                  "traffic": None, "ms_per_decode_step": dec_ms / steps_dec,
+                  "traffic": ncu_traffic(B * args.beam_size <= 8), "ms_per_decode_step": dec_ms / steps_dec,
                   "alg_bytes_per_step": stats["decode_alg_bytes"] / steps_dec},
         roofline_encoder={"bound": "tensor", "achieved": enc_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": enc_tf / pk["tflops"],
                           "flops_per_chunk": enc_flops_per_chunk(dims), "ms_per_chunk": stats["encoder_ms"] / (B * args.steps)},
     )
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, host_threads())
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     if use_dist:
@@ -265,6 +312,17 @@ def run_engine(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def ncu_traffic(persistent: bool):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("dstep_kernel" if persistent else "decode_graph")
+    except (OSError, ValueError):
+        return None
 
 
 def enc_flops_per_chunk(dims) -> float:

@@ -226,11 +226,24 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
       }
     }
   } else {
-    const int c8 = d >> 3;
-#pragma unroll 2
-    for (int i = tid; i < a.R * c8; i += kDsThreads) {
-      const int r = i / c8, c = i - r * c8;
-      *reinterpret_cast<uint4*>(xs + r * ld + c * 8) = __ldcg(reinterpret_cast<const uint4*>(src16 + (long long)r * src_ld) + c);
+    // all 16-byte loads of a thread are in flight together (one L2 round trip): up to 8 rows x d/8 chunks over 256 threads
+    const int c8 = d >> 3, total = a.R * c8;
+    uint4 v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = tid + k * kDsThreads;
+      if (i < total) {
+        const int r = i / c8, c = i - r * c8;
+        v[k] = __ldcg(reinterpret_cast<const uint4*>(src16 + (long long)r * src_ld) + c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = tid + k * kDsThreads;
+      if (i < total) {
+        const int r = i / c8, c = i - r * c8;
+        *reinterpret_cast<uint4*>(xs + r * ld + c * 8) = v[k];
+      }
     }
   }
   __syncthreads();

@@ -1561,6 +1561,7 @@ int b2w_debug_gemm(int32_t device, int32_t impl, const float* a, const float* w,
       ga.out = dc; ga.out_ld = N; ga.epilogue = EPI_F32;
     }
     if (impl == 0) {
+      gemm_configure();  // per-device kernel attributes (build_model does this for real models)
       GemmPlan p = gemm_plan(ga, prop.multiProcessorCount);
       gemm_run(p, 0);
     } else {
