@@ -35,12 +35,12 @@
 
 namespace b2w {
 
-constexpr int kDsThreads = 256;
+constexpr int kDsThreads = 256;   // compute threads (8 warps)
+constexpr int kDsLaunchThreads = 320;  // + one warp streaming weight tiles, one prefetching cross-attention K/V
 constexpr int kDsWarps = 8;
 constexpr int kDsXQ = 8;
 constexpr int kDsNBuf = 3;         // weight-tile ring: the tile being consumed + two in flight
 constexpr int kDsSelfKeys = 192;   // keys staged per self-attention pass
-constexpr int kDsProducer = 128;   // the thread that owns the TMA issue state (first thread outside the epilogue warps)
 constexpr int kDsKvBytes = 2 * kDsXKeysMax * 64 * 2;  // cross-attention K + V tile
 constexpr int kDsScLd = kDsXKeysMax + 4;   // fp32 score rows
 constexpr int kDsPLd = kDsXKeysMax + 8;    // fp16 probability rows
@@ -75,14 +75,17 @@ __device__ __forceinline__ unsigned long long ds_globaltimer() {
   return t;
 }
 
-// fine-grained cycle accounting for CTA 0 (B2W_DSTEP_PROF): slot = 3000 + kind*16 + point
-#define DS_TICK(a, kind, point, tprev)                                                      \
-  do {                                                                                      \
-    if ((a).prof && blockIdx.x == 0 && threadIdx.x == 0) {                                  \
-      const long long _now = clock64();                                                     \
-      (a).prof[3000 + (kind) * 16 + (point)] += (unsigned long long)(_now - (tprev));       \
-      (tprev) = _now;                                                                       \
-    }                                                                                       \
+// barrier of the 256 compute threads (the producer warps never join it)
+__device__ __forceinline__ void ds_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// fine-grained cycle accounting for CTA 0 (B2W_DSTEP_PROF): accumulated in shared memory, dumped to prof[3000 + kind*16 + point] at the end
+#define DS_TICK(a, kind, point, tprev)                                    \
+  do {                                                                    \
+    if ((a).prof && blockIdx.x == 0 && threadIdx.x == 0) {                \
+      const long long _now = clock64();                                   \
+      sh.ticks[(kind) * 8 + (point)] += (unsigned)(_now - (tprev));       \
+      (tprev) = _now;                                                     \
+    }                                                                     \
   } while (0)
 
 // per-CTA state that lives in shared memory (pointers/tables are never re-fetched from L2 inside the layer loop)
@@ -92,15 +95,17 @@ struct DsShared {
   unsigned epoch;
   int prof_i;
   int flag;
-  int p_s, p_j, p_issued;  // producer-thread state: next (phase, item ordinal) to fetch, tiles issued so far
-  uint64_t wbar[kDsNBuf];
-  uint64_t kvbar;
+  unsigned ticks[8 * 8];
+  uint64_t wfull[kDsNBuf];   // weight tile landed (TMA complete_tx)
+  uint64_t wempty[kDsNBuf];  // weight tile consumed (one arrival by compute thread 0)
+  uint64_t kvfull;           // cross-attention K/V tile landed
+  uint64_t kvfree;           // K/V buffer released by this layer's self-attention
 };
 
 // Grid barrier: every CTA arrives once; sh.epoch is the running arrival target (the host zeroes *bar before the launch).
 // Arrive = red.release (orders the CTA's earlier writes, cumulative through bar.sync); wait = relaxed polling.
 __device__ __forceinline__ void ds_grid_barrier(const DStepArgs& a, DsShared& sh) {
-  __syncthreads();
+  ds_sync();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();  // arrival of CTA 0
@@ -113,7 +118,7 @@ __device__ __forceinline__ void ds_grid_barrier(const DStepArgs& a, DsShared& sh
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();  // release
     sh.prof_i += 2;
   }
-  __syncthreads();
+  ds_sync();
 }
 
 enum { DS_QKV = 0, DS_F16 = 1, DS_GELU = 2, DS_RESID = 3, DS_F32 = 4 };
@@ -144,29 +149,29 @@ __device__ __forceinline__ int ds_item(int ntiles, int ksplit, int j) {
 }
 __device__ __forceinline__ uint32_t ds_tile_bytes(int d) { return (uint32_t)(16 * (d + 32) + 32) * 2u; }
 
-// Producer thread only: keep the ring full.  `consumed` tiles have been released so far.
-__device__ __noinline__ void ds_produce(const DStepArgs& a, DsShared& sh, unsigned char* ring, int tile_stride, int consumed) {
+// Weight producer (one thread of a dedicated warp): walks this CTA's work items of the whole step in order and keeps the
+// ring full — wait until the buffer's previous tile has been consumed, then one TMA bulk copy per tile.  It never
+// synchronises with the compute warps other than through the mbarriers, so it runs ahead across phase boundaries.
+__device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh, unsigned char* ring, int tile_stride) {
   const int last = 6 * a.L;
   const uint32_t bytes = ds_tile_bytes(a.d);
+  int n = 0;
 #pragma unroll 1
-  while (sh.p_issued < consumed + kDsNBuf) {
-    int s = sh.p_s, j = sh.p_j, item = -1;
-#pragma unroll 1
-    for (; s <= last; ++s, j = 0) {
-      int ntiles, ksplit;
-      ds_geom(a, s, ntiles, ksplit);
-      item = ds_item(ntiles, ksplit, j);
-      if (item >= 0) break;
-    }
-    sh.p_s = s;
-    if (item < 0) return;
+  for (int s = 0; s <= last; ++s) {
+    int ntiles, ksplit;
+    ds_geom(a, s, ntiles, ksplit);
     const __half* base = s >= last ? a.logit_tiles : sh.lay[s / 6].wt[s % 6];
-    const int buf = sh.p_issued % kDsNBuf;
-    fence_proxy_async();  // the buffer was last read through the generic proxy
-    mbar_expect_tx(&sh.wbar[buf], bytes);
-    ds_bulk_g2s(ring + (size_t)buf * tile_stride, base + (long long)item * (bytes >> 1), bytes, &sh.wbar[buf]);
-    sh.p_j = j + 1;
-    sh.p_issued += 1;
+#pragma unroll 1
+    for (int j = 0;; ++j) {
+      const int item = ds_item(ntiles, ksplit, j);
+      if (item < 0) break;
+      const int buf = n % kDsNBuf;
+      mbar_wait(&sh.wempty[buf], (uint32_t)(((n / kDsNBuf) & 1) ^ 1));  // passes immediately on the first lap
+      fence_proxy_async();
+      mbar_expect_tx(&sh.wfull[buf], bytes);
+      ds_bulk_g2s(ring + (size_t)buf * tile_stride, base + (long long)item * (bytes >> 1), bytes, &sh.wfull[buf]);
+      n += 1;
+    }
   }
 }
 
@@ -246,7 +251,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
       }
     }
   }
-  __syncthreads();
+  ds_sync();
   DS_TICK(a, sub, 0, tp);  // input staged
   bool first = true;
 #pragma unroll 1
@@ -255,7 +260,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     if (item < 0) break;
     const int tl = ksplit == 1 ? item : item >> 2;
     const int buf = consumed % kDsNBuf;
-    mbar_wait(&sh.wbar[buf], (uint32_t)((consumed / kDsNBuf) & 1));
+    mbar_wait(&sh.wfull[buf], (uint32_t)((consumed / kDsNBuf) & 1));
     if (first) DS_TICK(a, sub, 1, tp);  // weight tile landed
     const __half* wt = reinterpret_cast<const __half*>(ring + (size_t)buf * tile_stride);
     const __half* w_lo = wt + g * ld + 8 * t;
@@ -276,9 +281,9 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     *reinterpret_cast<float2*>(my + (g + 8) * 8 + 2 * t) = make_float2(acc[2] + acc2[2], acc[3] + acc2[3]);
     const int ch = tid & 15, r = tid >> 4;
     float v = (tid < 128) ? reinterpret_cast<const float*>(wt + 16 * ld)[ch] : 0.f;  // bias (zero for ks > 0)
-    __syncthreads();  // partials visible; the weight buffer is free
+    ds_sync();  // partials visible; the weight buffer is free
     consumed += 1;
-    if (tid == kDsProducer) ds_produce(a, sh, ring, tile_stride, consumed);
+    if (tid == 0) mbar_arrive(&sh.wempty[buf]);
     if (first) DS_TICK(a, sub, 2, tp);  // MMAs + partials
     if (tid < 128 && r < a.R) {
 #pragma unroll
@@ -304,7 +309,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     }
     if (first) {
       DS_TICK(a, sub, 3, tp);  // epilogue
-      if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[3000 + sub * 16 + 15] += 1;
+      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[sub * 8 + 7] += 1;
     }
     first = false;
   }
@@ -342,7 +347,7 @@ __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShare
     }
     ds_cp_commit();
     ds_cp_wait_all();
-    __syncthreads();
+    ds_sync();
     float mx = -INFINITY;
     if (tid < n) {
       const __half2* kp = reinterpret_cast<const __half2*>(kt + tid * 72);
@@ -358,7 +363,7 @@ __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShare
     }
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
+    ds_sync();
     mx = red[0];
 #pragma unroll
     for (int i = 1; i < kDsWarps; ++i) mx = fmaxf(mx, red[i]);
@@ -371,7 +376,7 @@ __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShare
     }
     sum = warp_sum(sum);
     if ((tid & 31) == 0) red[8 + (tid >> 5)] = sum;
-    __syncthreads();
+    ds_sync();
     sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kDsWarps; ++i) sum += red[8 + i];
@@ -387,15 +392,15 @@ __device__ __noinline__ void ds_self_attn_task(const DStepArgs& a, const DsShare
     acc = fmaf(acc, alpha, a0 + a1);
     l_run = fmaf(l_run, alpha, sum);
     m_run = m_new;
-    __syncthreads();  // the staging buffers are reused by the next pass
+    ds_sync();  // the staging buffers are reused by the next pass
   }
   oacc[part * 64 + e] = acc;
-  __syncthreads();
+  ds_sync();
   if (tid < 64) a.ao[(long long)r * d + h * 64 + tid] = __float2half_rn((oacc[tid] + oacc[64 + tid] + oacc[128 + tid] + oacc[192 + tid]) / l_run);
-  __syncthreads();
+  ds_sync();
 }
 
-// Producer thread only: TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf.
+// TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf (one thread).
 __device__ __noinline__ void ds_issue_cross_kv(const DStepArgs& a, DsShared& sh, int layer, int task, unsigned char* kvbuf) {
   const int split = task % kDsXSplits, rest = task / kDsXSplits;
   const int h = rest % a.H, b = rest / a.H, T = a.T;
@@ -405,10 +410,21 @@ __device__ __noinline__ void ds_issue_cross_kv(const DStepArgs& a, DsShared& sh,
   const long long off = (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
   const __half* Kb = bd.xkv + ((long long)layer * 2 + 0) * per + off;
   const __half* Vb = bd.xkv + ((long long)layer * 2 + 1) * per + off;
-  fence_proxy_async();
-  mbar_expect_tx(&sh.kvbar, (uint32_t)nk * 256u);
-  ds_bulk_g2s(kvbuf, Kb, (uint32_t)nk * 128u, &sh.kvbar);
-  ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, &sh.kvbar);
+  fence_proxy_async();  // the buffer was last written through the generic proxy (self-attention staging)
+  mbar_expect_tx(&sh.kvfull, (uint32_t)nk * 256u);
+  ds_bulk_g2s(kvbuf, Kb, (uint32_t)nk * 128u, &sh.kvfull);
+  ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, &sh.kvfull);
+}
+
+// K/V producer (one thread of a second dedicated warp): per layer, as soon as the layer's self-attention has released the
+// buffer, fetch the tile of this CTA's first cross-attention task — it does not depend on the step, only on the layer.
+__device__ __noinline__ void ds_kv_producer(const DStepArgs& a, DsShared& sh, unsigned char* kvbuf) {
+  if ((int)blockIdx.x >= kDsXSplits * a.H * a.n_chunks) return;
+#pragma unroll 1
+  for (int l = 0; l < a.L; ++l) {
+    mbar_wait(&sh.kvfree, (uint32_t)(l & 1));
+    ds_issue_cross_kv(a, sh, l, blockIdx.x, kvbuf);
+  }
 }
 
 // Beam-shared cross attention: one (key split, head, chunk) task for all rows of the chunk; the last split of a
@@ -431,7 +447,7 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
   __half* pr = reinterpret_cast<__half*>(sc + kDsXQ * kDsScLd);   // [8][kDsPLd]
   float* wred = reinterpret_cast<float*>(pr + kDsXQ * kDsPLd);    // [2][8][64]
   float* stat = wred + 2 * kDsXQ * 64;                            // [8][2]
-  if (!prefetched && tid == kDsProducer) ds_issue_cross_kv(a, sh, layer, task, kvbuf);
+  if (!prefetched && tid == 0) ds_issue_cross_kv(a, sh, layer, task, kvbuf);
   if (tid < 64) {
     const int q = tid >> 3, c = tid & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -446,8 +462,8 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
   }
   // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite
   for (int i = tid; i < (nkp - nk) * 8; i += kDsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  mbar_wait(&sh.kvbar, (uint32_t)(kv_uses & 1));
-  __syncthreads();
+  mbar_wait(&sh.kvfull, (uint32_t)(kv_uses & 1));
+  ds_sync();
   // ---- scores ----
 #pragma unroll 1
   for (int tile = warp; tile * 16 < nkp; tile += kDsWarps) {
@@ -467,7 +483,7 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
     sc[(2 * t) * kDsScLd + rg + 8] = acc[2];
     sc[(2 * t + 1) * kDsScLd + rg + 8] = acc[3];
   }
-  __syncthreads();
+  ds_sync();
   {  // one warp per query: partial softmax statistics, probabilities as fp16
     const int q = warp;
     if (q < nq) {
@@ -490,7 +506,7 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
       for (int j = lane; j < nkp; j += 32) pr[q * kDsPLd + j] = __float2half_rn(0.f);
     }
   }
-  __syncthreads();
+  ds_sync();
   {  // ---- O^T = V^T P^T: warp -> (16 output dims, half of the key tiles) ----
     const int dtile = warp & 3, khalf = warp >> 2;
     const int mi = lane >> 3, r8 = lane & 7;
@@ -511,7 +527,7 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
     w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
     w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
   }
-  __syncthreads();
+  ds_sync();
   const long long group = (long long)b * a.H + h;
   float* part = a.xpart + (group * S + split) * (kDsXQ * 66);
 #pragma unroll 1
@@ -523,14 +539,14 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
     __stcg(part + tid * 66 + 64, stat[tid * 2]);
     __stcg(part + tid * 66 + 65, stat[tid * 2 + 1]);
   }
-  __syncthreads();
+  ds_sync();
   if (tid == 0) {
     int ticket;  // release: the CTA's partials are visible before the ticket; the combiner reads them with ld.cg (L2)
     asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(a.xcounters + group) : "memory");
     sh.flag = (ticket == S - 1);
     if (sh.flag) a.xcounters[group] = 0;
   }
-  __syncthreads();
+  ds_sync();
   if (sh.flag) {
     const float* pg = a.xpart + group * S * (kDsXQ * 66);
 #pragma unroll 1
@@ -558,11 +574,11 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
       a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
     }
   }
-  __syncthreads();
+  ds_sync();
   return kv_uses + 1;
 }
 
-__global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_param) {
+__global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepArgs a_param) {
   extern __shared__ __align__(128) unsigned char ds_smem[];
   // the argument block is copied to shared memory: the out-of-line phase functions take it by reference, and a reference
   // to a kernel parameter would otherwise be materialised on the (L1-cached, local-memory) stack
@@ -584,22 +600,29 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.layers);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh.lay);
-    for (int i = threadIdx.x; i < L * (int)(sizeof(DLayer) / 8); i += kDsThreads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < L * (int)(sizeof(DLayer) / 8); i += kDsLaunchThreads) dst[i] = src[i];
     if (threadIdx.x < a.R) sh.rows[threadIdx.x] = a.rows[threadIdx.x];
     if (threadIdx.x == 0) {
       sh.epoch = 0;
       sh.prof_i = 1;
-      sh.p_s = 0;
-      sh.p_j = 0;
-      sh.p_issued = 0;
-      for (int i = 0; i < kDsNBuf; ++i) mbar_init(&sh.wbar[i], 1);
-      mbar_init(&sh.kvbar, 1);
+      for (int i = 0; i < kDsNBuf; ++i) {
+        mbar_init(&sh.wfull[i], 1);
+        mbar_init(&sh.wempty[i], 1);
+      }
+      mbar_init(&sh.kvfull, 1);
+      mbar_init(&sh.kvfree, 1);
       fence_mbar_init();
       if (a.prof && blockIdx.x == 0) a.prof[0] = ds_globaltimer();
     }
+    if (threadIdx.x < 64) sh.ticks[threadIdx.x] = 0;
   }
   __syncthreads();
-  if (threadIdx.x == kDsProducer) ds_produce(a, sh, ring, tile_stride, 0);  // the first weight tiles are in flight before anything else happens
+  // ---- role split: warp 8 streams the weight tiles, warp 9 prefetches cross-attention K/V, warps 0-7 compute ----
+  if (threadIdx.x >= kDsThreads) {
+    if (threadIdx.x == kDsThreads) ds_weight_producer(a, sh, ring, tile_stride);
+    if (threadIdx.x == kDsThreads + 32) ds_kv_producer(a, sh, kvbuf);
+    return;
+  }
   int consumed = 0, kv_uses = 0;
 
   // ---- embed: x = tok_emb[token] + pos_emb[pos] (CTA r owns row r) ----
@@ -625,8 +648,8 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
 #pragma unroll 1
         for (int task = blockIdx.x; task < a.H * a.R; task += gridDim.x)
           ds_self_attn_task(a, sh, task % a.H, task / a.H, kc, vc, reinterpret_cast<float*>(kvbuf));
-        // the buffer is free until this layer's cross attention: fetch its K/V tile now (it does not depend on the step)
-        if (threadIdx.x == kDsProducer && (int)blockIdx.x < xtasks) ds_issue_cross_kv(a, sh, l, blockIdx.x, kvbuf);
+        // the buffer is free until this layer's cross attention: let the K/V producer fetch the tile now
+        if (threadIdx.x == 0) mbar_arrive(&sh.kvfree);
       } else if (ph == 4) {  // beam-shared cross attention
         bool pre = true;
 #pragma unroll 1
@@ -644,7 +667,11 @@ __global__ void __launch_bounds__(kDsThreads, 1) dstep_kernel(const DStepArgs a_
   }
   // ---- logits = LN_f(x) E^T ----
   consumed = ds_gemv_phase(a, sh, 6 * L, consumed, ring, tile_stride, xs, red, nullptr, nullptr);
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.prof[sh.prof_i] = ds_globaltimer();
+    for (int k = 0; k < 8; ++k)
+      for (int p2 = 0; p2 < 8; ++p2) a.prof[3000 + k * 16 + (p2 == 7 ? 15 : p2)] += sh.ticks[k * 8 + p2];
+  }
 }
 
 // ---- weight re-layout: row-major [N][K] -> stream of work-item tiles -------------------------------------------------------
@@ -687,7 +714,7 @@ int dstep_max_grid(int num_sms, const DStepArgs& a) {
   if (smem > 220 * 1024 || self_scratch > (size_t)kDsKvBytes) return 0;
   if (a.d % 64 != 0 || a.d > 1280 || a.L > 32 || a.R > 8 || (a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || num_sms < 4) return 0;
   int per_sm = 0;
-  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel, kDsThreads, smem));
+  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel, kDsLaunchThreads, smem));
   return per_sm >= 1 ? num_sms : 0;
 }
 
@@ -696,7 +723,7 @@ void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s) {
   B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
   DStepArgs copy = a;
   void* args[] = {&copy};
-  B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dstep_kernel), dim3(grid), dim3(kDsThreads), args, smem, s));
+  B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dstep_kernel), dim3(grid), dim3(kDsLaunchThreads), args, smem, s));
   count_launch();
 }
 
