@@ -674,6 +674,32 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
   }
 }
 
+// The same cross-attention task as a stand-alone kernel for the multi-kernel step (many chunks per call): one CTA per
+// (key split, head, chunk), ~74 KB of shared memory so three CTAs per SM overlap each other's tile fetches.
+__global__ void __launch_bounds__(kDsThreads) ds_cross_attn_kernel(const DStepArgs a_param, int layer) {
+  extern __shared__ __align__(128) unsigned char ds_smem[];
+  __shared__ DStepArgs a_sh;
+  __shared__ DsShared sh;
+  if (threadIdx.x == 0) {
+    a_sh = a_param;
+    mbar_init(&sh.kvfull, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  ds_cross_attn_task(a_sh, sh, layer, blockIdx.x, false, 0, ds_smem, ds_smem + kDsKvBytes);
+}
+
+bool dstep_cross_attn_supported(int T, int rows_per_chunk) {
+  return rows_per_chunk <= kDsXQ && (T + kDsXSplits - 1) / kDsXSplits + 1 <= kDsXKeysMax;
+}
+
+// a: q, ao, bind, xpart, xcounters, H, T, d, rows_per_chunk, n_chunks
+void dstep_cross_attn_launch(const DStepArgs& a, int layer, cudaStream_t s) {
+  const size_t smem = kDsKvBytes + ((kDsXScratch + 127) & ~127);
+  ds_cross_attn_kernel<<<kDsXSplits * a.H * a.n_chunks, kDsThreads, smem, s>>>(a, layer);
+  B2W_LAUNCHED();
+}
+
 // ---- weight re-layout: row-major [N][K] -> stream of work-item tiles -------------------------------------------------------
 __global__ void ds_pack_kernel(const __half* __restrict__ W, const float* __restrict__ bias, int K, int ksplit, __half* __restrict__ out) {
   const int item = blockIdx.x, tl = item / ksplit, ks = item - tl * ksplit;
@@ -705,6 +731,7 @@ size_t dstep_smem_bytes(const DStepArgs& a) {
 
 void dstep_configure() {
   B2W_CUDA(cudaFuncSetAttribute(dstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  B2W_CUDA(cudaFuncSetAttribute(ds_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsKvBytes + ((kDsXScratch + 127) & ~127)));
 }
 
 // 0 when the shape is not supported by the persistent kernel (the caller falls back to the multi-kernel step)

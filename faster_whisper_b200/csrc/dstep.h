@@ -46,6 +46,10 @@ size_t dstep_tile_halves(int kr);
 size_t dstep_packed_halves(int N, int K, int ksplit);
 void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int ksplit, __half* out, cudaStream_t s);
 
+// stand-alone beam-shared cross attention on mma.sync (the persistent kernel's task as its own launch)
+bool dstep_cross_attn_supported(int T, int rows_per_chunk);
+void dstep_cross_attn_launch(const DStepArgs& a, int layer, cudaStream_t s);
+
 size_t dstep_smem_bytes(const DStepArgs& a);
 void dstep_configure();
 int dstep_max_grid(int num_sms, const DStepArgs& a);

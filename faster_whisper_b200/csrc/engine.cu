@@ -827,13 +827,20 @@ static void decoder_layers(Model* m, int n_chunks, int rows_per_chunk, int slots
     GvArgs q;
     q.x = m->d_xn; q.W = W.wq_x; q.bias = W.bq_x; q.R = R; q.N = dt; q.K = dt; q.mode = GV_F16; q.out_h = m->d_q;
     gv(m, q);
-    CrossAttnArgs ca;
-    ca.q = m->d_q;
-    ca.bind = m->d_bind;
-    ca.layer = l;
-    ca.out = m->d_ao; ca.partial = m->d_xpart; ca.counters = m->d_counters + 64;
-    ca.T = 1500; ca.H = H; ca.d = dt; ca.rows_per_chunk = rows_per_chunk; ca.splits = splits; ca.qgroups = qgroups;
-    dec_cross_attn(ca, n_chunks, s);
+    if (m->use_mma_xattn && splits >= kDsXSplits && dstep_cross_attn_supported(1500, rows_per_chunk)) {
+      DStepArgs xa{};
+      xa.q = m->d_q; xa.ao = m->d_ao; xa.bind = m->d_bind; xa.xpart = m->d_xpart; xa.xcounters = m->d_counters + 64;
+      xa.H = H; xa.T = 1500; xa.d = dt; xa.rows_per_chunk = rows_per_chunk; xa.n_chunks = n_chunks;
+      dstep_cross_attn_launch(xa, l, s);
+    } else {
+      CrossAttnArgs ca;
+      ca.q = m->d_q;
+      ca.bind = m->d_bind;
+      ca.layer = l;
+      ca.out = m->d_ao; ca.partial = m->d_xpart; ca.counters = m->d_counters + 64;
+      ca.T = 1500; ca.H = H; ca.d = dt; ca.rows_per_chunk = rows_per_chunk; ca.splits = splits; ca.qgroups = qgroups;
+      dec_cross_attn(ca, n_chunks, s);
+    }
     GvArgs ox;
     ox.x = m->d_ao; ox.W = W.wo_x; ox.bias = W.bo_x; ox.R = R; ox.N = dt; ox.K = dt; ox.mode = GV_RESID_LN;
     ox.xres = m->d_x; ox.ln_g = W.ln3_g; ox.ln_b = W.ln3_b; ox.xn_out = m->d_xn; ox.counter = m->d_counters;
@@ -1237,6 +1244,7 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     if (const char* v = getenv("B2W_GEMV_IMPL")) m->use_ref_gemv = !strcmp(v, "ref");
     if (const char* v = getenv("B2W_GRAPH")) m->use_graph = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_DSTEP")) m->use_dstep = strcmp(v, "0") != 0;
+    if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {
       if (strcmp(v, "0") != 0) {
         m->d_prof = dalloc<unsigned long long>(4096);

@@ -115,6 +115,7 @@ struct Model {
   unsigned long long* d_prof = nullptr;  // B2W_DSTEP_PROF=1: per-phase timestamps of the persistent step kernel
   int dstep_grid = 0;
   bool use_dstep = true;
+  bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)
   DecBindings h_bind{};
   SearchParams h_params{};
   // search buffers

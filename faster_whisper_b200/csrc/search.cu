@@ -27,6 +27,7 @@ struct ArgMax {
   float v;
   int i;
 };
+__device__ __forceinline__ bool is_better(ArgMax c, ArgMax m) { return c.v > m.v || (c.v == m.v && c.i < m.i); }
 __device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
 __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
 #pragma unroll
@@ -91,9 +92,11 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
   // ---- no_speech probability from the raw first-step logits (sot is the last prompt token) ----
   if (p.want_no_speech_first && step == 0 && k == 0) {
     float mx = -INFINITY;
+#pragma unroll 4
     for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, row[v]);
     mx = block_max(mx, red);
     float sm = 0.f;
+#pragma unroll 4
     for (int v = tid; v < V; v += kRowThreads) sm += __expf(row[v] - mx);
     sm = block_sum(sm, red);
     if (tid == 0) bf.no_speech[b] = __expf(row[p.no_speech] - mx) / sm;
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
     const int last_ts = sh_flags[0], penult_ts = sh_flags[1], t_last = sh_flags[2];
     if (step == 0) {
       const int hi = ts0 + p.max_initial_ts;
+#pragma unroll 4
       for (int v = tid; v < V; v += kRowThreads)
         if (v < ts0 || (p.max_initial_ts >= 0 && v > hi)) s[v] = B2W_LOWEST;
     } else {
@@ -204,14 +208,17 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
           hi_a = p.eot;
         }
       }
+#pragma unroll 4
       for (int v = tid; v < V; v += kRowThreads)
         if ((v >= lo_a && v < hi_a) || (t_last >= 0 && v >= ts0 && v < t_last)) s[v] = B2W_LOWEST;
       __syncthreads();
       // if the timestamps' total probability beats every text token, force a timestamp
       float mx = -INFINITY;
+#pragma unroll 4
       for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, s[v]);
       mx = block_max(mx, red);
       float sum_all = 0.f, sum_ts = 0.f, max_text = -INFINITY;
+#pragma unroll 4
       for (int v = tid; v < V; v += kRowThreads) {
         const float e = __expf(s[v] - mx);
         sum_all += e;
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
       const float ts_lp = (sum_ts > 0.f) ? (mx + logf(sum_ts) - lse) : -INFINITY;
       const float text_lp = max_text - lse;
       if (ts_lp > text_lp)
+#pragma unroll 4
         for (int v = tid; v < ts0; v += kRowThreads) s[v] = B2W_LOWEST;
     }
     __syncthreads();
@@ -234,9 +242,11 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
 
   // ---- log-softmax ----
   float mx = -INFINITY;
+#pragma unroll 4
   for (int v = tid; v < V; v += kRowThreads) mx = fmaxf(mx, s[v]);
   mx = block_max(mx, red);
   float sm = 0.f;
+#pragma unroll 4
   for (int v = tid; v < V; v += kRowThreads) sm += __expf(s[v] - mx);
   sm = block_sum(sm, red);
   const float lse = mx + logf(sm);
@@ -246,6 +256,7 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
   const bool sampling = (p.mode == 1 && p.sampling_topk != 1);
   const float inv_t = 1.0f / p.temperature;
   // transform in place to the ranking key; masked entries become -inf so they are never selected before real ones
+#pragma unroll 4
   for (int v = tid; v < V; v += kRowThreads) {
     float x = s[v];
     if (x <= B2W_LOWEST * 0.5f) {
@@ -261,9 +272,21 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
   //      merges the 32 sorted lists (ties -> lower token id, as a stable top-k would) ----
   const int ncand = p.ncand;
   const int warp = tid >> 5, lane = tid & 31;
-  ArgMax mine{-INFINITY, 0x7fffffff};
-  for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
+  // every thread tracks the best two of its own strided slice, so removing a winner rarely needs a rescan
+  ArgMax mine{-INFINITY, 0x7fffffff}, second{-INFINITY, 0x7fffffff};
+#pragma unroll 4
+  for (int v = tid; v < V; v += kRowThreads) {
+    const ArgMax c{s[v], v};
+    if (is_better(c, mine)) {
+      second = mine;
+      mine = c;
+    } else if (is_better(c, second)) {
+      second = c;
+    }
+  }
   if (mine.v == -INFINITY) mine.i = 0x7fffffff;
+  if (second.v == -INFINITY) second.i = 0x7fffffff;
+  bool have_second = true;
   for (int c = 0; c < ncand; ++c) {
     const ArgMax w = warp_argmax(mine);
     if (lane == 0) {
@@ -272,9 +295,15 @@ __global__ void __launch_bounds__(kRowThreads) search_rows_kernel(const float* _
     }
     if (w.i != 0x7fffffff && (w.i % kRowThreads) == tid) {
       s[w.i] = -INFINITY;  // only this thread ever reads or writes this element again
-      mine = ArgMax{-INFINITY, 0x7fffffff};
-      for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
-      if (mine.v == -INFINITY) mine.i = 0x7fffffff;
+      if (have_second) {
+        mine = second;
+        have_second = false;
+      } else {
+        mine = ArgMax{-INFINITY, 0x7fffffff};
+#pragma unroll 4
+        for (int v = tid; v < V; v += kRowThreads) mine = better(mine, ArgMax{s[v], v});
+        if (mine.v == -INFINITY) mine.i = 0x7fffffff;
+      }
     }
   }
   __syncthreads();
