@@ -204,8 +204,14 @@ def run_engine(args):
         import torch
         import torch.distributed as dist
 
+        # NCCL on a real multi-GPU box; B2W_DIST_BACKEND=gloo lets the same code path be exercised with several ranks on one GPU
+        backend = os.environ.get("B2W_DIST_BACKEND", "nccl")
+        local_rank = local_rank % max(1, torch.cuda.device_count())
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
 
     from faster_whisper_b200 import BatchedInferencePipeline, WhisperModel
     from faster_whisper_b200.config import MODEL_DIMS, special_tokens
@@ -252,7 +258,7 @@ def run_engine(args):
         eng.sync()
         dt = time.perf_counter() - t0
         if use_dist:
-            t = torch.tensor([dt], device="cuda")
+            t = torch.tensor([dt], device="cuda" if dist.get_backend() == "nccl" else "cpu")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         return dt
