@@ -4,8 +4,8 @@ The reference loads a CTranslate2 directory (``model.bin`` + ``config.json`` + `
 ``preprocessor_config.json``; ``faster_whisper/utils.py:91-97``, ``transcribe.py:689-710``).  No such checkpoint
 exists offline, so the native on-disk format here is the plainest possible: ``weights.npz`` (OpenAI-Whisper
 state-dict names, float16/float32) + ``b2w_config.json`` (geometry) and, optionally, ``tokenizer.json`` /
-``preprocessor_config.json`` exactly as in a CTranslate2 directory.  A ``model.bin`` reader is SURVEY.md §8(f)
-row 1 ("next").
+``preprocessor_config.json`` exactly as in a CTranslate2 directory.  Directories holding a CTranslate2 ``model.bin`` are
+read through ``ct2_format.py`` (layout restated, unpinned).
 """
 
 from __future__ import annotations
@@ -48,10 +48,31 @@ def load_model_dir(path: str, files: Optional[dict] = None) -> Tuple[WhisperDims
     wts = read("weights.npz")
     if cfg is None or wts is None:
         if read("model.bin") is not None:
-            raise RuntimeError(f"{path} holds a CTranslate2 model.bin; the model.bin reader is not implemented yet "
-                               "(convert to weights.npz + b2w_config.json with faster_whisper_b200.checkpoint.save_model_dir)")
+            # a CTranslate2 directory, as the reference loads it (ct2_format.py; layout restated, unpinned)
+            from .ct2_format import load_ct2_dir
+
+            dims, weights, _ = load_ct2_dir(path, files)
+            return dims, weights
         raise RuntimeError(f"Unable to open file 'weights.npz' in model '{path}'")
     dims = WhisperDims(**json.loads(cfg))
     with np.load(io.BytesIO(wts)) as z:
         weights = {k: z[k] for k in z.files}
     return dims, weights
+
+
+def read_alignment_heads(path: str, files: Optional[dict] = None):
+    """``alignment_heads`` of a model directory's ``config.json`` ([[layer, head], ...]) or None."""
+    blob = None
+    if files and "config.json" in files:
+        blob = files["config.json"]
+        blob = blob.read() if hasattr(blob, "read") else blob
+    elif path and os.path.isfile(os.path.join(path, "config.json")):
+        with open(os.path.join(path, "config.json"), "rb") as f:
+            blob = f.read()
+    if not blob:
+        return None
+    try:
+        heads = json.loads(blob).get("alignment_heads")
+    except ValueError:
+        return None
+    return [tuple(int(x) for x in p) for p in heads] if heads else None

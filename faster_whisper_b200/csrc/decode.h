@@ -143,5 +143,9 @@ void fake_logits(float* logits, int R, const SearchBuffers& b, cudaStream_t s);
 void no_speech_from_logits(const float* logits, int row_stride, int R, int rows_per_chunk, int row_in_chunk, int n_vocab,
                            int no_speech_id, float* out, cudaStream_t s);
 void lang_probs_from_logits(const float* logits, int row_stride, int B, int lang_begin, int n_lang, float* out, cudaStream_t s);
+// Whisper.align helpers (search.cu)
+void row_target_probs(const float* logits, int row_stride, int R, int n_vocab, const int* targets, float* out, cudaStream_t s);
+void align_probs(const __half* q, const DecBindings* bind, int layer, const int2* heads, int n_heads, float* out, int n_tok, int nf,
+                 int pos0, int R, int H, int T, int d, cudaStream_t s);
 
 }  // namespace b2w

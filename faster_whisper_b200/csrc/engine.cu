@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
+#include <limits>
 #include <numeric>
 
 #include "model.h"
@@ -463,6 +465,8 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
     m->d_bar = dalloc<unsigned>(4);
     B2W_CUDA(cudaMemset(m->d_bar, 0, 4 * sizeof(unsigned)));
   }
+  for (int l = L / 2; l < L; ++l)  // default alignment heads: every head of the last half of the decoder (OpenAI Whisper's default)
+    for (int hh = 0; hh < cfg.n_text_head; ++hh) m->align_heads.push_back(make_int2(l, hh));
   B2W_CUDA(cudaStreamSynchronize(m->stream));
 }
 
@@ -827,6 +831,9 @@ static void decoder_layers(Model* m, int n_chunks, int rows_per_chunk, int slots
     GvArgs q;
     q.x = m->d_xn; q.W = W.wq_x; q.bias = W.bq_x; q.R = R; q.N = dt; q.K = dt; q.mode = GV_F16; q.out_h = m->d_q;
     gv(m, q);
+    if (m->align_out)
+      align_probs(m->d_q, m->d_bind, l, m->d_align_heads, (int)m->align_heads.size(), m->align_out, m->align_n_tok, m->align_nf,
+                  m->align_pos0, R, H, 1500, dt, s);
     if (m->use_mma_xattn && splits >= kDsXSplits && dstep_cross_attn_supported(1500, rows_per_chunk)) {
       DStepArgs xa{};
       xa.q = m->d_q; xa.ao = m->d_ao; xa.bind = m->d_bind; xa.xpart = m->d_xpart; xa.xcounters = m->d_counters + 64;
@@ -1501,10 +1508,189 @@ int b2w_detect_language(b2w_model* h, b2w_encoded* enc, float* probs) {
   });
 }
 
-int b2w_align(b2w_model*, b2w_encoded*, int32_t, const int32_t*, int32_t, const int32_t*, int32_t, int32_t, int32_t, int32_t*,
-              int32_t, int32_t*, float*) {
-  g_last_error = "b2w_align (word timestamps) is not implemented yet";
-  return 3;
+// ---- Whisper.align: host-side post-processing (fp64) ------------------------------------------------------------------------
+static void median_filter_rows(std::vector<double>& x, int rows, int cols, int width) {
+  const int pad = width / 2;
+  if (pad == 0 || cols <= pad) return;
+  std::vector<double> row(cols + 2 * pad), win(width), out(cols);
+  for (int r = 0; r < rows; ++r) {
+    double* p = x.data() + (size_t)r * cols;
+    for (int i = 0; i < pad; ++i) {  // reflect (edge sample not repeated)
+      row[pad - 1 - i] = p[i + 1];
+      row[pad + cols + i] = p[cols - 2 - i];
+    }
+    for (int i = 0; i < cols; ++i) row[pad + i] = p[i];
+    for (int i = 0; i < cols; ++i) {
+      for (int k = 0; k < width; ++k) win[k] = row[i + k];
+      std::nth_element(win.begin(), win.begin() + pad, win.end());
+      out[i] = win[pad];
+    }
+    for (int i = 0; i < cols; ++i) p[i] = out[i];
+  }
+}
+
+// monotone minimal-cost path through cost[N][M]; moves diagonal / down / right with the reference tie rule
+static void dtw_path(const std::vector<double>& c, int N, int M, std::vector<int>& ti, std::vector<int>& fi) {
+  const double inf = std::numeric_limits<double>::infinity();
+  std::vector<double> cost((size_t)(N + 1) * (M + 1), inf);
+  std::vector<int8_t> trace((size_t)(N + 1) * (M + 1), -1);
+  auto at = [&](int i, int j) { return (size_t)i * (M + 1) + j; };
+  cost[0] = 0.0;
+  for (int j = 1; j <= M; ++j)
+    for (int i = 1; i <= N; ++i) {
+      const double c0 = cost[at(i - 1, j - 1)], c1 = cost[at(i - 1, j)], c2 = cost[at(i, j - 1)];
+      double best;
+      int8_t t;
+      if (c0 < c1 && c0 < c2) { best = c0; t = 0; }
+      else if (c1 < c0 && c1 < c2) { best = c1; t = 1; }
+      else { best = c2; t = 2; }
+      cost[at(i, j)] = c[(size_t)(i - 1) * M + (j - 1)] + best;
+      trace[at(i, j)] = t;
+    }
+  for (int j = 0; j <= M; ++j) trace[at(0, j)] = 2;
+  for (int i = 0; i <= N; ++i) trace[at(i, 0)] = 1;
+  int i = N, j = M;
+  ti.clear();
+  fi.clear();
+  while (i > 0 || j > 0) {
+    ti.push_back(i - 1);
+    fi.push_back(j - 1);
+    const int8_t t = trace[at(i, j)];
+    if (t == 0) { --i; --j; }
+    else if (t == 1) --i;
+    else --j;
+  }
+  std::reverse(ti.begin(), ti.end());
+  std::reverse(fi.begin(), fi.end());
+}
+
+int b2w_model_set_alignment_heads(b2w_model* h, const int32_t* layer_head_pairs, int32_t n_pairs) {
+  return guarded([&] {
+    B2W_CHECK(h && (n_pairs == 0 || layer_head_pairs) && n_pairs >= 0 && n_pairs <= 32 * 32, "bad arguments");
+    Model* m = &h->m;
+    std::lock_guard<std::mutex> lk(m->mu);
+    std::vector<int2> v;
+    for (int i = 0; i < n_pairs; ++i) {
+      const int l = layer_head_pairs[2 * i], hd = layer_head_pairs[2 * i + 1];
+      if (l < 0 || l >= m->cfg.n_text_layer || hd < 0 || hd >= m->cfg.n_text_head) throw Error("alignment head out of range", true);
+      v.push_back(make_int2(l, hd));
+    }
+    if (v.empty())
+      for (int l = m->cfg.n_text_layer / 2; l < m->cfg.n_text_layer; ++l)
+        for (int hd = 0; hd < m->cfg.n_text_head; ++hd) v.push_back(make_int2(l, hd));
+    m->align_heads = v;
+    if (m->d_align_heads) {
+      DeviceGuard g(m->device);
+      cudaFree(m->d_align_heads);
+      m->d_align_heads = nullptr;
+    }
+  });
+}
+
+int b2w_align(b2w_model* h, b2w_encoded* enc, int32_t batch_index, const int32_t* start_sequence, int32_t n_start,
+              const int32_t* text_tokens, int32_t n_text, int32_t num_frames, int32_t median_filter_width, int32_t* alignments_out,
+              int32_t capacity_pairs, int32_t* n_pairs_out, float* text_token_probs_out) {
+  return guarded([&] {
+    B2W_CHECK(h && enc && enc->e && start_sequence && n_pairs_out && n_start >= 1 && n_text >= 0, "bad arguments");
+    Model* m = &h->m;
+    const b2w_config& c = m->cfg;
+    Encoded* e = enc->e;
+    if (batch_index < 0 || batch_index >= e->B) throw Error("align: batch index out of range", true);
+    if (median_filter_width < 1 || median_filter_width % 2 == 0) throw Error("align: median_filter_width must be odd", true);
+    *n_pairs_out = 0;
+    if (n_text == 0) return;
+    B2W_CHECK(text_tokens && text_token_probs_out && (alignments_out || capacity_pairs == 0), "bad arguments");
+    // forced sequence: start_sequence + <|notimestamps|> + text + <|endoftext|>
+    std::vector<int32_t> seq(start_sequence, start_sequence + n_start);
+    seq.push_back(c.no_timestamps);
+    const int n_head_rows = (int)seq.size();
+    seq.insert(seq.end(), text_tokens, text_tokens + n_text);
+    seq.push_back(c.eot);
+    const int n_tok = (int)seq.size();
+    if (n_tok > c.n_text_ctx) throw Error("align: start sequence + text exceed the decoder context", true);
+    for (int t : seq)
+      if (t < 0 || t >= c.n_vocab) throw Error("align: token id out of range", true);
+    const int nf = std::max(1, std::min(1500, (int)num_frames / 2));
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    cudaStream_t s = m->stream;
+    ensure_cross_kv(m, e);
+    ensure_decoder_ws(m, 1, 1);
+    ensure_search_ws(m, 1, 1);
+    const int n_heads = (int)m->align_heads.size();
+    B2W_CHECK(n_heads > 0, "no alignment heads");
+    if (!m->d_align_heads) {
+      m->d_align_heads = dalloc<int2>(n_heads);
+      B2W_CUDA(cudaMemcpy(m->d_align_heads, m->align_heads.data(), n_heads * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    const size_t n_att = (size_t)n_heads * n_tok * nf;
+    float* d_att = reinterpret_cast<float*>(m->pool_get(n_att * sizeof(float)));
+    int* d_targets = reinterpret_cast<int*>(m->pool_get((size_t)n_tok * sizeof(int)));
+    float* d_tp = reinterpret_cast<float*>(m->pool_get((size_t)n_tok * sizeof(float)));
+    std::vector<int> targets(n_tok, -1);
+    for (int t = 0; t < n_text; ++t) targets[n_head_rows - 1 + t] = text_tokens[t];  // position p predicts token p + 1
+    B2W_CUDA(cudaMemcpyAsync(d_targets, targets.data(), (size_t)n_tok * sizeof(int), cudaMemcpyHostToDevice, s));
+    B2W_CUDA(cudaMemsetAsync(d_tp, 0, (size_t)n_tok * sizeof(float), s));
+    B2W_CUDA(cudaMemsetAsync(m->sb.anc, 0, (size_t)2 * c.n_text_ctx, s));
+    std::vector<int32_t> padded((size_t)(batch_index + 1) * n_tok, 0);  // prefill_pass indexes tokens by absolute chunk
+    std::copy(seq.begin(), seq.end(), padded.begin() + (size_t)batch_index * n_tok);
+    m->align_out = d_att;
+    m->align_n_tok = n_tok;
+    m->align_nf = nf;
+    try {
+      for (int i0 = 0; i0 < n_tok; i0 += kMaxRows) {
+        const int i1 = std::min(n_tok, i0 + kMaxRows);
+        m->align_pos0 = i0;
+        prefill_pass(m, e, batch_index, 1, padded.data(), n_tok, i0, i1, 1, 0);
+        logits_gemm(m, i1 - i0);
+        row_target_probs(m->d_logits, m->vpad, i1 - i0, c.n_vocab, d_targets + i0, d_tp + i0, s);
+      }
+    } catch (...) {
+      m->align_out = nullptr;
+      throw;
+    }
+    m->align_out = nullptr;
+    std::vector<float> att(n_att), tp(n_tok);
+    B2W_CUDA(cudaMemcpyAsync(att.data(), d_att, n_att * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2W_CUDA(cudaMemcpyAsync(tp.data(), d_tp, (size_t)n_tok * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B2W_CUDA(cudaStreamSynchronize(s));
+    m->pool_put(d_att, n_att * sizeof(float));
+    m->pool_put(d_targets, (size_t)n_tok * sizeof(int));
+    m->pool_put(d_tp, (size_t)n_tok * sizeof(float));
+    for (int t = 0; t < n_text; ++t) text_token_probs_out[t] = tp[n_head_rows - 1 + t];
+    // per head: normalise over the token axis (population std), median filter along time; then the head mean
+    std::vector<double> mean_w((size_t)n_tok * nf, 0.0), w((size_t)n_tok * nf);
+    for (int hd = 0; hd < n_heads; ++hd) {
+      const float* a = att.data() + (size_t)hd * n_tok * nf;
+      for (int f = 0; f < nf; ++f) {
+        double mu = 0.0, var = 0.0;
+        for (int t = 0; t < n_tok; ++t) mu += a[(size_t)t * nf + f];
+        mu /= n_tok;
+        for (int t = 0; t < n_tok; ++t) {
+          const double dlt = a[(size_t)t * nf + f] - mu;
+          var += dlt * dlt;
+        }
+        const double sd = std::sqrt(var / n_tok);
+        for (int t = 0; t < n_tok; ++t) w[(size_t)t * nf + f] = (a[(size_t)t * nf + f] - mu) / sd;
+      }
+      median_filter_rows(w, n_tok, nf, median_filter_width);
+      for (size_t i = 0; i < w.size(); ++i) mean_w[i] += w[i];
+    }
+    // rows of the inputs that predict text + eot (drop the start-sequence rows and the eot input row: the consumer indexes
+    // word boundaries up to n_text, transcribe.py:1744-1746), negated, DTW
+    const int n_rows = n_text + 1;
+    std::vector<double> cost((size_t)n_rows * nf);
+    for (int t = 0; t < n_rows; ++t)
+      for (int f = 0; f < nf; ++f) cost[(size_t)t * nf + f] = -mean_w[(size_t)(n_start + t) * nf + f] / n_heads;
+    std::vector<int> ti, fi;
+    dtw_path(cost, n_rows, nf, ti, fi);
+    *n_pairs_out = (int32_t)ti.size();
+    if ((int)ti.size() > capacity_pairs) throw Error("align: alignment buffer too small", true);
+    for (size_t i = 0; i < ti.size(); ++i) {
+      alignments_out[2 * i] = ti[i];
+      alignments_out[2 * i + 1] = fi[i];
+    }
+  });
 }
 
 int b2w_timing_enable(b2w_model* h, int32_t on) {

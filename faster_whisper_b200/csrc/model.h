@@ -109,6 +109,12 @@ struct Model {
   int* d_counters = nullptr;  // [0]: GEMM ticket, [64..]: cross-attention groups
   uint8_t* d_suppress = nullptr;
   DecBindings* d_bind = nullptr;
+  // Whisper.align: (layer, head) pairs whose cross-attention is captured; while `align_out` is set, decoder_layers() writes
+  // the probabilities of the forced-decoding rows there
+  std::vector<int2> align_heads;
+  int2* d_align_heads = nullptr;
+  float* align_out = nullptr;
+  int align_n_tok = 0, align_nf = 0, align_pos0 = 0;
   __half* logit_tiles = nullptr;  // output embedding as the persistent step kernel's tile stream
   DLayer* d_layers = nullptr;   // device copy of the decoder layer pointer table (persistent step kernel)
   unsigned* d_bar = nullptr;

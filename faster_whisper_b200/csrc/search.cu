@@ -558,6 +558,77 @@ void no_speech_from_logits(const float* logits, int row_stride, int R, int rows_
   B2W_LAUNCHED();
 }
 
+// softmax probability of a per-row target token (text_token_probs of Whisper.align); rows with target < 0 are skipped
+__global__ void row_target_prob_kernel(const float* __restrict__ logits, int row_stride, int n_vocab, const int* __restrict__ targets,
+                                       float* __restrict__ out) {
+  __shared__ float red[32];
+  const int r = blockIdx.x, tok = targets[r];
+  if (tok < 0) return;
+  const float* row = logits + (long long)r * row_stride;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < n_vocab; v += blockDim.x) mx = fmaxf(mx, row[v]);
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int v = threadIdx.x; v < n_vocab; v += blockDim.x) sm += __expf(row[v] - mx);
+  sm = block_sum(sm, red);
+  if (threadIdx.x == 0) out[r] = __expf(row[tok] - mx) / sm;
+}
+void row_target_probs(const float* logits, int row_stride, int R, int n_vocab, const int* targets, float* out, cudaStream_t s) {
+  row_target_prob_kernel<<<R, 1024, 0, s>>>(logits, row_stride, n_vocab, targets, out);
+  B2W_LAUNCHED();
+}
+
+// Cross-attention probabilities of the alignment heads of one layer for forced-decoding rows (Whisper.align): CTA per
+// (alignment head, row); softmax over all T encoder positions, the first nf written out as out[head][pos0 + row][t].
+// K rows are stored with their 16-byte chunks at chunk ^ (t & 7) (gemm.cu EPI_F16_XKV).
+__global__ void __launch_bounds__(256) align_probs_kernel(const __half* __restrict__ q, const DecBindings* __restrict__ bind, int layer,
+                                                          const int2* __restrict__ heads, float* __restrict__ out, int n_tok, int nf,
+                                                          int pos0, int H, int T, int d) {
+  const int2 lh = heads[blockIdx.x];
+  if (lh.x != layer) return;
+  __shared__ float qs[64];
+  __shared__ float sc[1536];
+  __shared__ float red[32];
+  const int r = blockIdx.y, h = lh.y, tid = threadIdx.x;
+  const DecBindings bd = *bind;
+  const long long per = (long long)bd.B_total * H * T * 64;
+  const __half* Kb = bd.xkv + ((long long)layer * 2 + 0) * per + (((long long)bd.chunk0 * H + h) * T) * 64;
+  if (tid < 64) qs[tid] = __half2float(q[(long long)r * d + h * 64 + tid]) * 0.125f;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = tid; t < T; t += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(Kb + (long long)t * 64 + ((c ^ (t & 7)) << 3));
+      const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(k2[e]);
+        s = fmaf(f.x, qs[c * 8 + 2 * e], fmaf(f.y, qs[c * 8 + 2 * e + 1], s));
+      }
+    }
+    sc[t] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_max(mx, red);
+  float sm = 0.f;
+  for (int t = tid; t < T; t += 256) {
+    const float e = __expf(sc[t] - mx);
+    sc[t] = e;
+    sm += e;
+  }
+  sm = block_sum(sm, red);
+  float* o = out + ((long long)blockIdx.x * n_tok + pos0 + r) * nf;
+  for (int t = tid; t < nf; t += 256) o[t] = sc[t] / sm;
+}
+void align_probs(const __half* q, const DecBindings* bind, int layer, const int2* heads, int n_heads, float* out, int n_tok, int nf,
+                 int pos0, int R, int H, int T, int d, cudaStream_t s) {
+  B2W_CHECK(T <= 1536, "align_probs: encoder length");
+  align_probs_kernel<<<dim3(n_heads, R), 256, 0, s>>>(q, bind, layer, heads, out, n_tok, nf, pos0, H, T, d);
+  B2W_LAUNCHED();
+}
+
 __global__ void lang_probs_kernel(const float* __restrict__ logits, int row_stride, int lang_begin, int n_lang,
                                   float* __restrict__ out) {
   __shared__ float red[32];

@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
     "b2w_last_error", "b2w_abi_version", "b2w_device_count", "b2w_model_create", "b2w_model_destroy",
     "b2w_model_info", "b2w_model_sync", "b2w_logmel", "b2w_logmel_frames", "b2w_encode", "b2w_encode_audio",
     "b2w_encoded_shape", "b2w_encoded_to_host", "b2w_encoded_free", "b2w_generate", "b2w_gen_opts_default",
-    "b2w_detect_language", "b2w_align", "b2w_timing_enable", "b2w_timing_reset", "b2w_timing_get",
+    "b2w_detect_language", "b2w_align", "b2w_model_set_alignment_heads", "b2w_timing_enable", "b2w_timing_reset", "b2w_timing_get",
     "b2w_counters_get", "b2w_debug_gemm", "b2w_debug_attention", "b2w_debug_gemv", "b2w_debug_logits",
 )
 
@@ -100,6 +100,9 @@ def load_library():
         lib.b2w_gen_opts_default.argtypes = [C.POINTER(_GenOpts)]
         lib.b2w_gen_opts_default.restype = None
         lib.b2w_detect_language.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b2w_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]
+        lib.b2w_model_set_alignment_heads.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         lib.b2w_timing_enable.argtypes = [C.c_void_p, C.c_int32]
         lib.b2w_timing_reset.argtypes = [C.c_void_p]
         lib.b2w_timing_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -256,6 +259,9 @@ class Whisper:
             from .checkpoint import load_model_dir
 
             dims, weights = load_model_dir(model_path, files)
+            from .checkpoint import read_alignment_heads
+
+            self._config_alignment_heads = read_alignment_heads(model_path, files)
         self.dims = dims
         self.tokens = tokens or special_tokens(dims.n_vocab)
         cfg = _Config()
@@ -291,6 +297,8 @@ class Whisper:
         self._keep = []  # weights are on the device now
         self._rr = 0
         self._rr_lock = threading.Lock()
+        if getattr(self, "_config_alignment_heads", None):
+            self.set_alignment_heads(self._config_alignment_heads)
 
     # ---- read-only properties faster-whisper touches (transcribe.py:379,472,1394) ----
     @property
@@ -452,7 +460,32 @@ class Whisper:
 
     # ---- align (transcribe.py:1709-1715) ----
     def align(self, features, start_sequence, text_tokens, num_frames, *, median_filter_width: int = 7):
-        raise NotImplementedError("Whisper.align (word timestamps) is not implemented in this engine yet")
+        """``ctranslate2.models.Whisper.align`` (transcribe.py:1709-1715): one result per batch item with ``.alignments``
+        (list of (text_token_index, time_index)) and ``.text_token_probs``."""
+        enc = self._as_encoded(features)
+        rep = self._replica_for(enc)
+        start = np.ascontiguousarray(list(start_sequence), dtype=np.int32)
+        if len(text_tokens) != enc.shape[0]:
+            raise ValueError("align: one text token list per batch item is required")
+        results = []
+        for b, toks in enumerate(text_tokens):
+            nf = int(num_frames[b] if isinstance(num_frames, (list, tuple)) else num_frames)
+            toks = np.ascontiguousarray(list(toks), dtype=np.int32)
+            cap = len(toks) + nf // 2 + 2
+            pairs = np.zeros((cap, 2), np.int32)
+            probs = np.zeros(max(1, len(toks)), np.float32)
+            n_pairs = C.c_int32(0)
+            with rep.lock:
+                _check(rep._lib.b2w_align(rep._h, enc._handle, b, _ptr(start), len(start), _ptr(toks), len(toks), nf, int(median_filter_width),
+                                          _ptr(pairs), cap, C.byref(n_pairs), _ptr(probs)))
+            results.append(WhisperAlignmentResult([(int(a), int(t)) for a, t in pairs[: n_pairs.value]], [float(p) for p in probs[: len(toks)]]))
+        return results
+
+    def set_alignment_heads(self, heads=None):
+        """(layer, head) pairs from a converted model's config.json ``alignment_heads``; None restores the default."""
+        flat = np.ascontiguousarray([x for p in (heads or []) for x in p], dtype=np.int32)
+        for rep in self._replicas:
+            _check(rep._lib.b2w_model_set_alignment_heads(rep._h, _ptr(flat) if flat.size else None, flat.size // 2))
 
     # ---- measurement / test hooks ----
     def timing(self, enable: Optional[bool] = None, reset: bool = False, replica: int = 0) -> Dict[str, float]:

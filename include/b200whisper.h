@@ -126,12 +126,21 @@ void b2w_gen_opts_default(b2w_gen_opts* o);
 int b2w_detect_language(b2w_model* m, b2w_encoded* e, float* probs);
 
 /* Whisper.align(encoder_output, start_sequence, text_tokens, num_frames, median_filter_width=7)
- * (transcribe.py:1709-1715): for one batch item, DTW over median-filtered cross-attention of the
- * alignment heads.  alignments_out: pairs (text_idx, time_idx), capacity in pairs. */
+ * (transcribe.py:1709-1715; consumer :1698-1766) for ONE batch item: teacher-forces
+ * start_sequence + <|notimestamps|> + text_tokens + <|endoftext|>, captures the cross-attention probabilities of
+ * the alignment heads over the first num_frames/2 encoder positions, normalises them over the token axis,
+ * median-filters along time, averages the heads and runs DTW.  alignments_out receives n_pairs_out pairs
+ * (text_index, time_index) over the n_text + 1 rows that predict text + eot, capacity in pairs
+ * (n_text + 1 + num_frames/2 always suffices);
+ * text_token_probs_out[n_text] = softmax probability of each text token at the position predicting it. */
 int b2w_align(b2w_model* m, b2w_encoded* e, int32_t batch_index, const int32_t* start_sequence,
               int32_t n_start, const int32_t* text_tokens, int32_t n_text, int32_t num_frames,
               int32_t median_filter_width, int32_t* alignments_out, int32_t capacity_pairs,
               int32_t* n_pairs_out, float* text_token_probs_out);
+
+/* config.json "alignment_heads" of a converted model (transcribe.py:700-710 reads the model directory): n_pairs
+ * (layer, head) pairs; n_pairs = 0 restores the default (every head of the last half of the decoder layers). */
+int b2w_model_set_alignment_heads(b2w_model* m, const int32_t* layer_head_pairs, int32_t n_pairs);
 
 /* ---- measurement --------------------------------------------------------------------------------
  * CUDA-event stage timers accumulated since the last reset (the roofline report in bench.py). */

@@ -76,8 +76,11 @@ def make_whisper_class(dims, weights, calls=None):
             names = (LANGUAGE_CODES + ["xx1", "xx2", "xx3"])
             return [[(f"<|{names[i - st.lang_begin]}|>", p) for i, p in row] for row in oracle.detect_language(enc)]
 
-        def align(self, *a, **k):
-            raise NotImplementedError
+        def align(self, features, start_sequence, text_tokens, num_frames, median_filter_width=7):
+            if calls is not None:
+                calls.append(("align", list(start_sequence), [list(t) for t in text_tokens], num_frames, median_filter_width))
+            enc = features.tensor if features.tensor is not None else oracle.encode(features.array)
+            return oracle.align(enc, start_sequence, text_tokens, num_frames, median_filter_width)
 
         def encode_audio(self, chunks, return_features=False):
             from oracle.whisper_oracle import log_mel, pad_or_trim

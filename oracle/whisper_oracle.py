@@ -564,3 +564,94 @@ class WhisperOracle:
             order = np.argsort(-pr[b], kind="stable")
             out.append([(ids[i], float(pr[b, i])) for i in order])
         return out
+
+    # ---- word-level alignment (CT2 Whisper.align; consumer at transcribe.py:1698-1766) ---------------------------------
+    def default_alignment_heads(self) -> List[Tuple[int, int]]:
+        """Every head of the last half of the decoder layers (OpenAI Whisper's default when a checkpoint lists none)."""
+        L, H = self.dims["n_text_layer"], self.dims["n_text_head"]
+        return [(l, h) for l in range(L // 2, L) for h in range(H)]
+
+    @torch.no_grad()
+    def align(self, enc: torch.Tensor, start_sequence: Sequence[int], text_tokens: Sequence[Sequence[int]], num_frames,
+              median_filter_width: int = 7, alignment_heads: Optional[Sequence[Tuple[int, int]]] = None) -> List["AlignmentResult"]:
+        """Restated (parity unpinned): teacher-force ``start_sequence + [no_timestamps] + text + [eot]``, take
+        the cross-attention probabilities of the alignment heads over the first ``num_frames // 2`` encoder positions,
+        normalise over the token axis (population std), median-filter along time (reflect padding), average the heads, keep
+        the rows of the inputs that predict ``text + [eot]`` (drop the start-sequence rows and the eot input row: the consumer
+        indexes word boundaries up to len(text), transcribe.py:1744-1746), DTW on the negated matrix.  ``text_token_probs[t]`` is the full-vocabulary
+        softmax probability of text token t at the position that predicts it."""
+        tok = self.tok
+        heads = list(alignment_heads) if alignment_heads is not None else self.default_alignment_heads()
+        out = []
+        for b, toks in enumerate(text_tokens):
+            nf = int(num_frames[b] if isinstance(num_frames, (list, tuple)) else num_frames)
+            start = list(start_sequence) + [tok["no_timestamps"]]
+            seq = start + list(toks) + [tok["eot"]]
+            xkv = self.cross_kv(enc[b : b + 1])
+            cache: list = [None] * self.dims["n_text_layer"]
+            logits, atts = self.decoder_forward(torch.tensor([seq], dtype=torch.long), 0, cache, xkv, torch.zeros(1, dtype=torch.long),
+                                                want_cross_att=True)
+            probs = torch.softmax(logits[0].double(), dim=-1)
+            tprobs = [float(probs[len(start) - 1 + t, toks[t]]) for t in range(len(toks))]
+            w = torch.stack([atts[l][0, h] for l, h in heads]).double()[:, :, : max(1, nf // 2)]
+            mean = w.mean(dim=-2, keepdim=True)
+            std = w.std(dim=-2, keepdim=True, unbiased=False)
+            w = (w - mean) / std
+            w = median_filter(w.numpy(), median_filter_width)
+            m = w.mean(axis=0)[len(start_sequence) : -1]  # inputs <|notimestamps|>, text[0..n-2], text[n-1]: the rows predicting text + eot
+            ti, fi = dtw(-m)
+            out.append(AlignmentResult(alignments=list(zip(ti.tolist(), fi.tolist())), text_token_probs=tprobs))
+        return out
+
+
+@dataclass
+class AlignmentResult:
+    alignments: List[Tuple[int, int]]
+    text_token_probs: List[float]
+
+
+def median_filter(x: np.ndarray, width: int) -> np.ndarray:
+    """Median over a sliding window of odd `width` along the last axis, reflect padding; rows shorter than the padding are
+    returned unchanged."""
+    pad = width // 2
+    if pad == 0 or x.shape[-1] <= pad:
+        return x
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(pad, pad)], mode="reflect")
+    win = np.lib.stride_tricks.sliding_window_view(xp, width, axis=-1)
+    return np.sort(win, axis=-1)[..., pad]
+
+
+def dtw(cost_in: np.ndarray):
+    """Monotone path of minimal accumulated cost through [N, M] (moves: diagonal, down, right; ties prefer the right move
+    unless the diagonal is strictly best, then the down move)."""
+    N, M = cost_in.shape
+    cost = np.full((N + 1, M + 1), np.inf)
+    trace = np.full((N + 1, M + 1), -1, dtype=np.int64)
+    cost[0, 0] = 0.0
+    for j in range(1, M + 1):
+        for i in range(1, N + 1):
+            c0, c1, c2 = cost[i - 1, j - 1], cost[i - 1, j], cost[i, j - 1]
+            if c0 < c1 and c0 < c2:
+                c, t = c0, 0
+            elif c1 < c0 and c1 < c2:
+                c, t = c1, 1
+            else:
+                c, t = c2, 2
+            cost[i, j] = cost_in[i - 1, j - 1] + c
+            trace[i, j] = t
+    i, j = N, M
+    trace[0, :] = 2
+    trace[:, 0] = 1
+    ti, fi = [], []
+    while i > 0 or j > 0:
+        ti.append(i - 1)
+        fi.append(j - 1)
+        t = trace[i, j]
+        if t == 0:
+            i -= 1
+            j -= 1
+        elif t == 1:
+            i -= 1
+        else:
+            j -= 1
+    return np.array(ti[::-1]), np.array(fi[::-1])

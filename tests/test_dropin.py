@@ -118,3 +118,25 @@ def test_detect_language_matches_reference(both):
     a = ref_model.detect_language(audio=audio, language_detection_segments=2, language_detection_threshold=0.99)
     b = our_model.detect_language(audio=audio, language_detection_segments=2, language_detection_threshold=0.99)
     assert a[0] == b[0] and a[1] == pytest.approx(b[1]) and [x[0] for x in a[2]] == [x[0] for x in b[2]]
+
+
+def word_tuple(w):
+    return (round(float(w.start), 3), round(float(w.end), 3), w.word, round(float(w.probability), 5))
+
+
+def test_word_timestamps_match_reference(both):
+    """word_timestamps=True: both host layers call Whisper.align over the shim and post-process its alignments
+    (merge punctuation, duration clamps, segment boundary fix-ups — transcribe.py:1567-1766)."""
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(80, 30.0), synthetic_audio(81, 9.0)])
+    kw = dict(language="en", beam_size=2, max_new_tokens=10, word_timestamps=True, **COMMON)
+    calls_ref.clear()
+    calls_our.clear()
+    ref_segs, _ = ref_model.transcribe(audio.copy(), **kw)
+    ref = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in ref_segs]
+    our_segs, _ = our_model.transcribe(audio.copy(), **kw)
+    our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in our_segs]
+    assert our == ref
+    assert any(c[0] == "align" for c in calls_ref)
+    assert strip(calls_our) == strip(calls_ref)
+    assert sum(len(w) for _, w in ref) > 0

@@ -221,3 +221,66 @@ def test_persistent_step_matches_multikernel_path(micro_ml, beam, n_chunks):
         else:
             assert abs(x.scores[0] - y.scores[0]) < 2e-3 and abs(x.scores[0] - w.scores[0]) < 0.05
         assert abs(x.no_speech_prob - w.no_speech_prob) < 5e-3 * max(1.0, w.no_speech_prob) + 1e-6
+
+
+# ---- Whisper.align (word timestamps): cross-attention capture + DTW vs the oracle ---------------------------------------------
+def _jump_frames(pairs, n_rows):
+    first = {}
+    for t, f in pairs:
+        first.setdefault(t, f)
+    return [first[t] for t in range(n_rows)]
+
+
+@pytest.mark.parametrize("heads", [None, [(1, 0), (1, 1), (0, 1)]])
+def test_align_matches_oracle(micro_ml, eng_ml, heads):
+    st = micro_ml["tokens"]
+    o = micro_ml["oracle"]
+    feats = features_for(micro_ml, 2, seed=60)
+    rng = np.random.default_rng(3)
+    text = [rng.integers(100, 5000, 14).tolist(), rng.integers(100, 5000, 6).tolist()]
+    frames = [3000, 1800]
+    start = [st.sot, st.lang_begin, st.transcribe]
+    want = o.align(o.encode(feats), start, text, frames, 7, alignment_heads=heads)
+    eng_ml.set_alignment_heads(heads)
+    try:
+        got = eng_ml.align(eng_ml.encode(feats), start, text, frames, median_filter_width=7)
+    finally:
+        eng_ml.set_alignment_heads(None)
+    for w, g, toks, nf in zip(want, got, text, frames):
+        assert np.allclose(g.text_token_probs, w.text_token_probs, rtol=0.1, atol=1e-6), (g.text_token_probs, w.text_token_probs)
+        gi, wi = np.array(g.alignments), np.array(w.alignments)
+        # a valid monotone path over the n_text + 1 rows and nf // 2 frames
+        assert gi[0].tolist() == [0, 0] and gi[-1].tolist() == [len(toks), nf // 2 - 1]
+        assert (np.diff(gi, axis=0) >= 0).all() and (np.diff(gi, axis=0).sum(axis=1) >= 1).all()
+        # the token boundaries (what word timestamps are made of) agree with the oracle's within two frames (40 ms)
+        gj, wj = _jump_frames(g.alignments, len(toks) + 1), _jump_frames(w.alignments, len(toks) + 1)
+        close = sum(abs(a - b) <= 2 for a, b in zip(gj, wj))
+        assert close >= len(gj) - 1, (gj, wj)
+    with pytest.raises(ValueError):
+        eng_ml.align(eng_ml.encode(feats), start, [text[0]], frames)
+
+
+def test_transcribe_word_timestamps_end_to_end(micro_ml):
+    """WhisperModel.transcribe(word_timestamps=True) on the CUDA engine: generate -> align -> words (transcribe.py:1567-1766)."""
+    import json
+
+    from faster_whisper_b200 import BatchedInferencePipeline, WhisperModel
+    from faster_whisper_b200.synthetic import make_tokenizer
+
+    dims = micro_ml["dims"]
+    files = {"tokenizer.json": make_tokenizer(dims.n_vocab).to_str().encode(),
+             "preprocessor_config.json": json.dumps({"feature_size": dims.n_mels}).encode()}
+    model = WhisperModel("synthetic", device="cuda", files=files, dims=dims, weights=micro_ml["weights"])
+    audio = np.concatenate([synthetic_audio(90, 30.0), synthetic_audio(91, 12.0)])
+    kw = dict(language="en", beam_size=2, max_new_tokens=12, word_timestamps=True, no_speech_threshold=None, log_prob_threshold=None,
+              compression_ratio_threshold=None)
+    segs, info = model.transcribe(audio, **kw)
+    segs = list(segs)
+    words = [w for s in segs for w in (s.words or [])]
+    assert len(segs) >= 2 and len(words) > 0
+    assert all(0.0 <= w.start <= w.end <= info.duration + 1e-6 and 0.0 <= w.probability <= 1.0 for w in words)
+    clips = [{"start": 0.0, "end": 30.0}, {"start": 30.0, "end": 42.0}]
+    bsegs, _ = BatchedInferencePipeline(model).transcribe(audio, batch_size=2, vad_filter=False, clip_timestamps=clips, language="en",
+                                                          beam_size=2, max_new_tokens=12, word_timestamps=True)
+    bwords = [w for s in bsegs for w in (s.words or [])]
+    assert len(bwords) > 0 and all(w.start <= w.end for w in bwords)

@@ -134,3 +134,32 @@ def test_tokenizer_wrapper(tok):
         Tokenizer(tok.tokenizer, True, task="transcribe", language="klingon")
     en = Tokenizer(make_tokenizer(51864), False)
     assert en.sot_sequence == [50257] and en.language_code == "en"
+
+
+# ---- CTranslate2 model directory (model.bin) reader/writer round trip --------------------------------------------------------
+def test_ct2_model_bin_round_trip(tmp_path):
+    from faster_whisper_b200 import checkpoint, ct2_format
+    from faster_whisper_b200.synthetic import custom_dims, make_weights
+
+    dims = custom_dims(name="rt", n_mels=80, d=64, heads=1, enc_layers=2, dec_layers=2, n_vocab=51864)
+    w = make_weights(dims, seed=3)
+    d = tmp_path / "m"
+    ct2_format.save_ct2_dir(str(d), dims, w, alignment_heads=[(1, 0)], dtype=np.float32)
+    spec, rev, variables, aliases = ct2_format.read_model_bin(str(d / "model.bin"))
+    assert spec == "WhisperSpec" and aliases["decoder/projection/weight"] == "decoder/embeddings/weight"
+    assert variables["decoder/layer_1/attention/linear_1/weight"].shape == (2 * dims.n_text_state, dims.n_text_state)
+    dims2, w2 = checkpoint.load_model_dir(str(d))
+    assert dims2.to_dict() | {"name": "x"} == dims.to_dict() | {"name": "x"}
+    assert set(w2) == set(w)
+    for k in w:
+        assert np.array_equal(w2[k], w[k].astype(np.float32)), k
+    assert checkpoint.read_alignment_heads(str(d)) == [(1, 0)]
+    # int8 storage with per-row scales de-quantises to within half a quantisation step
+    d8 = tmp_path / "m8"
+    ct2_format.save_ct2_dir(str(d8), dims, w, quantize_int8=True)
+    _, w8 = checkpoint.load_model_dir(str(d8))
+    k = "decoder.blocks.0.mlp.0.weight"
+    step = np.abs(w[k]).max(axis=1, keepdims=True) / 127.0
+    assert np.all(np.abs(w8[k] - w[k]) <= 0.5 * step + 1e-7)
+    with pytest.raises(ValueError):
+        ct2_format.read_model_bin(b"\\xff\\xff\\xff\\xff garbage")
