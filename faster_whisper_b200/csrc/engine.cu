@@ -761,6 +761,7 @@ static const GemmPlan& dec_plan(Model* m, const GvArgs& a) {
   g.N = a.N;
   g.rows = a.R;
   g.bias = a.bias;
+  g.narrow_tiles = true;
   switch (a.mode) {
     case GV_QKV:
       g.epilogue = EPI_QKV_CACHE;
@@ -774,7 +775,15 @@ static const GemmPlan& dec_plan(Model* m, const GvArgs& a) {
       break;
     case GV_F16: g.epilogue = EPI_F16; g.out = a.out_h; g.out_ld = a.N; break;
     case GV_GELU_F16: g.epilogue = EPI_GELU_F16; g.out = a.out_h; g.out_ld = a.N; break;
-    case GV_RESID_LN: g.epilogue = EPI_RESID_F32; g.out = a.xres; g.resid = a.xres; g.out_ld = a.N; break;
+    case GV_RESID_LN: {
+      // x += y W^T: four K ranges reduced in place with fp32 atomics when the K blocks allow it (more CTAs streaming the weights)
+      const int num_kb = a.K / 64;
+      const int ks = num_kb % 4 == 0 ? 4 : (num_kb % 2 == 0 ? 2 : 1);
+      g.epilogue = ks > 1 ? EPI_RESID_ATOMIC : EPI_RESID_F32;
+      g.ksplit = ks;
+      g.out = a.xres; g.resid = a.xres; g.out_ld = a.N;
+      break;
+    }
     case GV_F32: g.epilogue = EPI_F32; g.out = a.out_f; g.out_ld = a.ldo; break;
   }
   return m->dec_plans.emplace(key, gemm_plan(g, m->num_sms)).first->second;

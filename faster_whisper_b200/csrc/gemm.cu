@@ -19,7 +19,7 @@ constexpr int BK = 64;
 constexpr int kGemmThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
 
 struct GemmDev {
-  int batch, tiles_m, tiles_n, num_kb, kb_per_tap;
+  int batch, tiles_m, tiles_n, num_kb, kb_per_tap, ksplit;
   int tap_row[3], tap_col[3];
   int rows, N;
   const float* bias;
@@ -35,11 +35,11 @@ struct GemmDev {
 };
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row, int n0, const uint32_t* vraw) {
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row, int n0, const uint32_t* vraw, bool with_bias) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vraw[i]);
-  if (p.bias) {
+  if (p.bias && with_bias) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -94,7 +94,10 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row,
   } else {
     const long long idx = (long long)b * p.out_batch_stride + (long long)row * p.out_ld + n0;
     float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + idx);
-    if constexpr (EPI == EPI_RESID_F32) {
+    if constexpr (EPI == EPI_RESID_ATOMIC) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(o4 + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+    } else if constexpr (EPI == EPI_RESID_F32) {
       const float4* r4 = reinterpret_cast<const float4*>(p.resid + idx);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -118,12 +121,12 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, int b, int row,
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t IDESC = umma_idesc_f16(BM, BN, false);
-  constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: two accumulator buffers
+  constexpr int TMEM_COLS = 2 * BN;  // 64, 256 or 512: two accumulator buffers
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.batch * p.tiles_m * p.tiles_n;
+  const int total_tiles = p.batch * p.tiles_m * p.tiles_n * p.ksplit;  // tile = ((b * tiles_m + m) * tiles_n + n) * ksplit + ks
 
   if (warp == 0) {
     if (lane == 0) {
@@ -159,10 +162,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_idx = tile % p.tiles_n;
-        const int rest = tile / p.tiles_n;
+        const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
+        const int n_idx = t2 % p.tiles_n;
+        const int rest = t2 / p.tiles_n;
         const int m_idx = rest % p.tiles_m, b = rest / p.tiles_m;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int kb0 = ks * p.num_kb / p.ksplit, kb1 = (ks + 1) * p.num_kb / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
@@ -186,7 +191,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int ks = tile % p.ksplit;
+        const int kb0 = ks * p.num_kb / p.ksplit, kb1 = (ks + 1) * p.num_kb / p.ksplit;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -194,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb != kb0 || k != 0) ? 1u : 0u);
           tc_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
@@ -214,8 +221,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_idx = tile % p.tiles_n;
-      const int rest = tile / p.tiles_n;
+      const int ks = tile % p.ksplit, t2 = tile / p.ksplit;
+      const int n_idx = t2 % p.tiles_n;
+      const int rest = t2 / p.tiles_n;
       const int m_idx = rest % p.tiles_m, b = rest / p.tiles_m;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -227,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + acc * BN + c0, v);
         tc_wait_ld();
         const int n0 = n_idx * BN + c0;
-        if (valid && n0 < p.N) epilogue_store<EPI>(p, b, row, n0, v);
+        if (valid && n0 < p.N) epilogue_store<EPI>(p, b, row, n0, v, ks == 0);
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
@@ -247,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN>
 static int gemm_smem_bytes() {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   return STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
@@ -261,9 +269,16 @@ GemmPlan gemm_plan(const GemmArgs& a, int num_sms) {
   p.tiles_m = ceil_div(a.rows, BM);
   long long tiles256 = (long long)a.a_batch * p.tiles_m * ceil_div(a.N, 256);
   p.block_n = (a.N % 256 == 0 && tiles256 >= 2LL * num_sms) ? 256 : 128;
+  // few rows (one M tile): a 128-wide tiling leaves most SMs without work while the weights stream through N/128 CTAs
+  if (a.narrow_tiles && a.a_batch * p.tiles_m == 1 && ceil_div(a.N, 128) * 2 <= num_sms) p.block_n = 32;
   p.tiles_n = ceil_div(a.N, p.block_n);
   p.num_kb = K / BK;
-  long long total = (long long)a.a_batch * p.tiles_m * p.tiles_n;
+  p.ksplit = 1;
+  if (a.epilogue == EPI_RESID_ATOMIC) {
+    B2W_CHECK(a.ksplit >= 1 && p.num_kb % a.ksplit == 0, "GEMM K split must divide the K blocks");
+    p.ksplit = a.ksplit;
+  }
+  long long total = (long long)a.a_batch * p.tiles_m * p.tiles_n * p.ksplit;
   p.grid = (int)(total < num_sms ? total : num_sms);
   {
     uint64_t dims[3] = {(uint64_t)a.a_cols, (uint64_t)a.a_rows, (uint64_t)a.a_batch};
@@ -299,8 +314,10 @@ static void configure_bn() {
   configure_one<BN, EPI_F16_XKV>();
   configure_one<BN, EPI_F32>();
   configure_one<BN, EPI_QKV_CACHE>();
+  configure_one<BN, EPI_RESID_ATOMIC>();
 }
 void gemm_configure() {
+  configure_bn<32>();
   configure_bn<128>();
   configure_bn<256>();
 }
@@ -315,12 +332,14 @@ static void dispatch_epi(const GemmPlan& pl, const GemmDev& d, cudaStream_t s) {
     case EPI_F16_XKV: launch_tc<BN, EPI_F16_XKV>(pl, d, s); break;
     case EPI_F32: launch_tc<BN, EPI_F32>(pl, d, s); break;
     case EPI_QKV_CACHE: launch_tc<BN, EPI_QKV_CACHE>(pl, d, s); break;
+    case EPI_RESID_ATOMIC: launch_tc<BN, EPI_RESID_ATOMIC>(pl, d, s); break;
     default: throw Error("unknown GEMM epilogue");
   }
 }
 
-static GemmDev make_dev(const GemmArgs& a, int tiles_m, int tiles_n, int num_kb) {
+static GemmDev make_dev(const GemmArgs& a, int tiles_m, int tiles_n, int num_kb, int ksplit) {
   GemmDev d{};
+  d.ksplit = ksplit;
   d.batch = a.a_batch;
   d.tiles_m = tiles_m;
   d.tiles_n = tiles_n;
@@ -352,11 +371,13 @@ static GemmDev make_dev(const GemmArgs& a, int tiles_m, int tiles_n, int num_kb)
 }
 
 void gemm_run(const GemmPlan& pl, cudaStream_t stream) {
-  const GemmDev d = make_dev(pl.a, pl.tiles_m, pl.tiles_n, pl.num_kb);
+  const GemmDev d = make_dev(pl.a, pl.tiles_m, pl.tiles_n, pl.num_kb, pl.ksplit);
   if (pl.block_n == 256)
     dispatch_epi<256>(pl, d, stream);
-  else
+  else if (pl.block_n == 128)
     dispatch_epi<128>(pl, d, stream);
+  else
+    dispatch_epi<32>(pl, d, stream);
 }
 
 // ---- plain SIMT reference with the same contract (debug / bisecting; never the timed path) -----------------
@@ -401,6 +422,8 @@ __global__ void gemm_ref_kernel(const __half* __restrict__ A, int a_rows, int a_
     }
   } else if (epi == EPI_RESID_F32) {
     reinterpret_cast<float*>(p.out)[idx] = p.resid[idx] + acc;
+  } else if (epi == EPI_RESID_ATOMIC) {
+    reinterpret_cast<float*>(p.out)[idx] += acc;  // one thread per element: a plain in-place add
   } else if (epi == EPI_GELU_POS_F32) {
     reinterpret_cast<float*>(p.out)[idx] = acc + p.pos[(long long)row * p.N + n];
   } else {
@@ -409,7 +432,7 @@ __global__ void gemm_ref_kernel(const __half* __restrict__ A, int a_rows, int a_
 }
 
 void gemm_ref_run(const GemmArgs& a, cudaStream_t stream) {
-  const GemmDev d = make_dev(a, 0, 0, 0);
+  const GemmDev d = make_dev(a, 0, 0, 0, 1);
   dim3 block(32, 8);
   dim3 grid(ceil_div(a.N, 32), ceil_div(a.rows, 8), a.a_batch);
   gemm_ref_kernel<<<grid, block, 0, stream>>>(a.A, a.a_rows, a.a_cols, a.a_row_stride,
