@@ -251,17 +251,24 @@ def run_engine(args):
             dist.barrier()
 
     def timed(fn, steps):
+        """K steps between barrier + sync on both sides, timed on the device: CUDA events recorded on the engine's stream
+        before the first and after the last step (host work between launches is inside the span); max over ranks."""
         barrier()
         t0 = time.perf_counter()
+        eng.span_begin()
         for _ in range(steps):
             fn()
+        dt = eng.span_end() * 1e-3
         eng.sync()
-        dt = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
         if use_dist:
-            t = torch.tensor([dt], device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            t = torch.tensor([dt, wall], device="cuda" if dist.get_backend() == "nccl" else "cpu")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, wall = float(t[0].item()), float(t[1].item())
+        timed.wall.append(wall)
         return dt
+
+    timed.wall = []
 
     for _ in range(max(args.warmup, 3)):
         engine_step()
@@ -298,7 +305,8 @@ def run_engine(args):
         clocks=clocks,
         stages_ms={k[:-3]: round(v / args.steps, 3) for k, v in stats.items() if k.endswith("_ms") and v > 0},
         device_ms_per_step=round(sum(v for k, v in stats.items() if k.endswith("_ms")) / args.steps, 3),
-        timing="value/e2e: host clock around K steps bracketed by stream sync (+ barrier, max over ranks); stages_ms/roofline: CUDA events on the engine stream",
+        timing="value/e2e: CUDA events on the engine stream around the K steps (barrier + sync on both sides, max over ranks); stages_ms/roofline: per-stage CUDA events on the same stream",
+        host_wall_ms_per_step=[round(w / args.steps * 1e3, 3) for w in timed.wall],
         roofline={"bound": "hbm", "kernel": ("decode step = dstep_kernel (persistent: weight stream + self/cross attention + logits) + search kernels"
                                              if B * args.beam_size <= 8 else
                                              "decode step (CUDA graph: gemm_tc/skinny_gemm weight stream + self/cross attention + search)"),

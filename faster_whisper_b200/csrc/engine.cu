@@ -1702,6 +1702,33 @@ int b2w_align(b2w_model* h, b2w_encoded* enc, int32_t batch_index, const int32_t
   });
 }
 
+int b2w_span_begin(b2w_model* h) {
+  return guarded([&] {
+    B2W_CHECK(h, "bad arguments");
+    Model* m = &h->m;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    if (!m->span_a) {
+      B2W_CUDA(cudaEventCreate(&m->span_a));
+      B2W_CUDA(cudaEventCreate(&m->span_b));
+    }
+    B2W_CUDA(cudaEventRecord(m->span_a, m->stream));
+  });
+}
+int b2w_span_end(b2w_model* h, double* ms_out) {
+  return guarded([&] {
+    B2W_CHECK(h && ms_out && h->m.span_a, "b2w_span_end without b2w_span_begin");
+    Model* m = &h->m;
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard g(m->device);
+    B2W_CUDA(cudaEventRecord(m->span_b, m->stream));
+    B2W_CUDA(cudaEventSynchronize(m->span_b));
+    float ms = 0.f;
+    B2W_CUDA(cudaEventElapsedTime(&ms, m->span_a, m->span_b));
+    *ms_out = ms;
+  });
+}
+
 int b2w_timing_enable(b2w_model* h, int32_t on) {
   return guarded([&] {
     drain_timers(&h->m);

@@ -115,6 +115,7 @@ struct Model {
   int2* d_align_heads = nullptr;
   float* align_out = nullptr;
   int align_n_tok = 0, align_nf = 0, align_pos0 = 0;
+  cudaEvent_t span_a = nullptr, span_b = nullptr;  // b2w_span_begin / b2w_span_end
   __half* logit_tiles = nullptr;  // output embedding as the persistent step kernel's tile stream
   DLayer* d_layers = nullptr;   // device copy of the decoder layer pointer table (persistent step kernel)
   unsigned* d_bar = nullptr;

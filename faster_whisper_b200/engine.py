@@ -55,7 +55,7 @@ ABI_SYMBOLS = (
     "b2w_last_error", "b2w_abi_version", "b2w_device_count", "b2w_model_create", "b2w_model_destroy",
     "b2w_model_info", "b2w_model_sync", "b2w_logmel", "b2w_logmel_frames", "b2w_encode", "b2w_encode_audio",
     "b2w_encoded_shape", "b2w_encoded_to_host", "b2w_encoded_free", "b2w_generate", "b2w_gen_opts_default",
-    "b2w_detect_language", "b2w_align", "b2w_model_set_alignment_heads", "b2w_timing_enable", "b2w_timing_reset", "b2w_timing_get",
+    "b2w_detect_language", "b2w_align", "b2w_model_set_alignment_heads", "b2w_timing_enable", "b2w_timing_reset", "b2w_timing_get", "b2w_span_begin", "b2w_span_end",
     "b2w_counters_get", "b2w_debug_gemm", "b2w_debug_attention", "b2w_debug_gemv", "b2w_debug_logits",
 )
 
@@ -106,6 +106,8 @@ def load_library():
         lib.b2w_timing_enable.argtypes = [C.c_void_p, C.c_int32]
         lib.b2w_timing_reset.argtypes = [C.c_void_p]
         lib.b2w_timing_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        lib.b2w_span_begin.argtypes = [C.c_void_p]
+        lib.b2w_span_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.b2w_counters_get.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         lib.b2w_debug_gemm.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_void_p]
@@ -502,6 +504,18 @@ class Whisper:
         d = {f"{n}_ms": ms[i] for i, n in enumerate(T_STAGES)}
         d.update(launches=ln.value, decode_steps=st.value, decode_alg_bytes=by.value)
         return d
+
+    def span_begin(self, replica: int = 0):
+        """CUDA event on the engine stream: start of a device-timed region (bench.py)."""
+        rep = self._replicas[replica]
+        _check(rep._lib.b2w_span_begin(rep._h))
+
+    def span_end(self, replica: int = 0) -> float:
+        """Second event + wait; milliseconds between the two events on the engine stream."""
+        rep = self._replicas[replica]
+        ms = C.c_double()
+        _check(rep._lib.b2w_span_end(rep._h, C.byref(ms)))
+        return ms.value
 
     def sync(self):
         for r in self._replicas:

@@ -149,6 +149,10 @@ enum { B2W_T_MEL = 0, B2W_T_ENCODER = 1, B2W_T_CROSSKV = 2, B2W_T_PREFILL = 3, B
 int b2w_timing_enable(b2w_model* m, int32_t on);
 int b2w_timing_reset(b2w_model* m);
 int b2w_timing_get(b2w_model* m, double ms_out[B2W_T_COUNT], int64_t counts_out[B2W_T_COUNT]);
+/* Device-side span timer on the model's stream (bench.py: the timed region of K steps): `begin` records a CUDA event on the
+ * stream, `end` records a second one, waits for it and returns the elapsed milliseconds between the two. */
+int b2w_span_begin(b2w_model* m);
+int b2w_span_end(b2w_model* m, double* ms_out);
 /* kernels launched by this library on this model since the last reset (bench.py "gpu_launches"),
  * decode steps executed, and bytes the decode steps had to move (algorithmic: W + B*X + R*t*S). */
 int b2w_counters_get(b2w_model* m, int64_t* launches, int64_t* decode_steps, double* decode_alg_bytes);
