@@ -103,3 +103,56 @@ def test_sampling_is_seeded(micro):
     c = o.generate(None, [[st.sot, st.no_timestamps]], seed=8, **kw)[0]
     assert a.sequences_ids == b.sequences_ids and a.sequences_ids != c.sequences_ids
     assert a.scores == sorted(a.scores, reverse=True) and len(a.sequences_ids) == 3
+
+
+# ---- Whisper.align helpers ---------------------------------------------------------------------------------------------------
+def test_median_filter_matches_scipy_mirror():
+    from scipy.ndimage import median_filter as sp_median
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 5, 40))
+    for w in (3, 7):
+        assert np.array_equal(orc.median_filter(x, w), sp_median(x, size=(1, 1, w), mode="mirror"))
+    assert np.array_equal(orc.median_filter(x[..., :3], 7), x[..., :3])  # shorter than the padding: unchanged
+
+
+def test_dtw_is_optimal_and_monotone():
+    import itertools
+
+    rng = np.random.default_rng(1)
+    for n, m in ((2, 3), (3, 4), (4, 4)):
+        cost = rng.standard_normal((n, m))
+        ti, fi = orc.dtw(cost)
+        assert (ti[0], fi[0]) == (0, 0) and (ti[-1], fi[-1]) == (n - 1, m - 1)
+        steps = set(zip(np.diff(ti).tolist(), np.diff(fi).tolist()))
+        assert steps <= {(1, 1), (1, 0), (0, 1)}
+        got = cost[ti, fi].sum()
+        # brute force over all monotone paths
+        best = np.inf
+        moves = [(1, 1), (1, 0), (0, 1)]
+        for length in range(max(n, m) - 1, n + m - 1):
+            for seq in itertools.product(moves, repeat=length):
+                i = j = 0
+                tot = cost[0, 0]
+                ok = True
+                for di, dj in seq:
+                    i, j = i + di, j + dj
+                    if i >= n or j >= m:
+                        ok = False
+                        break
+                    tot += cost[i, j]
+                if ok and (i, j) == (n - 1, m - 1):
+                    best = min(best, tot)
+        assert abs(got - best) < 1e-9
+
+
+def test_align_shapes_and_probabilities(micro):
+    o, st = micro["oracle"], micro["tokens"]
+    feats = np.stack([orc.pad_or_trim(orc.log_mel(synthetic_audio(3, 30.0), micro["dims"].n_mels)[:, :-1])])
+    text = [[1000, 1001, 1002, 1003, 1004]]
+    res = o.align(o.encode(feats), [st.sot], text, 3000, 7)[0]
+    ti = np.array([p[0] for p in res.alignments])
+    fi = np.array([p[1] for p in res.alignments])
+    assert ti[0] == 0 and ti[-1] == len(text[0]) and fi[0] == 0 and fi[-1] == 1499  # rows predict text + eot
+    assert (np.diff(ti) >= 0).all() and (np.diff(fi) >= 0).all()
+    assert len(res.text_token_probs) == len(text[0]) and all(0.0 <= p <= 1.0 for p in res.text_token_probs)
