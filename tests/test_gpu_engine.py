@@ -284,3 +284,42 @@ def test_transcribe_word_timestamps_end_to_end(micro_ml):
                                                           beam_size=2, max_new_tokens=12, word_timestamps=True)
     bwords = [w for s in bsegs for w in (s.words or [])]
     assert len(bwords) > 0 and all(w.start <= w.end for w in bwords)
+
+
+# ---- full large-v3 geometry (d=1280, 20 heads, 32+32 layers, V=51866): the persistent step kernel at its production shape -----
+def test_large_v3_geometry_matches_oracle():
+    """Synthetic weights at the exact large-v3 shapes (the bench model): encoder output, first-step no_speech probability and
+    free-running greedy / beam-5 tokens against the fp32 CPU oracle.  Covers what the micro models cannot: 140 cross-attention
+    tasks on 148 SMs, the four-way FFN2 K split over CTA groups of four, 3 242 logits tiles, d = 1280 tiles."""
+    import torch
+
+    from faster_whisper_b200.config import MODEL_DIMS, special_tokens
+    from faster_whisper_b200.synthetic import make_weights
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    dims = MODEL_DIMS["large-v3"]
+    st = special_tokens(dims.n_vocab)
+    w = make_weights(dims, seed=0)
+    o = orc.WhisperOracle(dims.to_dict(), w, st.to_dict())
+    e = engine.Whisper(dims=dims, weights=w, tokens=st, device="cuda")
+    feats = np.stack([orc.pad_or_trim(orc.log_mel(synthetic_audio(0, 30.0), dims.n_mels)[:, :-1])])
+    want_enc = o.encode(feats)
+    enc = e.encode(feats)
+    got_enc = enc.numpy()
+    err = np.abs(got_enc - want_enc.numpy())
+    print("large-v3 encoder: max abs err %.4g, rel Frobenius %.4g" % (err.max(), rel_fro(got_enc, want_enc.numpy())))
+    # measured on B200: max abs 3.7e-3 on O(1) activations, relative Frobenius 6.8e-4
+    assert err.max() < 1e-2 and rel_fro(got_enc, want_enc.numpy()) < 1.5e-3
+    prompt = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]]
+    sup = [st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech]
+    for beam, n_new, extra in ((1, 10, {}), (1, 10, dict(repetition_penalty=1.4, no_repeat_ngram_size=2)), (5, 8, {})):
+        kw = dict(beam_size=beam, max_length=len(prompt[0]) + n_new, suppress_tokens=sup, return_scores=True, return_no_speech_prob=True, **extra)
+        want = o.generate(want_enc, prompt, **kw)[0]
+        got = e.generate(enc, prompt, **kw)[0]
+        print("large-v3 beam %d: tokens %s score %.4f (oracle %.4f, min margin %.3f)" % (beam, got.sequences_ids[0], got.scores[0], want.scores[0],
+                                                                                        want.min_margin))
+        assert abs(got.no_speech_prob - want.no_speech_prob) < 5e-3 * max(1.0, want.no_speech_prob) + 1e-6
+        if got.sequences_ids[0] != want.sequences_ids[0]:
+            assert want.min_margin < 2 * LOGIT_TOL, (want.min_margin, got.sequences_ids[0], want.sequences_ids[0])
+        else:
+            assert abs(got.scores[0] - want.scores[0]) < 0.05
