@@ -9,10 +9,12 @@ A *step* is one pass of the hot path over one batch of synthetic 30 s chunks on 
 ``--workload batched`` (configs[2]/[4]) = 16 chunks through one generate() call.  Weak scaling: per-GPU work is fixed.
 Decode length is pinned: prompt of 4 tokens, exactly 128 new tokens (EOT in suppress_tokens).
 
-Prints ONE JSON line (rank 0).  ``value`` = audio seconds per wall second through the engine calls
-(encode_audio + generate; the 1.92 MB/chunk PCM upload is inside, see ``stages_ms.h2d``); ``e2e`` = the same metric through the
-public API (``BatchedInferencePipeline.transcribe`` on a host NumPy waveform, segments consumed); ``roofline`` = decode-step
-HBM roofline (algorithmic bytes W + B*X + R*t*S per step over CUDA-event time on the engine's stream).
+Prints ONE JSON line (rank 0).  ``value`` = audio seconds per second through the engine calls (encode_audio + generate; the
+1.92 MB/chunk PCM upload is inside, see ``stages_ms.h2d``), timed with CUDA events on the engine's stream around the K steps
+(barrier + sync on both sides, max over ranks; the host wall clock of the same region is in ``host_wall_ms_per_step``);
+``e2e`` = the same metric through the public API (``BatchedInferencePipeline.transcribe`` on a host NumPy waveform, segments
+consumed); ``roofline`` = decode-step HBM roofline (algorithmic bytes W + B*X + R*t*S per step over the CUDA-event time of the
+decode stage on the engine's stream).
 """
 from __future__ import annotations
 
