@@ -323,3 +323,24 @@ def test_large_v3_geometry_matches_oracle():
             assert want.min_margin < 2 * LOGIT_TOL, (want.min_margin, got.sequences_ids[0], want.sequences_ids[0])
         else:
             assert abs(got.scores[0] - want.scores[0]) < 0.05
+
+
+def test_persistent_step_long_context(micro_ml):
+    """More than kDsSelfKeys (192) cached positions: the persistent kernel's multi-pass self-attention with online softmax."""
+    st = micro_ml["tokens"]
+    feats = features_for(micro_ml, 1, seed=95)
+    prompts = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]]
+    kw = dict(beam_size=1, max_length=240, return_scores=True, suppress_tokens=[st.eot], repetition_penalty=1.3, no_repeat_ngram_size=3)
+    fused = make_engine(micro_ml, B2W_DSTEP="1")
+    split = make_engine(micro_ml, B2W_DSTEP="0")
+    a = fused.generate(fused.encode(feats), prompts, **kw)[0]
+    b = split.generate(split.encode(feats), prompts, **kw)[0]
+    o = micro_ml["oracle"]
+    w = o.generate(o.encode(feats), prompts, **kw)[0]
+    assert len(w.sequences_ids[0]) == 236
+    for got in (a, b):
+        if got.sequences_ids[0] != w.sequences_ids[0]:
+            first = next(i for i, (x, y) in enumerate(zip(got.sequences_ids[0], w.sequences_ids[0])) if x != y)
+            assert w.min_margin < 2 * LOGIT_TOL, (first, w.min_margin)
+        else:
+            assert abs(got.scores[0] - w.scores[0]) < 0.05
