@@ -203,7 +203,7 @@ def test_generate_errors(micro, eng):
 
 
 # ---- persistent single-kernel decode step (R <= 8 rows) vs the multi-kernel path and the oracle --------------------------
-@pytest.mark.parametrize("beam,n_chunks", [(5, 1), (1, 1), (1, 4), (2, 3)])
+@pytest.mark.parametrize("beam,n_chunks", [(5, 1), (1, 1), (1, 4), (2, 3), (1, 8)])  # (1, 8): 168 cross-attention tasks > 148 CTAs
 def test_persistent_step_matches_multikernel_path(micro_ml, beam, n_chunks):
     st = micro_ml["tokens"]
     feats = features_for(micro_ml, n_chunks, seed=90)
