@@ -140,3 +140,40 @@ def test_word_timestamps_match_reference(both):
     assert any(c[0] == "align" for c in calls_ref)
     assert strip(calls_our) == strip(calls_ref)
     assert sum(len(w) for _, w in ref) > 0
+
+
+@pytest.mark.parametrize("kw", [
+    dict(language="en", beam_size=2, max_new_tokens=10, word_timestamps=True, hallucination_silence_threshold=0.5, **COMMON),
+    dict(language="en", beam_size=1, max_new_tokens=9, prefix="hello", condition_on_previous_text=True, prompt_reset_on_temperature=0.3, **COMMON),
+    dict(language="es", beam_size=2, max_new_tokens=8, without_timestamps=True, word_timestamps=True, prepend_punctuations="\"'“¿([{-",
+         append_punctuations="\"'.。,，!！?？:：”)]}、", **COMMON),
+    dict(beam_size=1, max_new_tokens=7, multilingual=True, language_detection_segments=2, language_detection_threshold=0.9, **COMMON),
+    dict(language="en", beam_size=2, max_new_tokens=6, chunk_length=20, max_initial_timestamp=0.5, suppress_blank=False,
+         suppress_tokens=[-1, 100, 200], length_penalty=0.8, patience=1.5, repetition_penalty=1.2, no_repeat_ngram_size=2, **COMMON),
+    dict(language="en", beam_size=1, max_new_tokens=8, clip_timestamps=[2.0, 21.5], word_timestamps=True, **COMMON),
+])
+def test_more_sequential_options_match_reference(both, kw):
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(85, 30.0), synthetic_audio(86, 18.0)])
+    calls_ref.clear()
+    calls_our.clear()
+    ref_segs, ref_info = ref_model.transcribe(audio.copy(), **kw)
+    ref = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in ref_segs]
+    our_segs, our_info = our_model.transcribe(audio.copy(), **kw)
+    our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in our_segs]
+    assert our == ref and len(ref) > 0
+    assert strip(calls_our) == strip(calls_ref)
+    assert (our_info.language, our_info.duration) == (ref_info.language, ref_info.duration)
+    assert dataclasses.asdict(our_info.transcription_options) == dataclasses.asdict(ref_info.transcription_options)
+
+
+def test_batched_word_timestamps_match_reference(both):
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(87 + i, 30.0) for i in range(2)] + [synthetic_audio(89, 11.0)])
+    clips = [{"start": 0.0, "end": 30.0}, {"start": 30.0, "end": 60.0}, {"start": 60.0, "end": 71.0}]
+    kw = dict(language="en", beam_size=2, batch_size=2, max_new_tokens=8, word_timestamps=True, vad_filter=False, clip_timestamps=clips)
+    ref_segs, _ = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), **kw)
+    ref = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in ref_segs]
+    our_segs, _ = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), **kw)
+    our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in our_segs]
+    assert our == ref and len(ref) >= 3 and sum(len(w) for _, w in ref) > 0
