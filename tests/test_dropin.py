@@ -177,3 +177,89 @@ def test_batched_word_timestamps_match_reference(both):
     our_segs, _ = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), **kw)
     our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in our_segs]
     assert our == ref and len(ref) >= 3 and sum(len(w) for _, w in ref) > 0
+
+
+# ---- VAD segmentation logic vs the reference's, on the same per-window speech probabilities ----------------------------------
+class _FakeVad:
+    def __init__(self, seed, n_windows_hint=0):
+        self.seed = seed
+
+    def __call__(self, padded_audio, *a, **k):
+        n = padded_audio.shape[0] // 512
+        rng = np.random.default_rng(self.seed)
+        # piecewise speech / silence with noisy probabilities so every branch of the hysteresis is visited
+        p = np.zeros(n, np.float32)
+        i = 0
+        speech = bool(rng.integers(0, 2))
+        while i < n:
+            run = int(rng.integers(1, 120))
+            lo, hi = (0.55, 1.0) if speech else (0.0, 0.45)
+            p[i : i + run] = rng.uniform(lo, hi, min(run, n - i))
+            i += run
+            speech = not speech
+        flip = rng.random(n) < 0.03
+        p[flip] = 1.0 - p[flip]
+        return p
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_vad_segmentation_matches_reference(both, seed):
+    from faster_whisper_b200 import vad as our_vad
+
+    fw = both[0]
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(16000 * 5, 16000 * 120))
+    audio = np.zeros(n, np.float32)
+    opts = dict(threshold=float(rng.choice([0.5, 0.35, 0.6])), neg_threshold=[None, 0.2, 0.4][seed % 3],
+                min_speech_duration_ms=int(rng.choice([0, 250, 1000])), max_speech_duration_s=float(rng.choice([float("inf"), 4.0, 12.0, 30.0])),
+                min_silence_duration_ms=int(rng.choice([100, 500, 2000])), speech_pad_ms=int(rng.choice([0, 30, 400])))
+    fake = _FakeVad(seed)
+    mp = pytest.MonkeyPatch()
+    mp.setattr(fw.vad, "get_vad_model", lambda: fake)
+    our_vad.set_vad_model(fake)
+    try:
+        want = fw.vad.get_speech_timestamps(audio, fw.vad.VadOptions(**opts))
+        got = our_vad.get_speech_timestamps(audio, our_vad.VadOptions(**opts))
+        assert got == want and all(type(v) is int for s in got for v in s.values()) == all(type(v) is int for s in want for v in s.values())
+        # and the chunk packing / timestamp restoration built on top of it
+        for max_dur in (float("inf"), 30.0):
+            a_chunks, a_meta = fw.vad.collect_chunks(audio, want, max_duration=max_dur)
+            b_chunks, b_meta = our_vad.collect_chunks(audio, got, max_duration=max_dur)
+            assert [len(c) for c in a_chunks] == [len(c) for c in b_chunks] and a_meta == b_meta
+        if want:
+            m1, m2 = fw.vad.SpeechTimestampsMap(want, 16000), our_vad.SpeechTimestampsMap(got, 16000)
+            for t in (0.0, 1.234, 7.5, 33.3):
+                assert m1.get_original_time(t) == m2.get_original_time(t) and m1.get_chunk_index(t) == m2.get_chunk_index(t)
+    finally:
+        mp.undo()
+        our_vad.set_vad_model(None)
+
+
+def test_transcribe_with_vad_filter_matches_reference(both):
+    """vad_filter=True end to end (the batched pipeline's default): speech spans -> packed chunks -> engine -> restored times."""
+    from faster_whisper_b200 import vad as our_vad
+
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(92, 30.0), synthetic_audio(93, 30.0), synthetic_audio(94, 12.0)])
+    fake = _FakeVad(5)
+    mp = pytest.MonkeyPatch()
+    mp.setattr(fw.vad, "get_vad_model", lambda: fake)
+    our_vad.set_vad_model(fake)
+    try:
+        kw = dict(language="en", beam_size=1, max_new_tokens=8, vad_filter=True, vad_parameters=dict(min_silence_duration_ms=300), **COMMON)
+        ref_segs, ref_info = ref_model.transcribe(audio.copy(), **kw)
+        ref = [seg_tuple(s) for s in ref_segs]
+        our_segs, our_info = our_model.transcribe(audio.copy(), **kw)
+        our = [seg_tuple(s) for s in our_segs]
+        assert our == ref and len(ref) > 0
+        assert our_info.duration_after_vad == ref_info.duration_after_vad < ref_info.duration
+        bkw = dict(language="en", beam_size=1, batch_size=2, max_new_tokens=6, word_timestamps=True)  # vad_filter defaults to True here
+        ref_segs, ref_info = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), **bkw)
+        ref = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in ref_segs]
+        our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), **bkw)
+        our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in our_segs]
+        assert our == ref and len(ref) > 0
+        assert our_info.duration_after_vad == ref_info.duration_after_vad
+    finally:
+        mp.undo()
+        our_vad.set_vad_model(None)
