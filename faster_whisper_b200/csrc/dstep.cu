@@ -147,14 +147,25 @@ __device__ __forceinline__ int ds_item(int ntiles, int ksplit, int j) {
   const int tl = (int)(blockIdx.x >> 2) + j * g4;
   return tl < ntiles ? tl * 4 + (int)(blockIdx.x & 3) : -1;
 }
-__device__ __forceinline__ uint32_t ds_tile_bytes(int d) { return (uint32_t)(16 * (d + 32) + 32) * 2u; }
+// fp16 tiles: 16 rows x (d + 32) halves + 16 fp32 bias values; int8 tiles: 16 rows x (d + 32) bytes (weights stored as q + 128)
+// + 16 fp32 per-channel scales + 16 fp32 bias values
+__host__ __device__ __forceinline__ uint32_t ds_tile_bytes(int d, int w8) {
+  return w8 ? (uint32_t)(16 * (d + 32) + 128) : (uint32_t)(16 * (d + 32) + 32) * 2u;
+}
+// two biased-uint8 weights (bytes selected by `sel`) -> half2 of their signed values: 0x64xx is 1024 + xx in fp16, minus 1152
+__device__ __forceinline__ uint32_t ds_cvt_u8x2(uint32_t word, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x64646464u), "r"(sel));
+  const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&r), __floats2half2_rn(1152.f, 1152.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 // Weight producer (one thread of a dedicated warp): walks this CTA's work items of the whole step in order and keeps the
 // ring full — wait until the buffer's previous tile has been consumed, then one TMA bulk copy per tile.  It never
 // synchronises with the compute warps other than through the mbarriers, so it runs ahead across phase boundaries.
 __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh, unsigned char* ring, int tile_stride) {
   const int last = 6 * a.L;
-  const uint32_t bytes = ds_tile_bytes(a.d);
+  const uint32_t bytes = ds_tile_bytes(a.d, a.w8);
   int n = 0;
 #pragma unroll 1
   for (int s = 0; s <= last; ++s) {
@@ -169,7 +180,7 @@ __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh
       mbar_wait(&sh.wempty[buf], (uint32_t)(((n / kDsNBuf) & 1) ^ 1));  // passes immediately on the first lap
       fence_proxy_async();
       mbar_expect_tx(&sh.wfull[buf], bytes);
-      ds_bulk_g2s(ring + (size_t)buf * tile_stride, base + (long long)item * (bytes >> 1), bytes, &sh.wfull[buf]);
+      ds_bulk_g2s(ring + (size_t)buf * tile_stride, reinterpret_cast<const unsigned char*>(base) + (long long)item * bytes, bytes, &sh.wfull[buf]);
       n += 1;
     }
   }
@@ -178,6 +189,7 @@ __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh
 // One GEMV phase: y[R,N] = in[R,K] W[N,K]^T for this CTA's items, weights consumed from the shared-memory ring.
 // Returns the updated count of consumed tiles (a warp-uniform register value; the ring index and mbarrier parity follow
 // from it).
+template <bool W8>
 __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int s, int consumed, unsigned char* ring, int tile_stride, __half* xs,
                                           float* red, __half* kc, __half* vc) {
   int ntiles, ksplit;
@@ -263,31 +275,58 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     mbar_wait(&sh.wfull[buf], (uint32_t)((consumed / kDsNBuf) & 1));
     if (first) DS_TICK(a, sub, 1, tp);  // weight tile landed
     const __half* wt = reinterpret_cast<const __half*>(ring + (size_t)buf * tile_stride);
-    const __half* w_lo = wt + g * ld + 8 * t;
-    const __half* w_hi = w_lo + 8 * ld;
     const __half* xb = xs + g * ld + 8 * t;
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (W8) {
+      // int8 weight stream: 8 bytes per (row, 32-wide k chunk) and lane, widened to fp16 in registers; the per-channel
+      // scale is applied to the fp32 sum in the epilogue
+      const unsigned char* w8 = ring + (size_t)buf * tile_stride;
+      const unsigned char* w_lo = w8 + g * ld + 8 * t;
+      const unsigned char* w_hi = w_lo + 8 * ld;
 #pragma unroll 5
-    for (int c = warp; c < kchunks; c += kDsWarps) {
-      const uint4 wa = *reinterpret_cast<const uint4*>(w_lo + c * 32);
-      const uint4 wb = *reinterpret_cast<const uint4*>(w_hi + c * 32);
-      const uint4 xv = *reinterpret_cast<const uint4*>(xb + c * 32);
-      ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
-      ds_mma(acc2, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+      for (int c = warp; c < kchunks; c += kDsWarps) {
+        const uint2 wa = *reinterpret_cast<const uint2*>(w_lo + c * 32);
+        const uint2 wb = *reinterpret_cast<const uint2*>(w_hi + c * 32);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xb + c * 32);
+        ds_mma(acc, ds_cvt_u8x2(wa.x, 0x5140u), ds_cvt_u8x2(wb.x, 0x5140u), ds_cvt_u8x2(wa.x, 0x5342u), ds_cvt_u8x2(wb.x, 0x5342u), xv.x, xv.y);
+        ds_mma(acc2, ds_cvt_u8x2(wa.y, 0x5140u), ds_cvt_u8x2(wb.y, 0x5140u), ds_cvt_u8x2(wa.y, 0x5342u), ds_cvt_u8x2(wb.y, 0x5342u), xv.z, xv.w);
+      }
+    } else {
+      const __half* w_lo = wt + g * ld + 8 * t;
+      const __half* w_hi = w_lo + 8 * ld;
+#pragma unroll 5
+      for (int c = warp; c < kchunks; c += kDsWarps) {
+        const uint4 wa = *reinterpret_cast<const uint4*>(w_lo + c * 32);
+        const uint4 wb = *reinterpret_cast<const uint4*>(w_hi + c * 32);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xb + c * 32);
+        ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
+        ds_mma(acc2, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+      }
     }
     float* rj = red + (j & 1) * (kDsWarps * 128);
     float* my = rj + warp * 128;  // [16 ch][8 rows]
     *reinterpret_cast<float2*>(my + g * 8 + 2 * t) = make_float2(acc[0] + acc2[0], acc[1] + acc2[1]);
     *reinterpret_cast<float2*>(my + (g + 8) * 8 + 2 * t) = make_float2(acc[2] + acc2[2], acc[3] + acc2[3]);
     const int ch = tid & 15, r = tid >> 4;
-    float v = (tid < 128) ? reinterpret_cast<const float*>(wt + 16 * ld)[ch] : 0.f;  // bias (zero for ks > 0)
+    float v = 0.f, wscale = 1.f;  // bias (zero for ks > 0) and, for int8 tiles, the channel's de-quantisation scale
+    if (tid < 128) {
+      if constexpr (W8) {
+        const float* tail = reinterpret_cast<const float*>(ring + (size_t)buf * tile_stride + 16 * ld);
+        wscale = tail[ch];
+        v = tail[16 + ch];
+      } else {
+        v = reinterpret_cast<const float*>(wt + 16 * ld)[ch];
+      }
+    }
     ds_sync();  // partials visible; the weight buffer is free
     consumed += 1;
     if (tid == 0) mbar_arrive(&sh.wempty[buf]);
     if (first) DS_TICK(a, sub, 2, tp);  // MMAs + partials
     if (tid < 128 && r < a.R) {
+      float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < kDsWarps; ++w) v += rj[w * 128 + ch * 8 + r];
+      for (int w = 0; w < kDsWarps; ++w) sum += rj[w * 128 + ch * 8 + r];
+      v = W8 ? fmaf(sum, wscale, v) : v + sum;
       const int n = tl * 16 + ch;
       if (mode == DS_QKV) {
         if (n < d) {
@@ -578,6 +617,7 @@ __device__ __noinline__ int ds_cross_attn_task(const DStepArgs& a, DsShared& sh,
   return kv_uses + 1;
 }
 
+template <bool W8>
 __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepArgs a_param) {
   extern __shared__ __align__(128) unsigned char ds_smem[];
   // the argument block is copied to shared memory: the out-of-line phase functions take it by reference, and a reference
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
   const DStepArgs& a = a_sh;
   // [weight ring: kDsNBuf tiles][cross-attention K/V tile | self-attention scratch][GEMV input xs | cross-attention scratch][red x2]
   const int d = a.d, L = a.L;
-  const int tile_stride = (int)((ds_tile_bytes(d) + 127u) & ~127u);
+  const int tile_stride = (int)((ds_tile_bytes(d, W8 ? 1 : 0) + 127u) & ~127u);
   unsigned char* ring = ds_smem;
   unsigned char* kvbuf = ring + (size_t)kDsNBuf * tile_stride;
   unsigned char* scr = kvbuf + kDsKvBytes;
@@ -660,13 +700,13 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
       } else {
         // GEMV sequence index inside the layer: ph 0 -> qkv(0), 2 -> out(1), 3 -> cross_q(2), 5 -> cross_out(3), 6 -> ffn1(4), 7 -> ffn2(5)
         const int j = ph == 0 ? 0 : (ph < 4 ? ph - 1 : ph - 2);
-        consumed = ds_gemv_phase(a, sh, 6 * l + j, consumed, ring, tile_stride, xs, red, kc, vc);
+        consumed = ds_gemv_phase<W8>(a, sh, 6 * l + j, consumed, ring, tile_stride, xs, red, kc, vc);
       }
       ds_grid_barrier(a, sh);
     }
   }
   // ---- logits = LN_f(x) E^T ----
-  consumed = ds_gemv_phase(a, sh, 6 * L, consumed, ring, tile_stride, xs, red, nullptr, nullptr);
+  consumed = ds_gemv_phase<W8>(a, sh, 6 * L, consumed, ring, tile_stride, xs, red, nullptr, nullptr);
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
     a.prof[sh.prof_i] = ds_globaltimer();
     for (int k = 0; k < 8; ++k)
@@ -713,8 +753,48 @@ __global__ void ds_pack_kernel(const __half* __restrict__ W, const float* __rest
   if (threadIdx.x < 16) ob[threadIdx.x] = (bias && ks == 0) ? bias[tl * 16 + threadIdx.x] : 0.f;
 }
 
+// ---- int8 weight stream: per-output-channel symmetric quantisation on the device -------------------------------------------
+// One CTA per row of W[N][K]: scale = max|w| / 127; q = clamp(rint(w / scale)) stored as q + 128; W is overwritten with
+// q * scale so that every other path (prefill, many-row decode) computes with exactly the weights the int8 stream encodes.
+__global__ void ds_quant_rows_kernel(__half* __restrict__ W, unsigned char* __restrict__ q, float* __restrict__ scale, int K) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  __half* w = W + row * K;
+  float mx = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) mx = fmaxf(mx, fabsf(__half2float(w[k])));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  const float sc = mx > 0.f ? mx / 127.f : 1.f;
+  if (threadIdx.x == 0) scale[row] = sc;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int v = max(-127, min(127, __float2int_rn(__half2float(w[k]) / sc)));
+    q[row * K + k] = (unsigned char)(v + 128);
+    w[k] = __float2half_rn((float)v * sc);
+  }
+}
+
+__global__ void ds_pack_i8_kernel(const unsigned char* __restrict__ q, const float* __restrict__ scale, const float* __restrict__ bias, int K,
+                                  int ksplit, unsigned char* __restrict__ out) {
+  const int item = blockIdx.x, tl = item / ksplit, ks = item - tl * ksplit;
+  const int kr = K / ksplit, ld = kr + 32;
+  unsigned char* o = out + (size_t)item * (16 * ld + 128);
+  for (int i = threadIdx.x; i < 16 * ld; i += blockDim.x) {
+    const int r = i / ld, c = i - r * ld;
+    o[i] = c < kr ? q[(size_t)(tl * 16 + r) * K + ks * kr + c] : (unsigned char)128;
+  }
+  float* tail = reinterpret_cast<float*>(o + 16 * ld);
+  if (threadIdx.x < 16) {
+    tail[threadIdx.x] = scale[tl * 16 + threadIdx.x];
+    tail[16 + threadIdx.x] = (bias && ks == 0) ? bias[tl * 16 + threadIdx.x] : 0.f;
+  }
+}
+
 size_t dstep_tile_halves(int kr) { return (size_t)16 * (kr + 32) + 32; }
 size_t dstep_packed_halves(int N, int K, int ksplit) { return (size_t)(N / 16) * ksplit * dstep_tile_halves(K / ksplit); }
+size_t dstep_packed_bytes_i8(int N, int K, int ksplit) { return (size_t)(N / 16) * ksplit * ((size_t)16 * (K / ksplit + 32) + 128); }
 
 void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int ksplit, __half* out, cudaStream_t s) {
   B2W_CHECK(N % 16 == 0 && K % (32 * ksplit) == 0, "dstep_pack_tiles: shape");
@@ -722,15 +802,28 @@ void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int kspl
   B2W_LAUNCHED();
 }
 
+void dstep_quantize_rows(__half* W, int N, int K, unsigned char* q, float* scale, cudaStream_t s) {
+  ds_quant_rows_kernel<<<N, 256, 0, s>>>(W, q, scale, K);
+  B2W_LAUNCHED();
+}
+
+void dstep_pack_tiles_i8(const unsigned char* q, const float* scale, const float* bias, int N, int K, int ksplit, unsigned char* out,
+                         cudaStream_t s) {
+  B2W_CHECK(N % 16 == 0 && K % (32 * ksplit) == 0, "dstep_pack_tiles_i8: shape");
+  ds_pack_i8_kernel<<<(N / 16) * ksplit, 256, 0, s>>>(q, scale, bias, K, ksplit, out);
+  B2W_LAUNCHED();
+}
+
 size_t dstep_smem_bytes(const DStepArgs& a) {
-  const size_t tile_stride = ((size_t)dstep_tile_halves(a.d) * 2 + 127) & ~size_t(127);
+  const size_t tile_stride = ((size_t)ds_tile_bytes(a.d, a.w8) + 127) & ~size_t(127);
   const size_t xs_bytes = (size_t)8 * (a.d + 32) * 2;
   const size_t scr = ((xs_bytes > (size_t)kDsXScratch ? xs_bytes : (size_t)kDsXScratch) + 127) & ~size_t(127);
   return kDsNBuf * tile_stride + kDsKvBytes + scr + 2 * kDsWarps * 128 * sizeof(float);
 }
 
 void dstep_configure() {
-  B2W_CUDA(cudaFuncSetAttribute(dstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  B2W_CUDA(cudaFuncSetAttribute(dstep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  B2W_CUDA(cudaFuncSetAttribute(dstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   B2W_CUDA(cudaFuncSetAttribute(ds_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsKvBytes + ((kDsXScratch + 127) & ~127)));
 }
 
@@ -741,7 +834,10 @@ int dstep_max_grid(int num_sms, const DStepArgs& a) {
   if (smem > 220 * 1024 || self_scratch > (size_t)kDsKvBytes) return 0;
   if (a.d % 64 != 0 || a.d > 1280 || a.L > 32 || a.R > 8 || (a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || num_sms < 4) return 0;
   int per_sm = 0;
-  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel, kDsLaunchThreads, smem));
+  if (a.w8)
+    B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel<true>, kDsLaunchThreads, smem));
+  else
+    B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dstep_kernel<false>, kDsLaunchThreads, smem));
   return per_sm >= 1 ? num_sms : 0;
 }
 
@@ -750,7 +846,8 @@ void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s) {
   B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
   DStepArgs copy = a;
   void* args[] = {&copy};
-  B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dstep_kernel), dim3(grid), dim3(kDsLaunchThreads), args, smem, s));
+  void* fn = a.w8 ? reinterpret_cast<void*>(dstep_kernel<true>) : reinterpret_cast<void*>(dstep_kernel<false>);
+  B2W_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kDsLaunchThreads), args, smem, s));
   count_launch();
 }
 

@@ -20,6 +20,7 @@ struct DStepArgs {
   const __half* logit_tiles;  // packed tiles of the (LayerNorm-folded) output embedding
   const float* pos_emb;
   int R, d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk;
+  int w8;  // 1: the tile streams hold int8 weights + per-channel scales (compute_type int8*), 0: fp16
   const RowInfo* rows;
   const int* tokens_in;
   float* x;        // [8][d] fp32 residual stream
@@ -45,6 +46,12 @@ struct DStepArgs {
 size_t dstep_tile_halves(int kr);
 size_t dstep_packed_halves(int N, int K, int ksplit);
 void dstep_pack_tiles(const __half* W, const float* bias, int N, int K, int ksplit, __half* out, cudaStream_t s);
+// int8 variant: rows of (K/ksplit + 32) bytes holding q + 128, then 16 fp32 scales and 16 fp32 bias values per item.
+// dstep_quantize_rows quantises W per output channel (symmetric, scale = max|w| / 127) and overwrites W with q * scale.
+size_t dstep_packed_bytes_i8(int N, int K, int ksplit);
+void dstep_quantize_rows(__half* W, int N, int K, unsigned char* q, float* scale, cudaStream_t s);
+void dstep_pack_tiles_i8(const unsigned char* q, const float* scale, const float* bias, int N, int K, int ksplit, unsigned char* out,
+                         cudaStream_t s);
 
 // stand-alone beam-shared cross attention on mma.sync (the persistent kernel's task as its own launch)
 bool dstep_cross_attn_supported(int T, int rows_per_chunk);

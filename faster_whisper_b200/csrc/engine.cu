@@ -443,9 +443,26 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   {
     // decoder weights re-laid out as the persistent step kernel's tile stream (a second copy: ~1.6 GB for large-v3)
     std::vector<DLayer> hl(L);
-    auto pack = [&](const __half* W, const float* bias, int N, int K, int ksplit) {
+    unsigned char* q_scratch = nullptr;
+    float* scale_scratch = nullptr;
+    if (m->w8 || m->w8_fake) {
+      q_scratch = dalloc<unsigned char>((size_t)m->vpad * dt > (size_t)4 * dt * dt ? (size_t)m->vpad * dt : (size_t)4 * dt * dt);
+      scale_scratch = dalloc<float>((size_t)std::max(m->vpad, 4 * dt));
+    }
+    auto pack = [&](const __half* W, const float* bias, int N, int K, int ksplit) -> const __half* {
+      if (m->w8 || m->w8_fake) {
+        // quantise per output channel; W now holds q * scale (what the prefill / many-row paths multiply with)
+        dstep_quantize_rows(const_cast<__half*>(W), N, K, q_scratch, scale_scratch, m->stream);
+        if (m->w8) {
+          unsigned char* out8 = up.alloc<unsigned char>(dstep_packed_bytes_i8(N, K, ksplit));
+          dstep_pack_tiles_i8(q_scratch, scale_scratch, bias, N, K, ksplit, out8, m->stream);
+          B2W_CUDA(cudaStreamSynchronize(m->stream));  // the scratch buffers are reused by the next matrix
+          return reinterpret_cast<const __half*>(out8);
+        }
+      }
       __half* out = up.alloc<__half>(dstep_packed_halves(N, K, ksplit));
       dstep_pack_tiles(W, bias, N, K, ksplit, out, m->stream);
+      B2W_CUDA(cudaStreamSynchronize(m->stream));
       return out;
     };
     const bool packable = dt % 64 == 0 && m->vpad % 16 == 0;
@@ -460,6 +477,11 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
     }
     if (packable) m->logit_tiles = pack(m->logit_w, m->logit_b, m->vpad, dt, 1);
     else m->use_dstep = false;
+    if (q_scratch) {
+      B2W_CUDA(cudaStreamSynchronize(m->stream));
+      cudaFree(q_scratch);
+      cudaFree(scale_scratch);
+    }
     m->d_layers = dalloc<DLayer>(L);
     B2W_CUDA(cudaMemcpy(m->d_layers, hl.data(), L * sizeof(DLayer), cudaMemcpyHostToDevice));
     m->d_bar = dalloc<unsigned>(4);
@@ -1015,6 +1037,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
   if (use_dstep) {
     ds.layers = m->d_layers; ds.L = c.n_text_layer; ds.tok_emb = m->tok_emb; ds.pos_emb = m->dec_pos;
     ds.logit_tiles = m->logit_tiles;
+    ds.w8 = m->w8 ? 1 : 0;
     ds.R = R; ds.d = c.n_text_state; ds.H = c.n_text_head; ds.n_ctx = c.n_text_ctx; ds.slots = K; ds.T = 1500;
     ds.vpad = m->vpad; ds.n_vocab = c.n_vocab; ds.n_chunks = n; ds.rows_per_chunk = K;
     ds.rows = sb.rows; ds.tokens_in = sb.tokens_in;
@@ -1259,6 +1282,13 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     if (const char* v = getenv("B2W_ATTN_IMPL")) m->use_ref_attn = !strcmp(v, "ref");
     if (const char* v = getenv("B2W_GEMV_IMPL")) m->use_ref_gemv = !strcmp(v, "ref");
     if (const char* v = getenv("B2W_GRAPH")) m->use_graph = strcmp(v, "0") != 0;
+    m->w8 = ct.rfind("int8", 0) == 0;
+    if (const char* v = getenv("B2W_W8_FAKE")) {
+      if (strcmp(v, "0") != 0) {
+        m->w8_fake = true;
+        m->w8 = false;
+      }
+    }
     if (const char* v = getenv("B2W_DSTEP")) m->use_dstep = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {

@@ -116,11 +116,15 @@ struct Model {
   float* align_out = nullptr;
   int align_n_tok = 0, align_nf = 0, align_pos0 = 0;
   cudaEvent_t span_a = nullptr, span_b = nullptr;  // b2w_span_begin / b2w_span_end
-  __half* logit_tiles = nullptr;  // output embedding as the persistent step kernel's tile stream
+  const __half* logit_tiles = nullptr;  // output embedding as the persistent step kernel's tile stream
   DLayer* d_layers = nullptr;   // device copy of the decoder layer pointer table (persistent step kernel)
   unsigned* d_bar = nullptr;
   unsigned long long* d_prof = nullptr;  // B2W_DSTEP_PROF=1: per-phase timestamps of the persistent step kernel
   int dstep_grid = 0;
+  // compute_type int8*: the decoder's linear layers (and the output embedding) are quantised per output channel; the persistent step
+  // kernel streams them as int8 (w8), every other path uses the de-quantised fp16 values.  w8_fake keeps fp16 tiles of the same
+  // de-quantised values (B2W_W8_FAKE=1: the reference the int8 stream is tested against).
+  bool w8 = false, w8_fake = false;
   bool use_dstep = true;
   bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)
   DecBindings h_bind{};

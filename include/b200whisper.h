@@ -78,7 +78,9 @@ int b2w_device_count(int* count);
 
 /* ---- model ------------------------------------------------------------------------------------- */
 /* ctranslate2.models.Whisper(model_path, device, device_index, compute_type, ...) (transcribe.py:689-698).
- * compute_type: "float16" | "default" | "auto" | "int8_float16" | "int8" (int8 weights, fp16 math). */
+ * compute_type: "float16" | "default" | "auto" -> fp16 weights; "int8" | "int8_float16" | ... -> the decoder's linear layers and the
+ * output embedding are quantised per output channel (symmetric, scale = max|w|/127) at load; the single-stream decode kernel
+ * streams them as int8 and applies the scale to the fp32 sums, all other paths multiply with the de-quantised fp16 values. */
 int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n_tensors, int32_t device,
                      const char* compute_type, b2w_model** out);
 void b2w_model_destroy(b2w_model* m);
