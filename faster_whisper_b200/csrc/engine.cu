@@ -438,6 +438,7 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   m->d_bind = dalloc<DecBindings>(1);
   decode_configure();
   search_configure();
+  search_v2_configure();
   gemm_configure();
   dstep_configure();
   {
@@ -1066,7 +1067,10 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         logits_gemm(m, R);
       }
     }
-    search_rows(m->d_logits, R, m->vpad, sb, s);
+    if (m->search_v2)
+      search_rows_v2(m->d_logits, R, m->vpad, sb, m->spart, s);
+    else
+      search_rows(m->d_logits, R, m->vpad, sb, s);
     search_update(n, sb, s);
   };
 
@@ -1081,6 +1085,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : 0, 0, 0};
     memcpy(k, misc, sizeof misc);
   }
+  if (m->search_v2) search_v2_reserve(m->spart, m->spart_rows, std::max(R, kMaxRows));
   if (sp.fake_logits == 0) {
     // make sure lazily-grown buffers exist before capture (capture forbids cudaMalloc/sync)
     const size_t need_part = cross_attn_partial_floats(n, c.n_text_head, K, splits);
@@ -1291,6 +1296,7 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     }
     if (const char* v = getenv("B2W_DSTEP")) m->use_dstep = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
+    if (const char* v = getenv("B2W_SEARCH_V2")) m->search_v2 = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {
       if (strcmp(v, "0") != 0) {
         m->d_prof = dalloc<unsigned long long>(4096);

@@ -125,6 +125,9 @@ struct Model {
   // kernel streams them as int8 (w8), every other path uses the de-quantised fp16 values.  w8_fake keeps fp16 tiles of the same
   // de-quantised values (B2W_W8_FAKE=1: the reference the int8 stream is tested against).
   bool w8 = false, w8_fake = false;
+  bool search_v2 = false;  // B2W_SEARCH_V2=1: vocabulary-split row search (search_v2.cu) instead of search_rows_kernel
+  SearchPartBuffers spart;
+  int spart_rows = 0;
   bool use_dstep = true;
   bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)
   DecBindings h_bind{};

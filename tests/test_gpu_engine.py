@@ -367,3 +367,25 @@ def test_int8_weight_stream_matches_dequantised_fp16(micro_ml, beam, n_chunks):
         assert abs(x.no_speech_prob - y.no_speech_prob) < 1e-3 * max(1.0, y.no_speech_prob) + 1e-6
         # quantisation noise vs the unquantised model stays small on the first-step statistics
         assert abs(x.no_speech_prob - z.no_speech_prob) < 0.2 * max(z.no_speech_prob, 1e-6) + 1e-6
+
+
+# ---- vocabulary-split row search (search_v2.cu, opt-in B2W_SEARCH_V2=1): same decisions as the default search ------------------
+@pytest.mark.skipif(not os.environ.get("B2W_TEST_EXPERIMENTAL"), reason="search_v2 was written after the GPU budget of round 1 was spent; enable with B2W_TEST_EXPERIMENTAL=1")
+def test_split_search_matches_oracle(micro):
+    e2 = make_engine(micro, B2W_SEARCH_V2="1")
+    st = micro["tokens"]
+    for beam in (1, 2, 5):
+        for timestamps in (False, True):
+            base = [st.sot] + ([] if timestamps else [st.no_timestamps])
+            prompts = [base + [100 + i] for i in range(3)]
+            _search_case(e2, micro, prompts, beam_size=beam, max_length=60, suppress_tokens=[5, 6, 7, st.sot, st.transcribe])
+    prompts = [[st.sot, 321], [st.sot, 654]]
+    _search_case(e2, micro, prompts, beam_size=5, patience=2.0, length_penalty=0.6, max_length=40)
+    _search_case(e2, micro, prompts, beam_size=4, num_hypotheses=3, repetition_penalty=1.3, no_repeat_ngram_size=2, max_length=50)
+    _search_case(e2, micro, prompts, beam_size=1, repetition_penalty=1.5, no_repeat_ngram_size=3, max_length=50,
+                 max_initial_timestamp_index=10, suppress_blank=False)
+    _search_case(e2, micro, [[st.sot, st.no_timestamps, 77]] * 2, beam_size=1, num_hypotheses=5, sampling_topk=0, sampling_temperature=0.6,
+                 seed=1234, max_length=30)
+    feats = features_for(micro, 2, seed=40)
+    exact, n = _compare_generate(e2, micro, feats, [[st.sot_prev, 1000, 1001, st.sot]] * 2, beam_size=5, max_length=36)
+    assert exact >= n - 1
