@@ -1052,7 +1052,12 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       if (m->dstep_grid == 0) m->dstep_grid = -1;
     }
     if (m->dstep_grid <= 0) use_dstep = false;
+    if (use_dstep && m->dstep_variant == 2 && m->dstep2_grid == 0) {
+      m->dstep2_grid = dstep2_max_grid(m->num_sms, ds);
+      if (m->dstep2_grid == 0) m->dstep2_grid = -1;  // not supported here: stay on the single-CTA variant
+    }
   }
+  const bool use_dstep2 = use_dstep && m->dstep_variant == 2 && m->dstep2_grid > 0;
   m->h_params = sp;
   B2W_CUDA(cudaMemcpyAsync(const_cast<SearchParams*>(sb.params), &m->h_params, sizeof(SearchParams), cudaMemcpyHostToDevice, s));
   bind_encoded(m, e, chunk0);
@@ -1060,7 +1065,9 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     if (sp.fake_logits) {
       fake_logits(m->d_logits, R, sb, s);
     } else {
-      if (use_dstep) {
+      if (use_dstep2) {
+        dstep2_launch(ds, m->dstep2_grid, s);
+      } else if (use_dstep) {
         dstep_launch(ds, m->dstep_grid, s);
       } else {
         decoder_layers(m, n, K, K, splits, P - 1);
@@ -1082,7 +1089,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : 0, 0, 0};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? (use_dstep2 ? 2 : 1) : 0, 0, 0};
     memcpy(k, misc, sizeof misc);
   }
   if (m->search_v2) search_v2_reserve(m->spart, m->spart_rows, std::max(R, kMaxRows));
@@ -1294,7 +1301,10 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
         m->w8 = false;
       }
     }
-    if (const char* v = getenv("B2W_DSTEP")) m->use_dstep = strcmp(v, "0") != 0;
+    if (const char* v = getenv("B2W_DSTEP")) {
+      m->use_dstep = strcmp(v, "0") != 0;
+      m->dstep_variant = strcmp(v, "2") == 0 ? 2 : 1;
+    }
     if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
     if (const char* v = getenv("B2W_SEARCH_V2")) m->search_v2 = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {
