@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
 // (7 grid barriers per layer instead of 8).  CTA `rank` of pair h computes the q/k/v channels [64h + 32 rank, +32) (six ring
 // tiles), then scores its 32-dim half of every (row, cached position) straight from the self-KV cache in L2, the two CTAs
 // exchange partial scores through distributed shared memory, both redo the (tiny) soft-max, and each produces its 32 output
-// dims.  Everything else is dstep_kernel.  Written after round 1's GPU budget was spent: NOT yet run on hardware.
+// dims.  Everything else is dstep_kernel.  Written after round 1's GPU budget was spent; the single hardware run it got hung
+// (full-mask shuffles inside a loop with a lane-dependent trip count — fixed below, not re-run).
 // ====================================================================================================================
 __device__ __forceinline__ uint32_t ds_mapa(const void* smem_ptr, uint32_t cta_rank) {
   uint32_t d;
@@ -795,8 +796,10 @@ __device__ __noinline__ void ds2_self_attn_pair(const DStepArgs& a, const DsShar
         const float2 f = __half22float2(k2[e]);
         sdot = fmaf(f.x, q8[2 * e], fmaf(f.y, q8[2 * e + 1], sdot));
       }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      // the four lanes of a position group always run the same number of iterations; other groups may already have left the loop
+      const unsigned quad = 0xFu << (lane & ~3);
+      sdot += __shfl_xor_sync(quad, sdot, 1);
+      sdot += __shfl_xor_sync(quad, sdot, 2);
       if (eq == 0) {
         xch[((size_t)rank * 8 + r) * sp + j] = sdot;
         ds_st_cluster_f32(xch_peer + (uint32_t)((r * sp + j) * 4), sdot);
