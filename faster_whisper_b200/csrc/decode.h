@@ -143,17 +143,6 @@ void fake_logits(float* logits, int R, const SearchBuffers& b, cudaStream_t s);
 void no_speech_from_logits(const float* logits, int row_stride, int R, int rows_per_chunk, int row_in_chunk, int n_vocab,
                            int no_speech_id, float* out, cudaStream_t s);
 void lang_probs_from_logits(const float* logits, int row_stride, int B, int lang_begin, int n_lang, float* out, cudaStream_t s);
-// Vocabulary-split row search (search_v2.cu, opt-in with B2W_SEARCH_V2=1): per (row, slice) soft-max statistics and sorted
-// candidate lists [row][slice][2 lists][kMaxCand] (list 0 ranks every token of the slice, list 1 its timestamp tokens only)
-struct SearchPartBuffers {
-  float* stats = nullptr;
-  float* key = nullptr;
-  float* x = nullptr;
-  int* idx = nullptr;
-};
-void search_v2_configure();
-void search_v2_reserve(SearchPartBuffers& pb, int& capacity_rows, int R);
-void search_rows_v2(const float* logits, int R, int vpad, const SearchBuffers& b, const SearchPartBuffers& pb, cudaStream_t s);
 // Whisper.align helpers (search.cu)
 void row_target_probs(const float* logits, int row_stride, int R, int n_vocab, const int* targets, float* out, cudaStream_t s);
 void align_probs(const __half* q, const DecBindings* bind, int layer, const int2* heads, int n_heads, float* out, int n_tok, int nf,

@@ -147,16 +147,6 @@ __device__ __forceinline__ int ds_item(int ntiles, int ksplit, int j) {
   const int tl = (int)(blockIdx.x >> 2) + j * g4;
   return tl < ntiles ? tl * 4 + (int)(blockIdx.x & 3) : -1;
 }
-// Work-item mapping of the head-pair variant (dstep2_kernel): in the QKV phase the CTA pair that owns head h computes that head's
-// q, k and v channels (item j -> kind j/2, 16-channel tile 2*rank + (j&1) of the head); every other phase keeps ds_item.
-__device__ __forceinline__ int ds2_item(const DStepArgs& a, int s, int ntiles, int ksplit, int j) {
-  if (s < 6 * a.L && s % 6 == 0) {
-    const int pair = (int)(blockIdx.x >> 1), rank = (int)(blockIdx.x & 1);
-    if (pair >= a.H || j >= 6) return -1;
-    return (j >> 1) * (a.d >> 4) + 4 * pair + 2 * rank + (j & 1);
-  }
-  return ds_item(ntiles, ksplit, j);
-}
 // fp16 tiles: 16 rows x (d + 32) halves + 16 fp32 bias values; int8 tiles: 16 rows x (d + 32) bytes (weights stored as q + 128)
 // + 16 fp32 per-channel scales + 16 fp32 bias values
 __host__ __device__ __forceinline__ uint32_t ds_tile_bytes(int d, int w8) {
@@ -173,7 +163,6 @@ __device__ __forceinline__ uint32_t ds_cvt_u8x2(uint32_t word, uint32_t sel) {
 // Weight producer (one thread of a dedicated warp): walks this CTA's work items of the whole step in order and keeps the
 // ring full — wait until the buffer's previous tile has been consumed, then one TMA bulk copy per tile.  It never
 // synchronises with the compute warps other than through the mbarriers, so it runs ahead across phase boundaries.
-template <bool PAIRS>
 __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh, unsigned char* ring, int tile_stride) {
   const int last = 6 * a.L;
   const uint32_t bytes = ds_tile_bytes(a.d, a.w8);
@@ -185,7 +174,7 @@ __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh
     const __half* base = s >= last ? a.logit_tiles : sh.lay[s / 6].wt[s % 6];
 #pragma unroll 1
     for (int j = 0;; ++j) {
-      const int item = PAIRS ? ds2_item(a, s, ntiles, ksplit, j) : ds_item(ntiles, ksplit, j);
+      const int item = ds_item(ntiles, ksplit, j);
       if (item < 0) break;
       const int buf = n % kDsNBuf;
       mbar_wait(&sh.wempty[buf], (uint32_t)(((n / kDsNBuf) & 1) ^ 1));  // passes immediately on the first lap
@@ -200,12 +189,12 @@ __device__ __noinline__ void ds_weight_producer(const DStepArgs& a, DsShared& sh
 // One GEMV phase: y[R,N] = in[R,K] W[N,K]^T for this CTA's items, weights consumed from the shared-memory ring.
 // Returns the updated count of consumed tiles (a warp-uniform register value; the ring index and mbarrier parity follow
 // from it).
-template <bool W8, bool PAIRS = false>
+template <bool W8>
 __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int s, int consumed, unsigned char* ring, int tile_stride, __half* xs,
                                           float* red, __half* kc, __half* vc) {
   int ntiles, ksplit;
   ds_geom(a, s, ntiles, ksplit);
-  if ((PAIRS ? ds2_item(a, s, ntiles, ksplit, 0) : ds_item(ntiles, ksplit, 0)) < 0) return consumed;
+  if (ds_item(ntiles, ksplit, 0) < 0) return consumed;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int d = a.d, ld = d + 32, kchunks = d >> 5;
@@ -279,7 +268,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
   bool first = true;
 #pragma unroll 1
   for (int j = 0;; ++j) {
-    const int item = PAIRS ? ds2_item(a, s, ntiles, ksplit, j) : ds_item(ntiles, ksplit, j);
+    const int item = ds_item(ntiles, ksplit, j);
     if (item < 0) break;
     const int tl = ksplit == 1 ? item : item >> 2;
     const int buf = consumed % kDsNBuf;
@@ -670,7 +659,7 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
   __syncthreads();
   // ---- role split: warp 8 streams the weight tiles, warp 9 prefetches cross-attention K/V, warps 0-7 compute ----
   if (threadIdx.x >= kDsThreads) {
-    if (threadIdx.x == kDsThreads) ds_weight_producer<false>(a, sh, ring, tile_stride);
+    if (threadIdx.x == kDsThreads) ds_weight_producer(a, sh, ring, tile_stride);
     if (threadIdx.x == kDsThreads + 32) ds_kv_producer(a, sh, kvbuf);
     return;
   }
@@ -723,236 +712,6 @@ __global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep_kernel(const DStepA
     for (int k = 0; k < 8; ++k)
       for (int p2 = 0; p2 < 8; ++p2) a.prof[3000 + k * 16 + (p2 == 7 ? 15 : p2)] += sh.ticks[k * 8 + p2];
   }
-}
-
-// ====================================================================================================================
-// Head-pair variant (opt-in, B2W_DSTEP=2): thread-block clusters of two CTAs own one attention head through the QKV
-// projection AND the masked self-attention, so the grid barrier between those two phases becomes a pair barrier
-// (7 grid barriers per layer instead of 8).  CTA `rank` of pair h computes the q/k/v channels [64h + 32 rank, +32) (six ring
-// tiles), then scores its 32-dim half of every (row, cached position) straight from the self-KV cache in L2, the two CTAs
-// exchange partial scores through distributed shared memory, both redo the (tiny) soft-max, and each produces its 32 output
-// dims.  Everything else is dstep_kernel.  Written after round 1's GPU budget was spent; the single hardware run it got hung
-// (full-mask shuffles inside a loop with a lane-dependent trip count — fixed below, not re-run).
-// ====================================================================================================================
-__device__ __forceinline__ uint32_t ds_mapa(const void* smem_ptr, uint32_t cta_rank) {
-  uint32_t d;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d) : "r"(smem_u32(smem_ptr)), "r"(cta_rank));
-  return d;
-}
-__device__ __forceinline__ void ds_st_cluster_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void ds_mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void ds_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-
-// Self-attention of head h for all rows, this CTA's 32-dim half.  `buf` (the K/V tile buffer, free in this phase) holds
-// qf [8][32] floats, xch [2 ranks][8 rows][sp] partial scores (the peer writes its half remotely), o staging.
-__device__ __noinline__ void ds2_self_attn_pair(const DStepArgs& a, const DsShared& sh, uint64_t* pairbar, int layer, int h, int rank,
-                                                const __half* kc, const __half* vc, unsigned char* buf) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int d = a.d, R = a.R, sp = a.n_ctx;  // score rows are n_ctx floats apart
-  float* qf = reinterpret_cast<float*>(buf);              // [8][32], pre-scaled by 1/8
-  float* xch = qf + 8 * 32;                               // [2][8][sp]
-  const int dim0 = h * 64 + rank * 32;
-  // channels [dim0, dim0 + 32) of q and of this position's K/V were produced by this CTA's own QKV items a moment ago
-  ds_sync();
-  for (int i = tid; i < R * 32; i += kDsThreads) {
-    const int r = i >> 5, e = i & 31;
-    qf[r * 32 + e] = __half2float(__ldcg(a.q + (long long)r * d + dim0 + e)) * 0.125f;
-  }
-  ds_sync();
-  const uint32_t peer = (uint32_t)(rank ^ 1);
-  const uint32_t xch_peer = ds_mapa(xch + (size_t)rank * 8 * sp, peer);  // where my partial scores live in the peer's buffer
-  // ---- partial scores: warp per row, lane = (position group jq, 8-dim chunk eq) ----
-  const int jq = lane >> 2, eq = lane & 3;
-  if (warp < R) {
-    const int r = warp;
-    const RowInfo ri = sh.rows[r];
-    const uint8_t* anc = a.anc + (ri.pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * a.n_ctx;
-    float q8[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) q8[e] = qf[r * 32 + eq * 8 + e];
-#pragma unroll 4
-    for (int j = jq; j <= ri.pos; j += 8) {
-      const int slot = (j == ri.pos) ? ri.slot : anc[j];
-      const uint4 kv = __ldcg(reinterpret_cast<const uint4*>(kc + (((long long)ri.chunk * a.n_ctx + j) * a.slots + slot) * d + dim0 + eq * 8));
-      const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
-      float sdot = 0.f;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(k2[e]);
-        sdot = fmaf(f.x, q8[2 * e], fmaf(f.y, q8[2 * e + 1], sdot));
-      }
-      // the four lanes of a position group always run the same number of iterations; other groups may already have left the loop
-      const unsigned quad = 0xFu << (lane & ~3);
-      sdot += __shfl_xor_sync(quad, sdot, 1);
-      sdot += __shfl_xor_sync(quad, sdot, 2);
-      if (eq == 0) {
-        xch[((size_t)rank * 8 + r) * sp + j] = sdot;
-        ds_st_cluster_f32(xch_peer + (uint32_t)((r * sp + j) * 4), sdot);
-      }
-    }
-  }
-  // ---- pair barrier: both halves of every score are in both CTAs ----
-  ds_sync();
-  if (tid == 0) {
-    ds_mbar_arrive_cluster(ds_mapa(pairbar, 0));
-    ds_mbar_arrive_cluster(ds_mapa(pairbar, 1));
-  }
-  ds_mbar_wait_cluster(pairbar, (uint32_t)(layer & 1));
-  // ---- soft-max (redundantly in both CTAs, same order -> identical), probabilities left in xch[0] ----
-  if (warp < R) {
-    const int r = warp, n = sh.rows[r].pos + 1;
-    float* s0 = xch + (size_t)r * sp;
-    const float* s1 = xch + ((size_t)8 + r) * sp;
-    float mx = -INFINITY;
-    for (int j = lane; j < n; j += 32) {
-      const float v = s0[j] + s1[j];
-      s0[j] = v;
-      mx = fmaxf(mx, v);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < n; j += 32) {
-      const float pj = __expf(s0[j] - mx);
-      s0[j] = pj;
-      sum += pj;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    // ---- o[r][dim0 + 8 eq + e] = sum_j p[j] v[j][...]: lanes with equal eq split the positions eight ways ----
-    const RowInfo ri = sh.rows[r];
-    const uint8_t* anc = a.anc + (ri.pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * a.n_ctx;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int j = jq; j < n; j += 8) {
-      const int slot = (j == ri.pos) ? ri.slot : anc[j];
-      const uint4 vv = __ldcg(reinterpret_cast<const uint4*>(vc + (((long long)ri.chunk * a.n_ctx + j) * a.slots + slot) * d + dim0 + eq * 8));
-      const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
-      const float pj = s0[j];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(v2[e]);
-        acc[2 * e] = fmaf(pj, f.x, acc[2 * e]);
-        acc[2 * e + 1] = fmaf(pj, f.y, acc[2 * e + 1]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 4);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-    }
-    if (jq == 0) {
-      const float li = 1.f / sum;
-      uint4 o;
-      o.x = pack_half2(acc[0] * li, acc[1] * li);
-      o.y = pack_half2(acc[2] * li, acc[3] * li);
-      o.z = pack_half2(acc[4] * li, acc[5] * li);
-      o.w = pack_half2(acc[6] * li, acc[7] * li);
-      *reinterpret_cast<uint4*>(a.ao + (long long)r * d + dim0 + eq * 8) = o;
-    }
-  }
-  ds_sync();
-}
-
-template <bool W8>
-__global__ void __launch_bounds__(kDsLaunchThreads, 1) dstep2_kernel(const DStepArgs a_param) {
-  extern __shared__ __align__(128) unsigned char ds_smem[];
-  __shared__ DStepArgs a_sh;
-  __shared__ DsShared sh;
-  __shared__ uint64_t pairbar;
-  if (threadIdx.x == 0) a_sh = a_param;
-  __syncthreads();
-  const DStepArgs& a = a_sh;
-  const int d = a.d, L = a.L;
-  const int tile_stride = (int)((ds_tile_bytes(d, W8 ? 1 : 0) + 127u) & ~127u);
-  unsigned char* ring = ds_smem;
-  unsigned char* kvbuf = ring + (size_t)kDsNBuf * tile_stride;
-  unsigned char* scr = kvbuf + kDsKvBytes;
-  const int xs_bytes = 8 * (d + 32) * 2;
-  const int scr_bytes = ((xs_bytes > kDsXScratch ? xs_bytes : kDsXScratch) + 127) & ~127;
-  float* red = reinterpret_cast<float*>(scr + scr_bytes);
-  __half* xs = reinterpret_cast<__half*>(scr);
-  {
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.layers);
-    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh.lay);
-    for (int i = threadIdx.x; i < L * (int)(sizeof(DLayer) / 8); i += kDsLaunchThreads) dst[i] = src[i];
-    if (threadIdx.x < a.R) sh.rows[threadIdx.x] = a.rows[threadIdx.x];
-    if (threadIdx.x == 0) {
-      sh.epoch = 0;
-      sh.prof_i = 1;
-      for (int i = 0; i < kDsNBuf; ++i) {
-        mbar_init(&sh.wfull[i], 1);
-        mbar_init(&sh.wempty[i], 1);
-      }
-      mbar_init(&sh.kvfull, 1);
-      mbar_init(&sh.kvfree, 1);
-      mbar_init(&pairbar, 2);  // one arrival per CTA of the pair
-      fence_mbar_init();
-    }
-    if (threadIdx.x < 64) sh.ticks[threadIdx.x] = 0;
-  }
-  __syncthreads();
-  // the peer must not arrive on (or write into) this CTA's shared memory before it is initialised
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (threadIdx.x >= kDsThreads) {
-    if (threadIdx.x == kDsThreads) ds_weight_producer<true>(a, sh, ring, tile_stride);
-    if (threadIdx.x == kDsThreads + 32) ds_kv_producer(a, sh, kvbuf);
-    return;
-  }
-  int consumed = 0, kv_uses = 0;
-  if ((int)blockIdx.x < a.R) {
-    const int r = blockIdx.x;
-    int tok = a.tokens_in[r];
-    tok = tok < 0 ? 0 : (tok >= a.n_vocab ? a.n_vocab - 1 : tok);
-    const int pos = sh.rows[r].pos;
-#pragma unroll 2
-    for (int i = threadIdx.x; i < d; i += kDsThreads)
-      __stcg(a.x + (long long)r * d + i, __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
-  }
-  ds_grid_barrier(a, sh);
-  const int xtasks = kDsXSplits * a.H * a.n_chunks;
-  const int pair = (int)(blockIdx.x >> 1), rank = (int)(blockIdx.x & 1);
-#pragma unroll 1
-  for (int l = 0; l < L; ++l) {
-    __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
-    __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
-    // ---- phase A: QKV channels of "my" head, pair barrier inside, self-attention of the head ----
-    consumed = ds_gemv_phase<W8, true>(a, sh, 6 * l, consumed, ring, tile_stride, xs, red, kc, vc);
-    if (pair < a.H) ds2_self_attn_pair(a, sh, &pairbar, l, pair, rank, kc, vc, kvbuf);
-    if (threadIdx.x == 0) mbar_arrive(&sh.kvfree);  // the K/V producer may fetch this layer's cross-attention tile now
-    ds_grid_barrier(a, sh);
-#pragma unroll 1
-    for (int ph = 2; ph < 8; ++ph) {
-      if (ph == 4) {
-        bool pre = true;
-#pragma unroll 1
-        for (int task = blockIdx.x; task < xtasks; task += gridDim.x) {
-          kv_uses = ds_cross_attn_task(a, sh, l, task, pre, kv_uses, kvbuf, scr);
-          pre = false;
-        }
-      } else {
-        const int j = ph < 4 ? ph - 1 : ph - 2;
-        consumed = ds_gemv_phase<W8, true>(a, sh, 6 * l + j, consumed, ring, tile_stride, xs, red, kc, vc);
-      }
-      ds_grid_barrier(a, sh);
-    }
-  }
-  consumed = ds_gemv_phase<W8, true>(a, sh, 6 * L, consumed, ring, tile_stride, xs, red, nullptr, nullptr);
 }
 
 // The same cross-attention task as a stand-alone kernel for the multi-kernel step (many chunks per call): one CTA per
@@ -1065,8 +824,6 @@ size_t dstep_smem_bytes(const DStepArgs& a) {
 void dstep_configure() {
   B2W_CUDA(cudaFuncSetAttribute(dstep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   B2W_CUDA(cudaFuncSetAttribute(dstep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  B2W_CUDA(cudaFuncSetAttribute(dstep2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  B2W_CUDA(cudaFuncSetAttribute(dstep2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   B2W_CUDA(cudaFuncSetAttribute(ds_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsKvBytes + ((kDsXScratch + 127) & ~127)));
 }
 
@@ -1091,58 +848,6 @@ void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s) {
   void* args[] = {&copy};
   void* fn = a.w8 ? reinterpret_cast<void*>(dstep_kernel<true>) : reinterpret_cast<void*>(dstep_kernel<false>);
   B2W_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kDsLaunchThreads), args, smem, s));
-  count_launch();
-}
-
-// ---- head-pair variant: cooperative launch of 2-CTA clusters ----
-static void dstep2_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attrs, int grid, size_t smem, cudaStream_t s) {
-  cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kDsLaunchThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = 2;
-  attrs[0].val.clusterDim.y = 1;
-  attrs[0].val.clusterDim.z = 1;
-  attrs[1].id = cudaLaunchAttributeCooperative;
-  attrs[1].val.cooperative = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = 2;
-}
-
-// grid size (an even number of CTAs, all co-resident as pairs) or 0 when the shape / device cannot run the variant
-int dstep2_max_grid(int num_sms, const DStepArgs& a) {
-  if (dstep_max_grid(num_sms, a) == 0) return 0;
-  // head h = channels [64h, 64h + 64); score rows of n_ctx floats for 8 rows and two ranks + q + 1/l must fit the K/V tile buffer
-  if (a.d != 64 * a.H || 2 * a.H > (num_sms & ~1)) return 0;
-  if ((size_t)(8 * 32 + 2 * 8 * a.n_ctx + 8) * sizeof(float) > (size_t)kDsKvBytes) return 0;
-  const size_t smem = dstep_smem_bytes(a);
-  cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attrs[2];
-  dstep2_config(cfg, attrs, num_sms & ~1, smem, nullptr);
-  int clusters = 0;
-  cudaError_t e = a.w8 ? cudaOccupancyMaxActiveClusters(&clusters, dstep2_kernel<true>, &cfg)
-                       : cudaOccupancyMaxActiveClusters(&clusters, dstep2_kernel<false>, &cfg);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return 2 * clusters >= (num_sms & ~1) ? (num_sms & ~1) : 0;
-}
-
-void dstep2_launch(const DStepArgs& a, int grid, cudaStream_t s) {
-  const size_t smem = dstep_smem_bytes(a);
-  B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
-  cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attrs[2];
-  dstep2_config(cfg, attrs, grid, smem, s);
-  DStepArgs copy = a;
-  copy.prof = nullptr;  // the per-phase profiler assumes eight barriers per layer
-  if (a.w8)
-    B2W_CUDA(cudaLaunchKernelEx(&cfg, dstep2_kernel<true>, copy));
-  else
-    B2W_CUDA(cudaLaunchKernelEx(&cfg, dstep2_kernel<false>, copy));
   count_launch();
 }
 

@@ -61,8 +61,5 @@ size_t dstep_smem_bytes(const DStepArgs& a);
 void dstep_configure();
 int dstep_max_grid(int num_sms, const DStepArgs& a);
 void dstep_launch(const DStepArgs& a, int grid, cudaStream_t s);
-// head-pair variant (2-CTA clusters own a head through QKV + self-attention; opt-in B2W_DSTEP=2, not yet run on hardware)
-int dstep2_max_grid(int num_sms, const DStepArgs& a);
-void dstep2_launch(const DStepArgs& a, int grid, cudaStream_t s);
 
 }  // namespace b2w

@@ -438,7 +438,6 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   m->d_bind = dalloc<DecBindings>(1);
   decode_configure();
   search_configure();
-  search_v2_configure();
   gemm_configure();
   dstep_configure();
   {
@@ -1052,12 +1051,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       if (m->dstep_grid == 0) m->dstep_grid = -1;
     }
     if (m->dstep_grid <= 0) use_dstep = false;
-    if (use_dstep && m->dstep_variant == 2 && m->dstep2_grid == 0) {
-      m->dstep2_grid = dstep2_max_grid(m->num_sms, ds);
-      if (m->dstep2_grid == 0) m->dstep2_grid = -1;  // not supported here: stay on the single-CTA variant
-    }
   }
-  const bool use_dstep2 = use_dstep && m->dstep_variant == 2 && m->dstep2_grid > 0;
   m->h_params = sp;
   B2W_CUDA(cudaMemcpyAsync(const_cast<SearchParams*>(sb.params), &m->h_params, sizeof(SearchParams), cudaMemcpyHostToDevice, s));
   bind_encoded(m, e, chunk0);
@@ -1065,19 +1059,14 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     if (sp.fake_logits) {
       fake_logits(m->d_logits, R, sb, s);
     } else {
-      if (use_dstep2) {
-        dstep2_launch(ds, m->dstep2_grid, s);
-      } else if (use_dstep) {
+      if (use_dstep) {
         dstep_launch(ds, m->dstep_grid, s);
       } else {
         decoder_layers(m, n, K, K, splits, P - 1);
         logits_gemm(m, R);
       }
     }
-    if (m->search_v2)
-      search_rows_v2(m->d_logits, R, m->vpad, sb, m->spart, s);
-    else
-      search_rows(m->d_logits, R, m->vpad, sb, s);
+    search_rows(m->d_logits, R, m->vpad, sb, s);
     search_update(n, sb, s);
   };
 
@@ -1089,10 +1078,9 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? (use_dstep2 ? 2 : 1) : 0, 0, 0};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : 0, 0, 0};
     memcpy(k, misc, sizeof misc);
   }
-  if (m->search_v2) search_v2_reserve(m->spart, m->spart_rows, std::max(R, kMaxRows));
   if (sp.fake_logits == 0) {
     // make sure lazily-grown buffers exist before capture (capture forbids cudaMalloc/sync)
     const size_t need_part = cross_attn_partial_floats(n, c.n_text_head, K, splits);
@@ -1303,10 +1291,8 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     }
     if (const char* v = getenv("B2W_DSTEP")) {
       m->use_dstep = strcmp(v, "0") != 0;
-      m->dstep_variant = strcmp(v, "2") == 0 ? 2 : 1;
     }
     if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
-    if (const char* v = getenv("B2W_SEARCH_V2")) m->search_v2 = strcmp(v, "0") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {
       if (strcmp(v, "0") != 0) {
         m->d_prof = dalloc<unsigned long long>(4096);

@@ -121,15 +121,10 @@ struct Model {
   unsigned* d_bar = nullptr;
   unsigned long long* d_prof = nullptr;  // B2W_DSTEP_PROF=1: per-phase timestamps of the persistent step kernel
   int dstep_grid = 0;
-  int dstep_variant = 1;   // B2W_DSTEP=2: head-pair cluster variant (dstep2_kernel)
-  int dstep2_grid = 0;
   // compute_type int8*: the decoder's linear layers (and the output embedding) are quantised per output channel; the persistent step
   // kernel streams them as int8 (w8), every other path uses the de-quantised fp16 values.  w8_fake keeps fp16 tiles of the same
   // de-quantised values (B2W_W8_FAKE=1: the reference the int8 stream is tested against).
   bool w8 = false, w8_fake = false;
-  bool search_v2 = false;  // B2W_SEARCH_V2=1: vocabulary-split row search (search_v2.cu) instead of search_rows_kernel
-  SearchPartBuffers spart;
-  int spart_rows = 0;
   bool use_dstep = true;
   bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)
   DecBindings h_bind{};
