@@ -1,0 +1,1055 @@
+// One persistent, cooperative kernel per decode step for many rows: R <= 80 (BatchedInferencePipeline's 16 chunks x beam 5).
+//
+// At 80 rows a decode step is a chain of skinny GEMMs [R x K] x [K x N] (3-13 MB of weights each), 1600 self-attention
+// (row, head) tasks over the paged self-KV cache and 2240 beam-shared cross-attention tasks that stream 3.9 GB of cross-K/V.
+// As separate launches (round 1) that was ~260 graph nodes and 4.4 ms; here one CTA per SM stays resident and walks
+//   embed | L x { QKV, self-attn, out-proj, cross-q, cross-attn, cross-out, FFN1, GELU, FFN2 } | final LN | logits
+// separated by grid barriers.  What shapes it (measured constants: DESIGN.md §4, /opt/skills/guides/B300_MICROARCH.md):
+//   * L2 -> SM bandwidth is only ~1.9x HBM (~6300 B/clk chip-wide), so no phase may broadcast the [R x K] activations to
+//     every CTA (205 KB x 148 per phase would cost more than the weights).  Every GEMM is therefore split over output
+//     channels AND over K ("stream-K"): the weights are a stream of 16 KB atoms (128 channels x 64 K values, pre-swizzled
+//     so that one 1-D TMA bulk copy lands a ready-made UMMA A tile), the atoms of a matrix are dealt out evenly to the CTAs
+//     in (n-block, k-atom) order, and a CTA stages only the [R x 64] activation slices of its own k-atoms;
+//   * the math is tcgen05.mma (UMMA 128 channels x R rows x 16, fp16 in, fp32 accumulators in TMEM, one issuing thread):
+//     the compute warps only stage activations and drain accumulators;
+//   * split-K partial sums meet in L2: the epilogue copies a [R x 128] fp32 tile to shared memory and issues one
+//     cp.reduce.async.bulk (.add.f32) per row — scalar red.global would cost ~1.3 clk per lane per SM;
+//   * since no CTA ever sees a whole row of a GEMM output, everything that needs one is deferred to the consumer: the
+//     LayerNorm of a residual-stream input is applied algebraically, y = rstd (W x - mean rowsum(W)) + b, with sum(x) and
+//     sum(x^2) accumulated by the CTAs that stage the first n-block; biases of q/k/v/cross-q/hidden are added by the consumer;
+//     GELU gets its own (cheap) phase so that it is evaluated once per element;
+//   * a weight-producer thread keeps a 5-slot ring of atoms full across phase boundaries, a K/V-producer thread double
+//     buffers the cross-attention tiles, an MMA thread issues the UMMAs; eight compute warps do the rest.
+//
+// Replaces the per-token body of CTranslate2's batched Whisper.generate loop (reference call sites
+// faster_whisper/transcribe.py:222-236 driven by :580-617) for BASELINE.json configs[2..4].
+#include <math.h>
+
+#include <algorithm>
+
+#include "bstep.h"
+#include "common.cuh"
+#include "dstep.h"
+#include "step_common.cuh"
+
+namespace b2w {
+
+constexpr int kBsThreads = 256;   // compute threads (8 warps)
+constexpr int kBsLaunch = 352;    // + weight producer warp, K/V producer warp, MMA warp
+constexpr int kBsWarps = 8;
+constexpr int kBsSlots = 5;       // weight-atom ring
+constexpr int kBsKvBytes = 2 * kDsXKeysMax * 64 * 2;  // one cross-attention K + V tile (57 344 B)
+constexpr int kBsXQ = 8;          // rows per chunk the cross-attention task handles
+constexpr int kBsScLd = kDsXKeysMax + 4;
+constexpr int kBsPLd = kDsXKeysMax + 8;
+constexpr int kBsQLd = 96;
+constexpr int kBsXScratch = kBsXQ * kBsQLd * 2 + kBsXQ * kBsScLd * 4 + kBsXQ * kBsPLd * 2 + 2 * kBsXQ * 64 * 4 + 64;
+constexpr int kBsTmemCols = 256;  // two accumulators, 128 columns apart
+
+__host__ __device__ __forceinline__ int bs_ceil16(int v) { return (v + 15) & ~15; }
+
+// logits: when the [R x d] fp16 activations do not fit next to the ring, adjacent CTAs split the rows in two halves and
+// stream the same n-blocks (the second reader hits L2)
+__host__ __device__ __forceinline__ void bs_logit_plan(int R, int d, int avail, int& nhalves, int& Rh, int& NPh) {
+  nhalves = 1;
+  Rh = R;
+  NPh = bs_ceil16(R);
+  if ((d >> 6) * NPh * 128 > avail) {
+    nhalves = 2;
+    Rh = (R + 1) >> 1;
+    NPh = bs_ceil16(Rh);
+  }
+}
+
+// ---- PTX helpers ----
+__device__ __forceinline__ void bs_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bs_bulk_reduce_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bs_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bs_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bs_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bs_fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// 32 lanes x 8 columns of fp32
+__device__ __forceinline__ void bs_tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+struct BsShared {
+  BLayer lay[32];
+  RowInfo rows[kBsMaxRows];
+  unsigned epoch;
+  int prof_i;
+  int flag;
+  int acc_par[2];            // parity of the next acc_full wait (compute side)
+  uint32_t tmem_base;
+  uint64_t wfull[kBsSlots];  // weight atom landed (TMA complete_tx)
+  uint64_t wempty[kBsSlots]; // weight atom consumed (tcgen05.commit)
+  uint64_t xs_ready;         // activations of the phase staged (compute -> MMA thread)
+  uint64_t acc_full[2];      // accumulator complete (tcgen05.commit -> compute)
+  uint64_t acc_empty[2];     // accumulator drained (compute -> MMA thread; logits phase only)
+  uint64_t kvfull[2];        // cross-attention K/V tile landed
+  uint64_t kvfree[2];        // K/V buffer may be overwritten
+};
+
+// ---- phase numbering -------------------------------------------------------------------------------------------------------
+// grid phase index: 0 embed; 1 + 9 l + {0 qkv, 1 self, 2 out, 3 cross_q, 4 cross, 5 cross_out, 6 ffn1, 7 gelu, 8 ffn2}; 1 + 9 L final LN; 2 + 9 L logits
+__device__ __forceinline__ bool bs_enabled(const BStepArgs& a, int phase) { return a.stop_phase <= 0 || phase < a.stop_phase; }
+// GEMM sequence s = 6 l + j (j: qkv, out, cross_q, cross_out, ffn1, ffn2) -> grid phase
+__device__ __forceinline__ int bs_gemm_phase_index(int s) {
+  const int l = s / 6, j = s - 6 * l;
+  const int ph = j == 0 ? 0 : (j == 1 ? 2 : (j == 2 ? 3 : (j == 3 ? 5 : (j == 4 ? 6 : 8))));
+  return 1 + 9 * l + ph;
+}
+struct BsRange {
+  int a0, a1, KA;
+  int nseg;
+  int nb[2], ka0[2], n[2];
+};
+// atoms of GEMM s owned by this CTA, cut at n-block boundaries (at most two segments: an even share is shorter than one n-block's K)
+__device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
+  const int j = s % 6, d = a.d;
+  const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
+  const int K = j == 5 ? 4 * d : d;
+  BsRange r;
+  r.KA = K >> 6;
+  const long long A = (long long)((N + 127) >> 7) * r.KA;
+  r.a0 = (int)(A * blockIdx.x / gridDim.x);
+  r.a1 = (int)(A * (blockIdx.x + 1) / gridDim.x);
+  r.nseg = 0;
+  int cur = r.a0;
+  while (cur < r.a1 && r.nseg < 2) {
+    const int nb = cur / r.KA, ka = cur - nb * r.KA;
+    const int n = min(r.a1 - cur, r.KA - ka);
+    r.nb[r.nseg] = nb;
+    r.ka0[r.nseg] = ka;
+    r.n[r.nseg] = n;
+    r.nseg += 1;
+    cur += n;
+  }
+  return r;
+}
+
+// Grid barrier (compute warps only): arrive = red.release (cumulative through bar.sync), wait = relaxed polling.
+__device__ __forceinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
+  bs_sync();
+  if (threadIdx.x == 0) {
+    sh.epoch += gridDim.x;
+    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+    const unsigned target = sh.epoch;
+    unsigned v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
+    } while (v < target);
+    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();
+    sh.prof_i += 2;
+  }
+  bs_sync();
+}
+
+// ---- producer threads ------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh, unsigned char* ring) {
+  int n = 0;
+  auto push = [&](const unsigned char* src) {
+    const int slot = n % kBsSlots;
+    mbar_wait(&sh.wempty[slot], (uint32_t)(((n / kBsSlots) & 1) ^ 1));
+    mbar_expect_tx(&sh.wfull[slot], kBsAtomBytes);
+    ds_bulk_g2s(ring + (size_t)slot * kBsAtomBytes, src, kBsAtomBytes, &sh.wfull[slot]);
+    n += 1;
+  };
+#pragma unroll 1
+  for (int s = 0; s < 6 * a.L; ++s) {
+    if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
+    const BsRange r = bs_range(a, s);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(sh.lay[s / 6].wt[s % 6]);
+#pragma unroll 1
+    for (int at = r.a0; at < r.a1; ++at) push(base + (size_t)at * kBsAtomBytes);
+  }
+  if (!bs_enabled(a, 2 + 9 * a.L)) return;
+  int nhalves, Rh, NPh;
+  bs_logit_plan(a.R, a.d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
+  const int groups = gridDim.x / nhalves, grp = blockIdx.x / nhalves;
+  if (grp >= groups) return;
+  const int KA = a.d >> 6, NBv = (a.vpad + 127) >> 7;
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(a.logit_atoms);
+#pragma unroll 1
+  for (int nb = grp; nb < NBv; nb += groups)
+#pragma unroll 1
+    for (int ka = 0; ka < KA; ++ka) push(base + ((size_t)nb * KA + ka) * kBsAtomBytes);
+}
+
+__device__ __forceinline__ int bs_xtasks_of_cta(int xtasks) {
+  return (int)blockIdx.x < xtasks ? (xtasks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+}
+
+// TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf (one thread).
+__device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer, int task, unsigned char* kvbuf, uint64_t* bar) {
+  const int split = task % kDsXSplits, rest = task / kDsXSplits;
+  const int h = rest % a.H, b = rest / a.H, T = a.T;
+  const int k0 = (int)((long long)T * split / kDsXSplits), k1 = (int)((long long)T * (split + 1) / kDsXSplits), nk = k1 - k0;
+  const DecBindings bd = *a.bind;
+  const long long per = (long long)bd.B_total * a.H * T * 64;
+  const long long off = (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
+  const __half* Kb = bd.xkv + ((long long)layer * 2 + 0) * per + off;
+  const __half* Vb = bd.xkv + ((long long)layer * 2 + 1) * per + off;
+  fence_proxy_async();
+  mbar_expect_tx(bar, (uint32_t)nk * 256u);
+  ds_bulk_g2s(kvbuf, Kb, (uint32_t)nk * 128u, bar);
+  ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, bar);
+}
+
+// K/V producer: tile k of this CTA (task blockIdx.x + k * grid) goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile
+// of a layer is fetched as soon as the previous layer released it; buffer 1 lives in the multi-purpose region and is opened
+// by the compute warps when the cross-attention phase starts.
+__device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, unsigned char* kv0, unsigned char* kv1) {
+  const int xtasks = kDsXSplits * a.H * a.n_chunks;
+  const int nt = bs_xtasks_of_cta(xtasks);
+  if (nt == 0) return;
+  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
+#pragma unroll 1
+  for (int l = 0; l < a.L; ++l) {
+    if (!bs_enabled(a, 1 + 9 * l + 4)) return;
+#pragma unroll 1
+    for (int k = 0; k < nt; ++k) {
+      const int buf = k & 1;
+      if (buf == 0) {
+        const int u = l * n_even + (k >> 1);
+        mbar_wait(&sh.kvfree[0], (uint32_t)((u & 1) ^ 1));
+      } else {
+        const int u = l * n_odd + (k >> 1);
+        mbar_wait(&sh.kvfree[1], (uint32_t)(u & 1));
+      }
+      bs_issue_cross_kv(a, l, blockIdx.x + k * gridDim.x, buf ? kv1 : kv0, &sh.kvfull[buf]);
+    }
+  }
+}
+
+// MMA thread: per GEMM phase wait for the staged activations, then per atom wait for the weights and issue four K=16 UMMAs.
+__device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, unsigned char* ring, unsigned char* xs, unsigned char* xs_logits) {
+  const uint32_t tmem = sh.tmem_base;
+  const uint32_t idesc = umma_idesc_f16(128, a.NP, false);
+  const uint32_t xs_tile = (uint32_t)a.NP * 128u;
+  int consumed = 0, xs_uses = 0;
+  auto atom = [&](uint32_t d_tmem, uint32_t b_addr, uint32_t id, bool first) {
+    const int slot = consumed % kBsSlots;
+    mbar_wait(&sh.wfull[slot], (uint32_t)((consumed / kBsSlots) & 1));
+    tc_fence_after();
+    const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + (size_t)slot * kBsAtomBytes));
+    const uint64_t db = umma_smem_desc_sw128(b_addr);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, id, (first && k == 0) ? 0u : 1u);
+    tc_commit(&sh.wempty[slot]);
+    consumed += 1;
+  };
+#pragma unroll 1
+  for (int s = 0; s < 6 * a.L; ++s) {
+    if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
+    const BsRange r = bs_range(a, s);
+    if (r.a1 <= r.a0) continue;
+    mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
+    xs_uses += 1;
+    tc_fence_after();
+    int local = 0;
+#pragma unroll 1
+    for (int sg = 0; sg < r.nseg; ++sg) {
+#pragma unroll 1
+      for (int i = 0; i < r.n[sg]; ++i) {
+        atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
+        local += 1;
+      }
+      tc_commit(&sh.acc_full[sg]);
+    }
+  }
+  if (!bs_enabled(a, 2 + 9 * a.L)) return;
+  int nhalves, Rh, NPh;
+  bs_logit_plan(a.R, a.d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
+  const int groups = gridDim.x / nhalves, grp = blockIdx.x / nhalves;
+  if (grp >= groups) return;
+  const int KA = a.d >> 6, NBv = (a.vpad + 127) >> 7;
+  const uint32_t idesc_l = umma_idesc_f16(128, NPh, false);
+  mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
+  tc_fence_after();
+  int it = 0;
+#pragma unroll 1
+  for (int nb = grp; nb < NBv; nb += groups, ++it) {
+    const int acc = it & 1;
+    mbar_wait(&sh.acc_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+    tc_fence_after();
+#pragma unroll 1
+    for (int ka = 0; ka < KA; ++ka) atom(tmem + acc * 128, smem_u32(xs_logits) + ka * (uint32_t)NPh * 128u, idesc_l, ka == 0);
+    tc_commit(&sh.acc_full[acc]);
+  }
+}
+
+// ---- compute-warp phase functions ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bs_zero_f32(float* p, long long n) {  // all compute threads of all CTAs, n % 4 == 0
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * kBsThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kBsThreads)
+    __stcg(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+__device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, float& mean, float& rstd) {
+  const float2 s = __ldcg(reinterpret_cast<const float2*>(st) + r);
+  mean = s.x / d;
+  rstd = rsqrtf(fmaxf(s.y / d - mean * mean, 0.f) + 1e-5f);
+}
+
+// Stage this CTA's activation slices as UMMA B tiles: tile i = [NP rows][64 K values] fp16, 128-byte swizzle, rows >= R zero.
+//   X == true : source = fp32 residual stream (converted raw; the LayerNorm is applied by the consumer of the GEMM output);
+//               segments of n-block 0 also accumulate sum(x), sum(x^2) of their K slice into `st`
+//   X == false: source = fp16 activations [R][ld]
+template <bool X>
+__device__ __forceinline__ void bs_stage(const BStepArgs& a, const BsRange& rg, const void* src, int ld, float* st, unsigned char* xs) {
+  const int NP = a.NP, R = a.R, tid = threadIdx.x;
+  const int per_atom = NP * 8, natoms = rg.a1 - rg.a0, total = natoms * per_atom;
+  constexpr int UNR = X ? 6 : 8;
+#pragma unroll 1
+  for (int base = tid; base < total; base += kBsThreads * UNR) {
+    uint4 v0[UNR], v1[X ? UNR : 1];
+    int dst[UNR], meta[UNR];  // meta: row | (stats << 8)
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int q = base + u * kBsThreads;
+      dst[u] = -1;
+      meta[u] = 0;
+      v0[u] = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (X) v1[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < total) {
+        const int i = q / per_atom, rem = q - i * per_atom, r = rem >> 3, c = rem & 7;
+        const int sg = i < rg.n[0] ? 0 : 1;
+        const int ka = sg == 0 ? rg.ka0[0] + i : i - rg.n[0];
+        dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
+        meta[u] = r | ((X && rg.nb[sg] == 0) ? 256 : 0);
+        if (r < R) {
+          if constexpr (X) {
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (long long)r * ld + ka * 64 + c * 8);
+            const float4 f0 = __ldcg(p), f1 = __ldcg(p + 1);
+            v0[u] = *reinterpret_cast<const uint4*>(&f0);
+            v1[u] = *reinterpret_cast<const uint4*>(&f1);
+          } else {
+            v0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if constexpr (X) {
+        const float4 f0 = *reinterpret_cast<const float4*>(&v0[u]), f1 = *reinterpret_cast<const float4*>(&v1[u]);
+        float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
+        float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
+        // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+        const int r = meta[u] & 255;
+        if ((meta[u] & 256) && (tid & 7) == 0 && r < R && dst[u] >= 0) {
+          atomicAdd(st + 2 * r, s1);
+          atomicAdd(st + 2 * r + 1, s2);
+        }
+        if (dst[u] >= 0)
+          *reinterpret_cast<uint4*>(xs + dst[u]) = make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
+      } else {
+        if (dst[u] >= 0) *reinterpret_cast<uint4*>(xs + dst[u]) = v0[u];
+      }
+    }
+  }
+}
+
+// One GEMM phase (compute warps): stage -> signal the MMA thread -> drain the accumulators into L2 with bulk reductions.
+__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U) {
+  const BsRange rg = bs_range(a, s);
+  if (rg.a1 <= rg.a0) return;
+  const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const BLayer& lay = sh.lay[l];
+  float* out;
+  int N, ldo;
+  const float* bias = nullptr;
+  switch (j) {
+    case 0: out = a.qkv32; N = 3 * d; ldo = 3 * d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
+    case 1: out = a.x; N = d; ldo = d; bias = lay.bias[1]; bs_stage<false>(a, rg, a.ao, d, nullptr, U); break;
+    case 2: out = a.cq32; N = d; ldo = d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
+    case 3: out = a.x; N = d; ldo = d; bias = lay.bias[3]; bs_stage<false>(a, rg, a.ao, d, nullptr, U); break;
+    case 4: out = a.h32; N = 4 * d; ldo = 4 * d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
+    default: out = a.x; N = d; ldo = d; bias = lay.bias[5]; bs_stage<false>(a, rg, a.h16, 4 * d, nullptr, U); break;
+  }
+  fence_proxy_async();
+  bs_sync();
+  if (tid == 0) mbar_arrive(&sh.xs_ready);
+  // all accumulators of the phase must be complete before the staging tile (which aliases the activation tiles) is written
+  for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
+  tc_fence_after();
+  bs_sync();
+  if (tid == 0)
+    for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
+  float* stg = reinterpret_cast<float*>(U);  // [NP][128] fp32
+  const int q = warp & 3, ch = warp >> 2, half_cols = a.NP >> 1;
+#pragma unroll 1
+  for (int sg = 0; sg < rg.nseg; ++sg) {
+    const int n_glob = rg.nb[sg] * 128 + q * 32 + lane;
+    const float bv = (bias && rg.ka0[sg] == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
+    const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
+#pragma unroll 1
+    for (int c = 0; c < half_cols; c += 8) {
+      uint32_t v[8];
+      bs_tmem_ld8(taddr + c, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = __uint_as_float(v[i]) + bv;
+    }
+    fence_proxy_async();
+    bs_sync();
+    if (tid < a.R) {
+      const int nvalid = min(128, N - rg.nb[sg] * 128);
+      bs_bulk_reduce_f32(out + (long long)tid * ldo + rg.nb[sg] * 128, stg + tid * 128, (uint32_t)nvalid * 4u);
+      bs_bulk_commit();
+      if (sg + 1 < rg.nseg) bs_bulk_wait_read();
+    }
+    if (sg + 1 < rg.nseg) bs_sync();
+  }
+  tc_fence_before();
+  if (tid < a.R) {
+    bs_bulk_wait_all();
+    bs_fence_async_all();
+  }
+}
+
+// Masked self-attention: one (row, head) task per half-warp.  q, k, v of the new token come from the raw QKV sums (deferred
+// LayerNorm + bias applied here), k and v are rounded to fp16 and written to the paged cache; the history is gathered through
+// the beam ancestry table (one key per lane for the scores, 4 output dims per lane for P V).
+__device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, l16 = lane & 15;
+  const int worker = warp * 2 + hw;
+  const unsigned hmask = hw ? 0xffff0000u : 0x0000ffffu;
+  const int d = a.d, H = a.H, n_ctx = a.n_ctx;
+  float* sc = reinterpret_cast<float*>(U) + worker * n_ctx;
+  float* qs = reinterpret_cast<float*>(U) + 16 * n_ctx + worker * 64;
+  uint8_t* sl = U + (size_t)(16 * n_ctx + 16 * 64) * 4 + worker * n_ctx;
+  const BLayer& lay = sh.lay[l];
+  const float* st = a.stats + (long long)(3 * l) * a.R * 2;
+  __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
+  __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
+  const int ntasks = H * a.R, e0 = 4 * l16;
+#pragma unroll 1
+  for (int t0 = (blockIdx.x * kBsWarps + warp) * 2; t0 < ntasks; t0 += gridDim.x * kBsWarps * 2) {
+    const int task = t0 + hw;
+    if (task >= ntasks) continue;  // the other half-warp keeps going: every sync below is half-warp scoped
+    const int r = task / H, h = task - r * H;
+    const RowInfo ri = sh.rows[r];
+    const int pos = ri.pos;
+    float mean, rstd;
+    bs_row_stats(st, r, d, mean, rstd);
+    const float* raw = a.qkv32 + (long long)r * 3 * d + h * 64 + e0;
+    const float4 rq = __ldcg(reinterpret_cast<const float4*>(raw)), rk = __ldcg(reinterpret_cast<const float4*>(raw + d)),
+                 rv = __ldcg(reinterpret_cast<const float4*>(raw + 2 * d));
+    const float* ws = lay.wsum[0] + h * 64 + e0;
+    const float* bs = lay.bias[0] + h * 64 + e0;
+    const float4 wq = __ldg(reinterpret_cast<const float4*>(ws)), wk = __ldg(reinterpret_cast<const float4*>(ws + d)),
+                 wv = __ldg(reinterpret_cast<const float4*>(ws + 2 * d));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(bs)), bk = __ldg(reinterpret_cast<const float4*>(bs + d)),
+                 bvv = __ldg(reinterpret_cast<const float4*>(bs + 2 * d));
+    const float mr = mean * rstd;
+#define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
+    float4 qv = make_float4(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y), BS_FIX(rq.z, wq.z, bq.z), BS_FIX(rq.w, wq.w, bq.w));
+    const float4 kv = make_float4(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y), BS_FIX(rk.z, wk.z, bk.z), BS_FIX(rk.w, wk.w, bk.w));
+    const float4 vv = make_float4(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y), BS_FIX(rv.z, wv.z, bvv.z), BS_FIX(rv.w, wv.w, bvv.w));
+#undef BS_FIX
+    // q is rounded to fp16 like the other decode paths (they store q as fp16), then pre-scaled by 1/8
+    {
+      const __half2 q01 = __floats2half2_rn(qv.x, qv.y), q23 = __floats2half2_rn(qv.z, qv.w);
+      const float2 f01 = __half22float2(q01), f23 = __half22float2(q23);
+      qv = make_float4(f01.x * 0.125f, f01.y * 0.125f, f23.x * 0.125f, f23.y * 0.125f);
+    }
+    const __half2 k01 = __floats2half2_rn(kv.x, kv.y), k23 = __floats2half2_rn(kv.z, kv.w);
+    const __half2 v01 = __floats2half2_rn(vv.x, vv.y), v23 = __floats2half2_rn(vv.z, vv.w);
+    const long long self_off = (((long long)ri.chunk * n_ctx + pos) * a.slots + ri.slot) * d + h * 64 + e0;
+    *reinterpret_cast<uint2*>(kc + self_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&k01), *reinterpret_cast<const uint32_t*>(&k23));
+    *reinterpret_cast<uint2*>(vc + self_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&v01), *reinterpret_cast<const uint32_t*>(&v23));
+    *reinterpret_cast<float4*>(qs + e0) = qv;
+    float sself;
+    {
+      const float2 ka = __half22float2(k01), kb = __half22float2(k23);
+      sself = qv.x * ka.x + qv.y * ka.y + qv.z * kb.x + qv.w * kb.y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sself += __shfl_xor_sync(hmask, sself, o);
+    }
+    __syncwarp(hmask);
+    const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
+    float mx = sself;
+#pragma unroll 1
+    for (int j0 = 0; j0 < pos; j0 += 16) {
+      const int jj = j0 + l16;
+      if (jj < pos) {
+        const int slot = anc[jj];
+        sl[jj] = (uint8_t)slot;
+        const uint4* kp = reinterpret_cast<const uint4*>(kc + (((long long)ri.chunk * n_ctx + jj) * a.slots + slot) * d + h * 64);
+        uint4 kr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) kr[i] = __ldcg(kp + i);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * i), qb = *reinterpret_cast<const float4*>(qs + 8 * i + 4);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].y)),
+                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].w));
+          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
+          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
+        }
+        const float sv = s0 + s1;
+        sc[jj] = sv;
+        mx = fmaxf(mx, sv);
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(hmask, mx, o));
+    __syncwarp(hmask);
+    float sum = 0.f;
+    for (int jj = l16; jj < pos; jj += 16) {
+      const float p = __expf(sc[jj] - mx);
+      sc[jj] = p;
+      sum += p;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
+    const float pself = __expf(sself - mx);
+    sum += pself;
+    __syncwarp(hmask);
+    float4 acc;
+    {
+      const float2 va = __half22float2(v01), vb = __half22float2(v23);
+      acc = make_float4(pself * va.x, pself * va.y, pself * vb.x, pself * vb.y);
+    }
+    const __half* vbase = vc + (long long)ri.chunk * n_ctx * a.slots * d + h * 64 + e0;
+    const long long pos_stride = (long long)a.slots * d;
+#pragma unroll 1
+    for (int j0 = 0; j0 < pos; j0 += 8) {
+      uint2 vr[8];
+      float pj[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int jj = j0 + i;
+        pj[i] = 0.f;
+        vr[i] = make_uint2(0u, 0u);
+        if (jj < pos) {
+          pj[i] = sc[jj];
+          vr[i] = __ldcg(reinterpret_cast<const uint2*>(vbase + jj * pos_stride + (long long)sl[jj] * d));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&vr[i].x)), vb = __half22float2(*reinterpret_cast<const __half2*>(&vr[i].y));
+        acc.x = fmaf(pj[i], va.x, acc.x);
+        acc.y = fmaf(pj[i], va.y, acc.y);
+        acc.z = fmaf(pj[i], vb.x, acc.z);
+        acc.w = fmaf(pj[i], vb.y, acc.w);
+      }
+    }
+    const float inv = 1.f / sum;
+    *reinterpret_cast<uint2*>(a.ao + (long long)r * d + h * 64 + e0) = make_uint2(pack_half2(acc.x * inv, acc.y * inv), pack_half2(acc.z * inv, acc.w * inv));
+    __syncwarp(hmask);  // sc / qs / sl are reused by this half-warp's next task
+  }
+}
+
+// Beam-shared cross attention: one (key split, head, chunk) task for all rows of the chunk (<= 8); the last split of a
+// (chunk, head) group to finish combines.  Same math as dstep.cu's task (S = K Q^T and O^T = V^T P^T on mma.sync from the
+// XOR-swizzled K/V tile); the query comes from the raw cross-q sums with the deferred LayerNorm + bias applied here.
+__device__ __noinline__ void bs_cross_attn_task(const BStepArgs& a, BsShared& sh, int layer, int task, uint32_t full_parity, uint64_t* full_bar,
+                                                unsigned char* kvbuf, unsigned char* scratch) {
+  const int T = a.T, S = kDsXSplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int split = task % S, rest = task / S, h = rest % a.H, b = rest / a.H;
+  const int nq = a.rows_per_chunk, row0 = b * a.rows_per_chunk, d = a.d;
+  const int k0 = (int)((long long)T * split / S), k1 = (int)((long long)T * (split + 1) / S), nk = k1 - k0;
+  const int nkp = (nk + 15) & ~15;
+  __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
+  __half* vt = kt + kDsXKeysMax * 64;
+  __half* qs = reinterpret_cast<__half*>(scratch);                // [8][96], pre-scaled by 1/8
+  float* sc = reinterpret_cast<float*>(qs + kBsXQ * kBsQLd);      // [8][kBsScLd]
+  __half* pr = reinterpret_cast<__half*>(sc + kBsXQ * kBsScLd);   // [8][kBsPLd]
+  float* wred = reinterpret_cast<float*>(pr + kBsXQ * kBsPLd);    // [2][8][64]
+  float* stat = wred + 2 * kBsXQ * 64;                            // [8][2]
+  const BLayer& lay = sh.lay[layer];
+  if (tid < 64) {
+    const int q = tid >> 3, c = tid & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (q < nq) {
+      const int r = row0 + q;
+      float mean, rstd;
+      bs_row_stats(a.stats + (long long)(3 * layer + 1) * a.R * 2, r, d, mean, rstd);
+      const float mr = mean * rstd;
+      const float* raw = a.cq32 + (long long)r * d + h * 64 + c * 8;
+      const float* ws = lay.wsum[1] + h * 64 + c * 8;
+      const float* bs = lay.bias[2] + h * 64 + c * 8;
+      const float4 r0 = __ldcg(reinterpret_cast<const float4*>(raw)), r1 = __ldcg(reinterpret_cast<const float4*>(raw) + 1);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(ws)), w1 = __ldg(reinterpret_cast<const float4*>(ws) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs)), b1 = __ldg(reinterpret_cast<const float4*>(bs) + 1);
+#define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
+      // fp16 rounding of q first (as the other decode paths store it), then the exact 1/8 scale
+      __half2 hq[4] = {__floats2half2_rn(BS_FIX(r0.x, w0.x, b0.x), BS_FIX(r0.y, w0.y, b0.y)), __floats2half2_rn(BS_FIX(r0.z, w0.z, b0.z), BS_FIX(r0.w, w0.w, b0.w)),
+                       __floats2half2_rn(BS_FIX(r1.x, w1.x, b1.x), BS_FIX(r1.y, w1.y, b1.y)), __floats2half2_rn(BS_FIX(r1.z, w1.z, b1.z), BS_FIX(r1.w, w1.w, b1.w))};
+#undef BS_FIX
+      const __half2 sc8 = __floats2half2_rn(0.125f, 0.125f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hq[i] = __hmul2(hq[i], sc8);
+      v = make_uint4(*reinterpret_cast<uint32_t*>(&hq[0]), *reinterpret_cast<uint32_t*>(&hq[1]), *reinterpret_cast<uint32_t*>(&hq[2]), *reinterpret_cast<uint32_t*>(&hq[3]));
+    }
+    *reinterpret_cast<uint4*>(qs + q * kBsQLd + c * 8) = v;
+  }
+  mbar_wait(full_bar, full_parity);
+  // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite (after the tile has landed: the TMA never writes them)
+  for (int i = tid; i < (nkp - nk) * 8; i += kBsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  bs_sync();
+  // ---- scores ----
+#pragma unroll 1
+  for (int tile = warp; tile * 16 < nkp; tile += kBsWarps) {
+    const int rg = tile * 16 + g, swz = (k0 + rg) & 7;  // rows rg and rg + 8 share the swizzle
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c2 = 0; c2 < 2; ++c2) {
+      const int pc = ((4 * c2 + t) ^ swz) << 3;
+      const uint4 wa = *reinterpret_cast<const uint4*>(kt + rg * 64 + pc);
+      const uint4 wb = *reinterpret_cast<const uint4*>(kt + (rg + 8) * 64 + pc);
+      const uint4 xv = *reinterpret_cast<const uint4*>(qs + g * kBsQLd + 32 * c2 + 8 * t);
+      ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
+      ds_mma(acc, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+    }
+    sc[(2 * t) * kBsScLd + rg] = acc[0];
+    sc[(2 * t + 1) * kBsScLd + rg] = acc[1];
+    sc[(2 * t) * kBsScLd + rg + 8] = acc[2];
+    sc[(2 * t + 1) * kBsScLd + rg + 8] = acc[3];
+  }
+  bs_sync();
+  {  // one warp per query: partial softmax statistics, probabilities as fp16
+    const int q = warp;
+    if (q < nq) {
+      float mx = -INFINITY;
+      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kBsScLd + j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < nkp; j += 32) {
+        const float p = j < nk ? __expf(sc[q * kBsScLd + j] - mx) : 0.f;
+        const __half ph = __float2half_rn(p);
+        pr[q * kBsPLd + j] = ph;
+        sum += __half2float(ph);
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        stat[q * 2] = mx;
+        stat[q * 2 + 1] = sum;
+      }
+    } else {
+      for (int j = lane; j < nkp; j += 32) pr[q * kBsPLd + j] = __float2half_rn(0.f);
+    }
+  }
+  bs_sync();
+  {  // ---- O^T = V^T P^T: warp -> (16 output dims, half of the key tiles) ----
+    const int dtile = warp & 3, khalf = warp >> 2;
+    const int mi = lane >> 3, r8 = lane & 7;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int tile = khalf; tile * 16 < nkp; tile += 2) {
+      const int row = tile * 16 + 8 * (mi >> 1) + r8;
+      const int pc = ((2 * dtile + (mi & 1)) ^ ((k0 + row) & 7)) << 3;
+      uint32_t a0, a1, a2, a3;
+      ds_ldmatrix_x4_trans(a0, a1, a2, a3, vt + row * 64 + pc);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + tile * 16 + 2 * t);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + tile * 16 + 2 * t + 8);
+      ds_mma(acc, a0, a1, a2, a3, b0, b1);
+    }
+    float* w = wred + khalf * (kBsXQ * 64);
+    w[(2 * t) * 64 + 16 * dtile + g] = acc[0];
+    w[(2 * t + 1) * 64 + 16 * dtile + g] = acc[1];
+    w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
+    w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
+  }
+  bs_sync();  // the K/V tile is dead from here on (the caller releases the buffer)
+  const long long group = (long long)b * a.H + h;
+  float* part = a.xpart + (group * S + split) * (kBsXQ * 66);
+#pragma unroll 1
+  for (int i = tid; i < nq * 64; i += kBsThreads) {
+    const int q = i >> 6, e = i & 63;
+    __stcg(part + q * 66 + e, wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]);
+  }
+  if (tid < nq) {
+    __stcg(part + tid * 66 + 64, stat[tid * 2]);
+    __stcg(part + tid * 66 + 65, stat[tid * 2 + 1]);
+  }
+  bs_sync();
+  if (tid == 0) {
+    int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(a.xcounters + group) : "memory");
+    sh.flag = (ticket == S - 1);
+    if (sh.flag) a.xcounters[group] = 0;
+  }
+  bs_sync();
+  if (sh.flag) {
+    const float* pg = a.xpart + group * S * (kBsXQ * 66);
+#pragma unroll 1
+    for (int i = tid; i < nq * 64; i += kBsThreads) {
+      const int q = i >> 6, e = i & 63;
+      float pm[8], pl[8], pa[8];
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        const bool on = s2 < S;
+        const float* base = pg + ((on ? s2 : 0) * kBsXQ + q) * 66;
+        pm[s2] = on ? __ldcg(base + 64) : -INFINITY;
+        pl[s2] = on ? __ldcg(base + 65) : 0.f;
+        pa[s2] = on ? __ldcg(base + e) : 0.f;
+      }
+      float M = pm[0];
+#pragma unroll
+      for (int s2 = 1; s2 < 8; ++s2) M = fmaxf(M, pm[s2]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < 8; ++s2) {
+        const float w = (s2 < S) ? __expf(pm[s2] - M) : 0.f;
+        num = fmaf(w, pa[s2], num);
+        den = fmaf(w, pl[s2], den);
+      }
+      a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
+    }
+  }
+  bs_sync();
+}
+
+__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* kv0, unsigned char* U) {
+  const int xtasks = kDsXSplits * a.H * a.n_chunks;
+  const int nt = bs_xtasks_of_cta(xtasks);
+  if (nt == 0) return;
+  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
+  unsigned char* kv1 = U;
+  unsigned char* scratch = U + kBsKvBytes;
+  if (threadIdx.x == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now
+#pragma unroll 1
+  for (int k = 0; k < nt; ++k) {
+    const int buf = k & 1;
+    const int u = l * (buf ? n_odd : n_even) + (k >> 1);
+    bs_cross_attn_task(a, sh, l, blockIdx.x + k * gridDim.x, (uint32_t)(u & 1), &sh.kvfull[buf], buf ? kv1 : kv0, scratch);
+    // release the tile: buffer 0 always (the producer may fetch the next layer's first tile), buffer 1 only for another tile of this phase
+    if (threadIdx.x == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+  }
+}
+
+// h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums
+__device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l) {
+  const int d = a.d, R = a.R;
+  const BLayer& lay = sh.lay[l];
+  const float* st = a.stats + (long long)(3 * l + 2) * R * 2;
+  const int per_row = d;  // float4 units per row of 4d
+  const int total = R * per_row;
+  for (int i = blockIdx.x * kBsThreads + threadIdx.x; i < total; i += gridDim.x * kBsThreads) {
+    const int r = i / per_row, n = (i - r * per_row) * 4;
+    float mean, rstd;
+    bs_row_stats(st, r, d, mean, rstd);
+    const float mr = mean * rstd;
+    float4* hp = reinterpret_cast<float4*>(a.h32 + (long long)r * 4 * d + n);
+    const float4 hv = __ldcg(hp);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n)), bb = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
+    const float y0 = gelu_erf(fmaf(rstd, hv.x, fmaf(-mr, w.x, bb.x))), y1 = gelu_erf(fmaf(rstd, hv.y, fmaf(-mr, w.y, bb.y)));
+    const float y2 = gelu_erf(fmaf(rstd, hv.z, fmaf(-mr, w.z, bb.z))), y3 = gelu_erf(fmaf(rstd, hv.w, fmaf(-mr, w.w, bb.w)));
+    *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+    __stcg(hp, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
+// xn16[r] = (x[r] - mean) * rstd  (CTA r; the final LayerNorm's affine part is folded into the output embedding)
+__device__ __noinline__ void bs_final_ln_phase(const BStepArgs& a, float* red) {
+  const int r = blockIdx.x, d = a.d, tid = threadIdx.x;
+  if (r >= a.R) return;
+  const int n4 = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)r * d);
+  float4 v[2];
+  float su = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + i * kBsThreads;
+    v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    su += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  su = warp_sum(su);
+  if ((tid & 31) == 0) red[tid >> 5] = su;
+  bs_sync();
+  su = 0.f;
+#pragma unroll
+  for (int i = 0; i < kBsWarps; ++i) su += red[i];
+  const float mean = su / d;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + i * kBsThreads;
+    if (idx < n4) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+  sq = warp_sum(sq);
+  bs_sync();
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  bs_sync();
+  sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kBsWarps; ++i) sq += red[i];
+  const float rstd = rsqrtf(sq / d + 1e-5f);
+  uint2* o = reinterpret_cast<uint2*>(a.xn16 + (long long)r * d);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = tid + i * kBsThreads;
+    if (idx < n4)
+      o[idx] = make_uint2(pack_half2((v[i].x - mean) * rstd, (v[i].y - mean) * rstd), pack_half2((v[i].z - mean) * rstd, (v[i].w - mean) * rstd));
+  }
+}
+
+// logits[r][v] = xn16[r] . E'[v] + b[v]: whole n-blocks (full K) per CTA group, double-buffered accumulators, direct fp32 stores
+__device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, unsigned char* xs_logits) {
+  int nhalves, Rh, NPh;
+  bs_logit_plan(a.R, a.d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
+  const int groups = gridDim.x / nhalves, grp = blockIdx.x / nhalves, half = blockIdx.x % nhalves;
+  if (grp >= groups) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int d = a.d, KA = d >> 6, NBv = (a.vpad + 127) >> 7;
+  const int r_lo = half * Rh, r_n = min(a.R - r_lo, Rh);
+  {  // stage all K of the rows [r_lo, r_lo + r_n): tile ka = [NPh][64]
+    const int per_atom = NPh * 8, total = KA * per_atom;
+    for (int q = tid; q < total; q += kBsThreads) {
+      const int ka = q / per_atom, rem = q - ka * per_atom, r = rem >> 3, c = rem & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r < r_n) v = __ldcg(reinterpret_cast<const uint4*>(a.xn16 + (long long)(r_lo + r) * d + ka * 64 + c * 8));
+      *reinterpret_cast<uint4*>(xs_logits + ka * (NPh * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+  }
+  fence_proxy_async();
+  bs_sync();
+  if (tid == 0) mbar_arrive(&sh.xs_ready);
+  const int q = warp & 3, ch = warp >> 2, half_cols = NPh >> 1;
+  int it = 0;
+#pragma unroll 1
+  for (int nb = grp; nb < NBv; nb += groups, ++it) {
+    const int acc = it & 1;
+    mbar_wait(&sh.acc_full[acc], (uint32_t)sh.acc_par[acc]);
+    tc_fence_after();
+    const int vidx = nb * 128 + q * 32 + lane;
+    const bool vok = vidx < a.vpad;
+    const float bv = vok ? __ldg(a.logit_bias + vidx) : 0.f;
+    const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + acc * 128 + ch * half_cols;
+#pragma unroll 1
+    for (int c = 0; c < half_cols; c += 8) {
+      uint32_t v[8];
+      bs_tmem_ld8(taddr + c, v);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = ch * half_cols + c + i;
+        if (vok && rr < r_n) a.logits[(long long)(r_lo + rr) * a.vpad + vidx] = __uint_as_float(v[i]) + bv;
+      }
+    }
+    tc_fence_before();
+    bs_sync();
+    if (tid == 0) {
+      sh.acc_par[acc] ^= 1;
+      mbar_arrive(&sh.acc_empty[acc]);
+    }
+    bs_sync();
+  }
+}
+
+__global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_param) {
+  extern __shared__ unsigned char bs_smem_raw[];
+  __shared__ BStepArgs a_sh;
+  __shared__ BsShared sh;
+  __shared__ float red[kBsWarps];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bs_smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0) a_sh = a_param;
+  __syncthreads();
+  const BStepArgs& a = a_sh;
+  unsigned char* ring = smem;
+  unsigned char* kv0 = ring + (size_t)kBsSlots * kBsAtomBytes;
+  unsigned char* U = kv0 + kBsKvBytes;
+  const int L = a.L, warp = threadIdx.x >> 5;
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.layers);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(sh.lay);
+    for (int i = threadIdx.x; i < L * (int)(sizeof(BLayer) / 8); i += kBsLaunch) dst[i] = src[i];
+    if (threadIdx.x < a.R) sh.rows[threadIdx.x] = a.rows[threadIdx.x];
+    if (threadIdx.x == 0) {
+      sh.epoch = 0;
+      sh.prof_i = 1;
+      sh.acc_par[0] = sh.acc_par[1] = 0;
+      for (int i = 0; i < kBsSlots; ++i) {
+        mbar_init(&sh.wfull[i], 1);
+        mbar_init(&sh.wempty[i], 1);
+      }
+      mbar_init(&sh.xs_ready, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sh.acc_full[i], 1);
+        mbar_init(&sh.acc_empty[i], 1);
+        mbar_init(&sh.kvfull[i], 1);
+        mbar_init(&sh.kvfree[i], 1);
+      }
+      fence_mbar_init();
+      if (a.prof && blockIdx.x == 0) a.prof[0] = ds_globaltimer();
+    }
+  }
+  if (warp == 10) tmem_alloc(&sh.tmem_base, kBsTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (threadIdx.x >= kBsThreads) {
+    if (threadIdx.x == kBsThreads) bs_weight_producer(a, sh, ring);
+    if (threadIdx.x == kBsThreads + 32) bs_kv_producer(a, sh, kv0, U);
+    if (threadIdx.x == kBsThreads + 64) bs_mma_thread(a, sh, ring, U, kv0);
+  } else {
+    int phase = 0;  // grid phases executed so far
+    // ---- embed: x = tok_emb[token] + pos_emb[pos]; zero the split-K accumulators and the LayerNorm statistics ----
+    if ((int)blockIdx.x < a.R) {
+      const int r = blockIdx.x, d = a.d;
+      int tok = a.tokens_in[r];
+      tok = tok < 0 ? 0 : (tok >= a.n_vocab ? a.n_vocab - 1 : tok);
+      const int pos = sh.rows[r].pos;
+      for (int i = threadIdx.x; i < d; i += kBsThreads)
+        __stcg(a.x + (long long)r * d + i, __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
+    }
+    bs_zero_f32(a.qkv32, (long long)a.R * 3 * a.d);
+    bs_zero_f32(a.cq32, (long long)a.R * a.d);
+    bs_zero_f32(a.h32, (long long)a.R * 4 * a.d);
+    bs_zero_f32(a.stats, (long long)((3 * L * a.R * 2 + 3) & ~3));
+    bool run = bs_enabled(a, ++phase);  // phase 0 done after the barrier; `phase` is the index of the next one
+    bs_grid_barrier(a, sh);
+#pragma unroll 1
+    for (int l = 0; l < L && run; ++l) {
+#pragma unroll 1
+      for (int ph = 0; ph < 9 && run; ++ph) {
+        switch (ph) {
+          case 0: bs_gemm_phase(a, sh, 6 * l + 0, U); break;
+          case 1: bs_self_attn_phase(a, sh, l, U); break;
+          case 2:
+            bs_zero_f32(a.qkv32, (long long)a.R * 3 * a.d);  // consumed by the self-attention of this layer
+            bs_gemm_phase(a, sh, 6 * l + 1, U);
+            break;
+          case 3: bs_gemm_phase(a, sh, 6 * l + 2, U); break;
+          case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
+          case 5:
+            bs_zero_f32(a.cq32, (long long)a.R * a.d);  // consumed by the cross attention of this layer
+            bs_gemm_phase(a, sh, 6 * l + 3, U);
+            break;
+          case 6: bs_gemm_phase(a, sh, 6 * l + 4, U); break;
+          case 7: bs_gelu_phase(a, sh, l); break;
+          default: bs_gemm_phase(a, sh, 6 * l + 5, U); break;
+        }
+        run = bs_enabled(a, ++phase);
+        bs_grid_barrier(a, sh);
+      }
+    }
+    if (run) {
+      bs_final_ln_phase(a, red);
+      run = bs_enabled(a, ++phase);
+      bs_grid_barrier(a, sh);
+    }
+    if (run) bs_logits_phase(a, sh, kv0);
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(sh.tmem_base, kBsTmemCols);
+  }
+}
+
+// ---- weight re-layout ------------------------------------------------------------------------------------------------------
+// One thread per 16-byte chunk of an atom: atom (nb, ka), row i (channel nb*128 + i), chunk c (k = ka*64 + 8c .. +8) is stored at
+// byte i*128 + ((c ^ (i & 7)) << 4) — the 128-byte-swizzled K-major layout UMMA reads (and TMA would write).
+__global__ void bs_pack_atoms_kernel(const __half* __restrict__ W, int N, int K, uint4* __restrict__ out) {
+  const int KA = K >> 6;
+  const long long total = (long long)((N + 127) >> 7) * KA * 1024;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long atom = idx >> 10;
+    const int w = (int)(idx & 1023), i = w >> 3, c = w & 7;
+    const int nb = (int)(atom / KA), ka = (int)(atom - (long long)nb * KA);
+    const int n = nb * 128 + i;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N) v = *reinterpret_cast<const uint4*>(W + (long long)n * K + ka * 64 + c * 8);
+    out[atom * 1024 + i * 8 + (c ^ (i & 7))] = v;
+  }
+}
+__global__ void bs_row_sums_kernel(const __half* __restrict__ W, int N, int K, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const __half2* w = reinterpret_cast<const __half2*>(W + (long long)row * K);
+  float s = 0.f;
+  for (int k = lane; k < (K >> 1); k += 32) {
+    const float2 f = __half22float2(w[k]);
+    s += f.x + f.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+size_t bstep_atoms_bytes(int N, int K) { return (size_t)((N + 127) / 128) * (K / 64) * kBsAtomBytes; }
+
+void bstep_pack_atoms(const __half* W, int N, int K, __half* out, cudaStream_t s) {
+  B2W_CHECK(K % 64 == 0 && N % 8 == 0, "bstep_pack_atoms: shape");
+  bs_pack_atoms_kernel<<<1024, 256, 0, s>>>(W, N, K, reinterpret_cast<uint4*>(out));
+  B2W_LAUNCHED();
+}
+void bstep_row_sums(const __half* W, int N, int K, float* out, cudaStream_t s) {
+  bs_row_sums_kernel<<<ceil_div(N, 8), 256, 0, s>>>(W, N, K, out);
+  B2W_LAUNCHED();
+}
+
+static size_t bstep_smem_bytes(const BStepArgs& a) { return (size_t)kBsSlots * kBsAtomBytes + kBsKvBytes + (size_t)a.u_bytes + 1024; }
+
+void bstep_configure() { B2W_CUDA(cudaFuncSetAttribute(bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); }
+
+int bstep_phase_count(int L) { return 3 + 9 * L; }
+
+size_t bstep_xpart_floats(const BStepArgs& a) { return (size_t)a.n_chunks * a.H * kDsXSplits * kBsXQ * 66; }
+
+bool bstep_supported(int num_sms, BStepArgs& a) {
+  if (a.R < 1 || a.R > kBsMaxRows || a.d % 64 != 0 || a.d > 1280 || a.d != 64 * a.H || a.L > 32 || a.rows_per_chunk > kBsXQ || num_sms < 8) return false;
+  if ((a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || a.vpad % 4 != 0) return false;
+  a.NP = bs_ceil16(a.R);
+  const int d = a.d, G = num_sms;
+  // activation tiles of the busiest GEMM phase (an even share of the atoms, rounded up) and the condition for two segments
+  int max_atoms = 1;
+  const int Ns[3] = {3 * d, 4 * d, d}, Ks[3] = {d, d, 4 * d};
+  for (int i = 0; i < 3; ++i) {
+    const int KA = Ks[i] / 64;
+    const long long A = (long long)((Ns[i] + 127) / 128) * KA;
+    const int share = (int)((A + G - 1) / G);
+    if (share > KA) return false;  // a CTA's range would span more than two n-blocks
+    max_atoms = std::max(max_atoms, share);
+  }
+  size_t u = (size_t)max_atoms * a.NP * 128;
+  u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
+  u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
+  u = std::max(u, (size_t)(16 * a.n_ctx + 16 * 64) * 4 + (size_t)16 * a.n_ctx);              // self-attention scores / q / slots
+  a.u_bytes = (int)((u + 1023) & ~size_t(1023));
+  int nhalves, Rh, NPh;
+  bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
+  if ((size_t)(d / 64) * NPh * 128 > (size_t)kBsKvBytes + a.u_bytes) return false;
+  const size_t smem = bstep_smem_bytes(a);
+  if (smem > 224 * 1024) return false;
+  int per_sm = 0;
+  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bstep_kernel, kBsLaunch, smem));
+  return per_sm >= 1;
+}
+
+void bstep_launch(const BStepArgs& a, int grid, cudaStream_t s) {
+  const size_t smem = bstep_smem_bytes(a);
+  B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
+  BStepArgs copy = a;
+  void* args[] = {&copy};
+  B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bstep_kernel), dim3(grid), dim3(kBsLaunch), args, smem, s));
+  count_launch();
+}
+
+}  // namespace b2w

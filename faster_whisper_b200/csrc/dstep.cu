@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "decode.h"
 #include "dstep.h"
+#include "step_common.cuh"
 
 namespace b2w {
 
@@ -46,34 +47,6 @@ constexpr int kDsScLd = kDsXKeysMax + 4;   // fp32 score rows
 constexpr int kDsPLd = kDsXKeysMax + 8;    // fp16 probability rows
 constexpr int kDsQLd = 96;                 // fp16 query rows
 constexpr int kDsXScratch = kDsXQ * kDsQLd * 2 + kDsXQ * kDsScLd * 4 + kDsXQ * kDsPLd * 2 + 2 * kDsXQ * 64 * 4 + 64;
-
-__device__ __forceinline__ void ds_mma(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ds_ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* smem_row) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(smem_u32(smem_row)));
-}
-__device__ __forceinline__ void ds_cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted on an mbarrier
-__device__ __forceinline__ void ds_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void ds_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ds_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long ds_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // barrier of the 256 compute threads (the producer warps never join it)
 __device__ __forceinline__ void ds_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }

@@ -440,6 +440,7 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
   search_configure();
   gemm_configure();
   dstep_configure();
+  bstep_configure();
   {
     // decoder weights re-laid out as the persistent step kernel's tile stream (a second copy: ~1.6 GB for large-v3)
     std::vector<DLayer> hl(L);
@@ -484,6 +485,33 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
     }
     m->d_layers = dalloc<DLayer>(L);
     B2W_CUDA(cudaMemcpy(m->d_layers, hl.data(), L * sizeof(DLayer), cudaMemcpyHostToDevice));
+    // the same (possibly de-quantised) weights as the many-row step kernel's atom stream (bstep.cu) + row sums for the deferred LayerNorm
+    if (m->use_bstep && dt % 64 == 0 && dt == 64 * cfg.n_text_head) {
+      std::vector<BLayer> bl(L);
+      auto atoms = [&](const __half* W, int N, int K) -> const __half* {
+        __half* out = reinterpret_cast<__half*>(up.alloc<unsigned char>(bstep_atoms_bytes(N, K)));
+        bstep_pack_atoms(W, N, K, out, m->stream);
+        return out;
+      };
+      auto sums = [&](const __half* W, int N, int K) -> const float* {
+        float* out = up.alloc<float>((size_t)N);
+        bstep_row_sums(W, N, K, out, m->stream);
+        return out;
+      };
+      for (int i = 0; i < L; ++i) {
+        const DecLayerW& D = m->dec[i];
+        bl[i].wt[0] = atoms(D.wqkv, 3 * dt, dt); bl[i].bias[0] = D.bqkv; bl[i].wsum[0] = sums(D.wqkv, 3 * dt, dt);
+        bl[i].wt[1] = atoms(D.wo, dt, dt);       bl[i].bias[1] = D.bo;
+        bl[i].wt[2] = atoms(D.wq_x, dt, dt);     bl[i].bias[2] = D.bq_x; bl[i].wsum[1] = sums(D.wq_x, dt, dt);
+        bl[i].wt[3] = atoms(D.wo_x, dt, dt);     bl[i].bias[3] = D.bo_x;
+        bl[i].wt[4] = atoms(D.w1, 4 * dt, dt);   bl[i].bias[4] = D.b1;   bl[i].wsum[2] = sums(D.w1, 4 * dt, dt);
+        bl[i].wt[5] = atoms(D.w2, dt, 4 * dt);   bl[i].bias[5] = D.b2;
+      }
+      m->logit_atoms = atoms(m->logit_w, m->vpad, dt);
+      m->d_blayers = dalloc<BLayer>(L);
+      B2W_CUDA(cudaMemcpy(m->d_blayers, bl.data(), L * sizeof(BLayer), cudaMemcpyHostToDevice));
+      m->bstep_packed = true;
+    }
     m->d_bar = dalloc<unsigned>(4);
     B2W_CUDA(cudaMemset(m->d_bar, 0, 4 * sizeof(unsigned)));
   }
@@ -665,6 +693,12 @@ static void ensure_decoder_ws(Model* m, int chunks, int slots) {
     m->d_ao = dalloc<__half>((size_t)kMaxRows * dt);
     m->d_h = dalloc<__half>((size_t)kMaxRows * 4 * dt);
     m->d_logits = dalloc<float>((size_t)kMaxRows * m->vpad);
+    m->d_qkv32 = dalloc<float>((size_t)kMaxRows * 3 * dt);
+    m->d_cq32 = dalloc<float>((size_t)kMaxRows * dt);
+    m->d_h32 = dalloc<float>((size_t)kMaxRows * 4 * dt);
+    m->d_h16 = dalloc<__half>((size_t)kMaxRows * 4 * dt);
+    m->d_xn16 = dalloc<__half>((size_t)kMaxRows * dt);
+    m->d_stats = dalloc<float>((size_t)3 * L * kMaxRows * 2 + 4);
     B2W_CUDA(cudaMemset(m->d_xn, 0, (size_t)kMaxRows * dt * 2));
     B2W_CUDA(cudaMemset(m->d_ao, 0, (size_t)kMaxRows * dt * 2));
     B2W_CUDA(cudaMemset(m->d_h, 0, (size_t)kMaxRows * 4 * dt * 2));
@@ -1031,6 +1065,17 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     B2W_CUDA(cudaStreamSynchronize(s));
   }
   const int splits = pick_splits(m, n, K);
+  if (!sp.fake_logits) {
+    // lazily-grown partial buffer of the cross attention: sized before any kernel argument block captures the pointer
+    size_t need_part = cross_attn_partial_floats(n, c.n_text_head, K, splits);
+    need_part = std::max(need_part, (size_t)n * c.n_text_head * kDsXSplits * 8 * 66);
+    if (need_part > m->d_xpart_floats) {
+      B2W_CUDA(cudaStreamSynchronize(s));
+      if (m->d_xpart) cudaFree(m->d_xpart);
+      m->d_xpart = dalloc<float>(need_part);
+      m->d_xpart_floats = need_part;
+    }
+  }
   // persistent single-kernel step for <= 8 rows
   DStepArgs ds{};
   bool use_dstep = m->use_dstep && !sp.fake_logits && R <= 8 && !m->use_ref_gemv && c.n_text_layer <= 32;
@@ -1052,6 +1097,35 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     }
     if (m->dstep_grid <= 0) use_dstep = false;
   }
+  // persistent many-row step (bstep.cu) for everything the <= 8-row kernel does not take
+  BStepArgs bs{};
+  bool use_bstep = m->use_bstep && m->bstep_packed && !sp.fake_logits && !m->use_ref_gemv && (m->bstep_all || !use_dstep) && R <= kBsMaxRows;
+  if (use_bstep) {
+    bs.layers = m->d_blayers; bs.L = c.n_text_layer; bs.tok_emb = m->tok_emb; bs.pos_emb = m->dec_pos;
+    bs.logit_atoms = m->logit_atoms; bs.logit_bias = m->logit_b;
+    bs.R = R; bs.d = c.n_text_state; bs.H = c.n_text_head; bs.n_ctx = c.n_text_ctx; bs.slots = K; bs.T = 1500;
+    bs.vpad = m->vpad; bs.n_vocab = c.n_vocab; bs.n_chunks = n; bs.rows_per_chunk = K;
+    bs.stop_phase = m->bstep_stop;
+    if (const char* v = getenv("B2W_BSTEP_STOP")) bs.stop_phase = atoi(v);  // re-read per call: tools/bstep_bisect.py steps it
+    bs.rows = sb.rows; bs.tokens_in = sb.tokens_in;
+    bs.x = m->d_x; bs.qkv32 = m->d_qkv32; bs.cq32 = m->d_cq32; bs.h32 = m->d_h32; bs.ao = m->d_ao; bs.h16 = m->d_h16; bs.xn16 = m->d_xn16;
+    bs.stats = m->d_stats; bs.logits = m->d_logits;
+    bs.kcache = m->kcache; bs.vcache = m->vcache; bs.kv_layer_stride = (long long)m->kv_elems;
+    bs.anc = sb.anc; bs.anc_buf_stride = (long long)n * K * c.n_text_ctx;
+    bs.bind = m->d_bind; bs.xcounters = m->d_counters + 64; bs.bar = m->d_bar; bs.prof = m->d_prof;
+    use_bstep = bstep_supported(m->num_sms, bs);
+    if (use_bstep) {
+      use_dstep = false;
+      const size_t need_part = std::max(bstep_xpart_floats(bs), cross_attn_partial_floats(n, c.n_text_head, K, splits));
+      if (need_part > m->d_xpart_floats) {
+        B2W_CUDA(cudaStreamSynchronize(s));
+        if (m->d_xpart) cudaFree(m->d_xpart);
+        m->d_xpart = dalloc<float>(need_part);
+        m->d_xpart_floats = need_part;
+      }
+      bs.xpart = m->d_xpart;
+    }
+  }
   m->h_params = sp;
   B2W_CUDA(cudaMemcpyAsync(const_cast<SearchParams*>(sb.params), &m->h_params, sizeof(SearchParams), cudaMemcpyHostToDevice, s));
   bind_encoded(m, e, chunk0);
@@ -1059,7 +1133,9 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     if (sp.fake_logits) {
       fake_logits(m->d_logits, R, sb, s);
     } else {
-      if (use_dstep) {
+      if (use_bstep) {
+        bstep_launch(bs, m->num_sms, s);
+      } else if (use_dstep) {
         dstep_launch(ds, m->dstep_grid, s);
       } else {
         decoder_layers(m, n, K, K, splits, P - 1);
@@ -1078,7 +1154,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : 0, 0, 0};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : (use_bstep ? 3 : 0), bs.stop_phase, 0};
     memcpy(k, misc, sizeof misc);
   }
   if (sp.fake_logits == 0) {
@@ -1140,6 +1216,28 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       }
     }
     m->decode_steps += steps_run;
+    if (m->d_prof && use_bstep) {
+      B2W_CUDA(cudaStreamSynchronize(s));
+      const int L = c.n_text_layer, nstamps = 1 + 2 * (2 + 9 * L) + 1;
+      std::vector<unsigned long long> t(nstamps);
+      B2W_CUDA(cudaMemcpy(t.data(), m->d_prof, nstamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      static const char* names[9] = {"qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "gelu", "ffn2"};
+      double work[9] = {0}, wait[9] = {0};
+      unsigned long long prev = t[2];
+      for (int l = 0; l < L; ++l)
+        for (int ph = 0; ph < 9; ++ph) {
+          const int bi = 1 + 2 * (1 + l * 9 + ph);
+          work[ph] += double(t[bi] - prev);
+          wait[ph] += double(t[bi + 1] - t[bi]);
+          prev = t[bi + 1];
+        }
+      const int bf = 1 + 2 * (1 + 9 * L);
+      fprintf(stderr, "[bstep prof] last step (R=%d): total %.1f us; embed %.1f us; final-LN %.1f us; logits %.1f us\n", R, (t[nstamps - 1] - t[0]) / 1e3,
+              (t[2] - t[0]) / 1e3, (t[bf] - prev) / 1e3, (t[nstamps - 1] - t[bf + 1]) / 1e3);
+      for (int ph = 0; ph < 9; ++ph)
+        fprintf(stderr, "[bstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
+                wait[ph] / L / 1e3, L);
+    }
     if (m->d_prof && use_dstep) {
       B2W_CUDA(cudaStreamSynchronize(s));
       const int L = c.n_text_layer, nstamps = 1 + 2 * (1 + 8 * L) + 1;
@@ -1292,6 +1390,11 @@ int b2w_model_create(const b2w_config* cfg, const b2w_tensor* tensors, int32_t n
     if (const char* v = getenv("B2W_DSTEP")) {
       m->use_dstep = strcmp(v, "0") != 0;
     }
+    if (const char* v = getenv("B2W_BSTEP")) {
+      m->use_bstep = strcmp(v, "0") != 0;
+      m->bstep_all = strcmp(v, "all") == 0;
+    }
+    if (const char* v = getenv("B2W_BSTEP_STOP")) m->bstep_stop = atoi(v);
     if (const char* v = getenv("B2W_XATTN_IMPL")) m->use_mma_xattn = strcmp(v, "simt") != 0;
     if (const char* v = getenv("B2W_DSTEP_PROF")) {
       if (strcmp(v, "0") != 0) {
@@ -1886,6 +1989,37 @@ int b2w_debug_gemv(int32_t device, int32_t impl, const float* x, const float* w,
     B2W_CUDA(cudaMemcpy(tmp.data(), dy, tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (int r = 0; r < R; ++r) memcpy(y_out + (size_t)r * N, tmp.data() + (size_t)r * Np, (size_t)N * 4);
     cudaFree(dx); cudaFree(dw); cudaFree(db); cudaFree(dy); cudaFree(hx); cudaFree(hw);
+  });
+}
+
+int b2w_debug_fetch(b2w_model* h, int32_t which, float* out, int64_t n) {
+  return guarded([&] {
+    B2W_CHECK(h && out && n >= 0, "null argument");
+    Model* m = &h->m;
+    DeviceGuard g(m->device);
+    B2W_CHECK(m->d_x, "no decoder workspace yet");
+    B2W_CUDA(cudaStreamSynchronize(m->stream));
+    const float* f32 = nullptr;
+    const __half* f16 = nullptr;
+    switch (which) {
+      case 0: f32 = m->d_x; break;
+      case 1: f32 = m->d_qkv32; break;
+      case 2: f32 = m->d_cq32; break;
+      case 3: f32 = m->d_h32; break;
+      case 4: f16 = m->d_ao; break;
+      case 5: f16 = m->d_h16; break;
+      case 6: f16 = m->d_xn16; break;
+      case 7: f32 = m->d_stats; break;
+      case 8: f32 = m->d_logits; break;
+      default: throw Error("b2w_debug_fetch: unknown buffer", true);
+    }
+    if (f32) {
+      B2W_CUDA(cudaMemcpy(out, f32, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<__half> tmp((size_t)n);
+      B2W_CUDA(cudaMemcpy(tmp.data(), f16, (size_t)n * sizeof(__half), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < n; ++i) out[i] = __half2float(tmp[(size_t)i]);
+    }
   });
 }
 

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "decode.h"
+#include "bstep.h"
 #include "dstep.h"
 #include "engine.h"
 
@@ -126,6 +127,15 @@ struct Model {
   // de-quantised values (B2W_W8_FAKE=1: the reference the int8 stream is tested against).
   bool w8 = false, w8_fake = false;
   bool use_dstep = true;
+  // many-row persistent step kernel (bstep.cu): decoder weights as 16 KB UMMA atoms + per-row sums for the deferred LayerNorm
+  bool use_bstep = true;     // B2W_BSTEP=0 falls back to the multi-kernel step for R > 8
+  bool bstep_all = false;    // B2W_BSTEP=all: also for R <= 8 (instead of dstep_kernel)
+  int bstep_stop = 0;        // B2W_BSTEP_STOP=n: run only the first n grid phases of every step (debug)
+  bool bstep_packed = false;
+  BLayer* d_blayers = nullptr;
+  const __half* logit_atoms = nullptr;
+  float *d_qkv32 = nullptr, *d_cq32 = nullptr, *d_h32 = nullptr, *d_stats = nullptr;
+  __half *d_h16 = nullptr, *d_xn16 = nullptr;
   bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)
   DecBindings h_bind{};
   SearchParams h_params{};

@@ -56,7 +56,7 @@ ABI_SYMBOLS = (
     "b2w_model_info", "b2w_model_sync", "b2w_logmel", "b2w_logmel_frames", "b2w_encode", "b2w_encode_audio",
     "b2w_encoded_shape", "b2w_encoded_to_host", "b2w_encoded_free", "b2w_generate", "b2w_gen_opts_default",
     "b2w_detect_language", "b2w_align", "b2w_model_set_alignment_heads", "b2w_timing_enable", "b2w_timing_reset", "b2w_timing_get", "b2w_span_begin", "b2w_span_end",
-    "b2w_counters_get", "b2w_debug_gemm", "b2w_debug_attention", "b2w_debug_gemv", "b2w_debug_logits",
+    "b2w_counters_get", "b2w_debug_gemm", "b2w_debug_attention", "b2w_debug_gemv", "b2w_debug_logits", "b2w_debug_fetch",
 )
 
 
@@ -115,6 +115,7 @@ def load_library():
         lib.b2w_debug_gemv.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p]
         lib.b2w_debug_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        lib.b2w_debug_fetch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
         if lib.b2w_abi_version() != 1:
             raise RuntimeError("libb200whisper ABI version mismatch")
         _lib = lib
@@ -528,6 +529,15 @@ class Whisper:
         rep = self._replica_for(enc)
         with rep.lock:
             _check(rep._lib.b2w_debug_logits(rep._h, enc._handle, _ptr(tokens), n, B, _ptr(out)))
+        return out
+
+
+    def debug_fetch(self, which: int, n: int, replica: int = 0) -> np.ndarray:
+        """Decoder workspace buffer `which` of the last decode step as float32 (tests / tools only)."""
+        out = np.empty(int(n), dtype=np.float32)
+        rep = self._replicas[replica]
+        with rep.lock:
+            _check(rep._lib.b2w_debug_fetch(rep._h, int(which), _ptr(out), int(n)))
         return out
 
 
