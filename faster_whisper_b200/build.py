@@ -65,7 +65,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             list(pool.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC"])
+        # link to a temporary name and rename: a concurrent reader (a gpurun snapshot, another process) never sees a half-written library
+        tmp = LIB + ".tmp%d" % os.getpid()
+        run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC"])
+        os.replace(tmp, LIB)
     return LIB
 
 

@@ -5,7 +5,8 @@ The reference loads a CTranslate2 directory (``model.bin`` + ``config.json`` + `
 exists offline, so the native on-disk format here is the plainest possible: ``weights.npz`` (OpenAI-Whisper
 state-dict names, float16/float32) + ``b2w_config.json`` (geometry) and, optionally, ``tokenizer.json`` /
 ``preprocessor_config.json`` exactly as in a CTranslate2 directory.  Directories holding a CTranslate2 ``model.bin`` are
-read through ``ct2_format.py`` (layout restated, unpinned).
+read through ``ct2_format.py`` (layout restated, unpinned); directories holding a ``transformers``
+checkpoint (``config.json`` + ``model.safetensors``) through ``hf_format.py`` (pinned against transformers' own writer).
 """
 
 from __future__ import annotations
@@ -44,16 +45,25 @@ def load_model_dir(path: str, files: Optional[dict] = None) -> Tuple[WhisperDims
         with open(p, "rb") as f:
             return f.read()
 
-    cfg = read("b2w_config.json")
-    wts = read("weights.npz")
-    if cfg is None or wts is None:
-        if read("model.bin") is not None:
+    def exists(name):  # never consumes a file-like entry and never reads a multi-GB blob just to probe
+        return bool(files and name in files) or bool(path and os.path.isfile(os.path.join(path, name)))
+
+    if not (exists("b2w_config.json") and exists("weights.npz")):
+        if exists("model.bin"):
             # a CTranslate2 directory, as the reference loads it (ct2_format.py; layout restated, unpinned)
             from .ct2_format import load_ct2_dir
 
             dims, weights, _ = load_ct2_dir(path, files)
             return dims, weights
+        from .hf_format import is_hf_dir, load_hf_dir
+
+        if is_hf_dir(path, files):
+            # a transformers checkpoint (config.json + model.safetensors), pinned by tests/test_hf_loader.py
+            dims, weights, _ = load_hf_dir(path, files)
+            return dims, weights
         raise RuntimeError(f"Unable to open file 'weights.npz' in model '{path}'")
+    cfg = read("b2w_config.json")
+    wts = read("weights.npz")
     dims = WhisperDims(**json.loads(cfg))
     with np.load(io.BytesIO(wts)) as z:
         weights = {k: z[k] for k in z.files}

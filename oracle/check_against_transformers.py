@@ -66,7 +66,8 @@ def to_hf_state(weights, dims):
     return sd
 
 
-def main():
+def run_check():
+    """Returns (encoder, logits, incremental-vs-parallel) max abs differences; tests/test_oracle_transformers.py asserts on them."""
     from transformers import WhisperConfig, WhisperForConditionalGeneration
 
     dims = custom_dims(d=128, heads=2, enc_layers=2, dec_layers=2, n_vocab=51864)
@@ -102,8 +103,14 @@ def main():
     e1 = float((enc - enc_hf).abs().max())
     e2 = float((logits - out_hf).abs().max())
     e3 = float((inc - logits).abs().max())
+    return e1, e2, e3
+
+
+def main():
+    e1, e2, e3 = run_check()
     print(f"encoder max|diff| {e1:.3e}  logits max|diff| {e2:.3e}  incremental-vs-parallel {e3:.3e}")
-    assert e1 < 2e-4 and e2 < 2e-3 and e3 < 2e-3
+    # measured here (torch 2.11 CPU fp32): 2.3e-6 / 1.0e-5 / 1.2e-5
+    assert e1 < 2e-5 and e2 < 1e-4 and e3 < 1e-4
     print("OK")
 
 
