@@ -1420,6 +1420,7 @@ int b2w_model_info(const b2w_model* m, b2w_config* cfg_out, int32_t* device_out)
 
 int b2w_model_sync(b2w_model* h) {
   return guarded([&] {
+    B2W_CHECK(h, "null model");
     DeviceGuard g(h->m.device);
     B2W_CUDA(cudaStreamSynchronize(h->m.stream));
   });
@@ -1866,12 +1867,14 @@ int b2w_span_end(b2w_model* h, double* ms_out) {
 
 int b2w_timing_enable(b2w_model* h, int32_t on) {
   return guarded([&] {
+    B2W_CHECK(h, "null model");
     drain_timers(&h->m);
     h->m.timing = on != 0;
   });
 }
 int b2w_timing_reset(b2w_model* h) {
   return guarded([&] {
+    B2W_CHECK(h, "null model");
     DeviceGuard g(h->m.device);
     drain_timers(&h->m);
     for (int i = 0; i < B2W_T_COUNT; ++i) {
@@ -1885,6 +1888,7 @@ int b2w_timing_reset(b2w_model* h) {
 }
 int b2w_timing_get(b2w_model* h, double ms_out[B2W_T_COUNT], int64_t counts_out[B2W_T_COUNT]) {
   return guarded([&] {
+    B2W_CHECK(h, "null model");
     DeviceGuard g(h->m.device);
     drain_timers(&h->m);
     for (int i = 0; i < B2W_T_COUNT; ++i) {
@@ -1895,6 +1899,7 @@ int b2w_timing_get(b2w_model* h, double ms_out[B2W_T_COUNT], int64_t counts_out[
 }
 int b2w_counters_get(b2w_model* h, int64_t* launches, int64_t* decode_steps, double* decode_alg_bytes) {
   return guarded([&] {
+    B2W_CHECK(h, "null model");
     if (launches) *launches = h->m.launches;
     if (decode_steps) *decode_steps = h->m.decode_steps;
     if (decode_alg_bytes) *decode_alg_bytes = h->m.decode_alg_bytes;

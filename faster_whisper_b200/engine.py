@@ -187,16 +187,26 @@ class StorageView:
         if self._handle is None:
             raise ValueError("empty StorageView")
         out = np.empty(self.shape, dtype=np.float32)
-        _check(_lib.b2w_encoded_to_host(self._owner._replica_for(self)._h, self._handle, _ptr(out)))
+        _check(_lib.b2w_encoded_to_host(self._owner._replica_for(self).handle, self._handle, _ptr(out)))
         return out
 
-    def __del__(self):
+    def _release(self):
+        """Frees the device buffer (idempotent).  Goes through the owning replica: an encoder output returns its memory to the
+        model's pool, so it must never outlive the native model (``Whisper.unload_model`` releases live outputs first)."""
         h, self._handle = getattr(self, "_handle", None), None
-        if h is not None and _lib is not None:
-            try:
-                _lib.b2w_encoded_free(h)
-            except Exception:  # noqa: BLE001
-                pass
+        rep = getattr(self, "_replica", None)
+        if h is None or _lib is None:
+            return
+        if rep is not None:
+            rep.release_output(h, id(self))
+        else:
+            _lib.b2w_encoded_free(h)
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 @dataclass
@@ -222,11 +232,40 @@ class _Replica:
         _check(lib.b2w_model_create(C.byref(cfg), arr, len(tensors), device, compute_type.encode(), C.byref(h)))
         self._h = h
         self.lock = threading.Lock()
+        self._outputs = {}  # id(StorageView) -> weakref: device-resident encoder outputs that borrow from this model's pool
+        self._out_lock = threading.Lock()
+
+    def track_output(self, sv) -> None:
+        import weakref
+
+        with self._out_lock:
+            self._outputs[id(sv)] = weakref.ref(sv)
+
+    def release_output(self, handle, key=None) -> None:
+        with self._out_lock:
+            self._outputs.pop(key, None)
+            if self._h:  # after close() the native model (and every buffer it handed out) is already gone
+                self._lib.b2w_encoded_free(handle)
 
     def close(self):
-        h, self._h = self._h, None
+        """Destroys the native model.  Live encoder outputs are detached first: they become empty StorageViews instead of
+        dangling pointers into a freed pool (use-after-free in b2w_encoded_free after unload_model)."""
+        with self._out_lock:
+            views = [r() for r in self._outputs.values()]
+            self._outputs.clear()
+        for sv in views:
+            if sv is not None:
+                sv._release()
+        with self._out_lock:
+            h, self._h = self._h, None
         if h:
             self._lib.b2w_model_destroy(h)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("the model is unloaded: call load_model() first")
+        return self._h
 
     def __del__(self):
         try:
@@ -298,6 +337,9 @@ class Whisper:
         self.compute_type = "float16" if compute_type in ("default", "auto") else compute_type
         self._replicas = [_Replica(lib, cfg, tensors, d, compute_type) for d in idx for _ in range(max(1, inter_threads))]
         self._keep = []  # weights are on the device now
+        # what load_model() needs to rebuild the replicas after unload_model() (a path is re-read; an in-memory dict is the caller's)
+        self._reload = dict(model_path=model_path, files=files, dims=dims if model_path == "" or weights is not None else None,
+                            weights=weights if not model_path else None, compute_type=compute_type, inter_threads=inter_threads)
         self._rr = 0
         self._rr_lock = threading.Lock()
         if getattr(self, "_config_alignment_heads", None):
@@ -333,9 +375,25 @@ class Whisper:
     def _replica_for(self, sv: StorageView) -> _Replica:
         return getattr(sv, "_replica", None) or self._replicas[0]
 
-    def unload_model(self):
+    @property
+    def model_is_loaded(self) -> bool:
+        return bool(self._replicas) and all(r._h for r in self._replicas)
+
+    def unload_model(self, to_cpu: bool = False):
+        """``ctranslate2`` ``Whisper.unload_model``: frees the device memory of every replica.  Encoder outputs still alive are
+        released first and read as empty afterwards; every other call raises until ``load_model()``."""
         for r in self._replicas:
             r.close()
+
+    def load_model(self, keep_cache: bool = False):
+        """``ctranslate2`` ``Whisper.load_model``: rebuilds the replicas dropped by ``unload_model`` (no-op while loaded)."""
+        if self.model_is_loaded:
+            return
+        rl = self._reload
+        fresh = Whisper(rl["model_path"], "cuda", device_index=self._device_index, compute_type=rl["compute_type"],
+                        inter_threads=rl["inter_threads"], files=rl["files"], dims=rl["dims"] or (self.dims if rl["weights"] is not None else None),
+                        weights=rl["weights"], tokens=self.tokens)
+        self._replicas, fresh._replicas = fresh._replicas, []
 
     # ---- encode (transcribe.py:209,1400) ----
     def encode(self, features: Union[StorageView, np.ndarray], to_cpu: bool = False) -> StorageView:
@@ -348,9 +406,10 @@ class Whisper:
         rep = self._next_replica()
         h = C.c_void_p()
         with rep.lock:
-            _check(rep._lib.b2w_encode(rep._h, _ptr(arr), arr.shape[0], C.byref(h)))
+            _check(rep._lib.b2w_encode(rep.handle, _ptr(arr), arr.shape[0], C.byref(h)))
         sv = StorageView(handle=h, owner=self, shape=(arr.shape[0], self.dims.n_audio_ctx, self.dims.n_audio_state))
         sv._replica = rep
+        rep.track_output(sv)
         if to_cpu:
             return StorageView.from_array(sv.numpy())
         return sv
@@ -367,9 +426,10 @@ class Whisper:
         feats = np.empty((n, self.dims.n_mels, 3000), dtype=np.float32) if return_features else None
         h = C.c_void_p()
         with rep.lock:
-            _check(rep._lib.b2w_encode_audio(rep._h, ptrs, lens, n, _ptr(feats), C.byref(h)))
+            _check(rep._lib.b2w_encode_audio(rep.handle, ptrs, lens, n, _ptr(feats), C.byref(h)))
         sv = StorageView(handle=h, owner=self, shape=(n, self.dims.n_audio_ctx, self.dims.n_audio_state))
         sv._replica = rep
+        rep.track_output(sv)
         return (sv, feats) if return_features else sv
 
     def _as_encoded(self, features: Union[StorageView, np.ndarray]) -> StorageView:
@@ -432,7 +492,7 @@ class Whisper:
         scores = np.zeros((B, H), dtype=np.float32)
         nsp = np.zeros((B,), dtype=np.float32)
         with rep.lock:
-            _check(rep._lib.b2w_generate(rep._h, enc._handle if enc is not None else None, _ptr(pr), P, B, C.byref(o),
+            _check(rep._lib.b2w_generate(rep.handle, enc._handle if enc is not None else None, _ptr(pr), P, B, C.byref(o),
                                          _ptr(ids), _ptr(lens), _ptr(scores), _ptr(nsp)))
         out = []
         for b in range(B):
@@ -453,7 +513,7 @@ class Whisper:
         nl = self.tokens.num_languages
         probs = np.zeros((enc.shape[0], nl), dtype=np.float32)
         with rep.lock:
-            _check(rep._lib.b2w_detect_language(rep._h, enc._handle, _ptr(probs)))
+            _check(rep._lib.b2w_detect_language(rep.handle, enc._handle, _ptr(probs)))
         names = (LANGUAGE_CODES + [f"xx{i}" for i in range(1, 8)])[:nl]
         out = []
         for b in range(enc.shape[0]):
@@ -479,7 +539,7 @@ class Whisper:
             probs = np.zeros(max(1, len(toks)), np.float32)
             n_pairs = C.c_int32(0)
             with rep.lock:
-                _check(rep._lib.b2w_align(rep._h, enc._handle, b, _ptr(start), len(start), _ptr(toks), len(toks), nf, int(median_filter_width),
+                _check(rep._lib.b2w_align(rep.handle, enc._handle, b, _ptr(start), len(start), _ptr(toks), len(toks), nf, int(median_filter_width),
                                           _ptr(pairs), cap, C.byref(n_pairs), _ptr(probs)))
             results.append(WhisperAlignmentResult([(int(a), int(t)) for a, t in pairs[: n_pairs.value]], [float(p) for p in probs[: len(toks)]]))
         return results
@@ -488,20 +548,20 @@ class Whisper:
         """(layer, head) pairs from a converted model's config.json ``alignment_heads``; None restores the default."""
         flat = np.ascontiguousarray([x for p in (heads or []) for x in p], dtype=np.int32)
         for rep in self._replicas:
-            _check(rep._lib.b2w_model_set_alignment_heads(rep._h, _ptr(flat) if flat.size else None, flat.size // 2))
+            _check(rep._lib.b2w_model_set_alignment_heads(rep.handle, _ptr(flat) if flat.size else None, flat.size // 2))
 
     # ---- measurement / test hooks ----
     def timing(self, enable: Optional[bool] = None, reset: bool = False, replica: int = 0) -> Dict[str, float]:
         rep = self._replicas[replica]
         if enable is not None:
-            _check(rep._lib.b2w_timing_enable(rep._h, int(enable)))
+            _check(rep._lib.b2w_timing_enable(rep.handle, int(enable)))
         if reset:
-            _check(rep._lib.b2w_timing_reset(rep._h))
+            _check(rep._lib.b2w_timing_reset(rep.handle))
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()
-        _check(rep._lib.b2w_timing_get(rep._h, ms, cnt))
+        _check(rep._lib.b2w_timing_get(rep.handle, ms, cnt))
         ln, st, by = C.c_int64(), C.c_int64(), C.c_double()
-        _check(rep._lib.b2w_counters_get(rep._h, C.byref(ln), C.byref(st), C.byref(by)))
+        _check(rep._lib.b2w_counters_get(rep.handle, C.byref(ln), C.byref(st), C.byref(by)))
         d = {f"{n}_ms": ms[i] for i, n in enumerate(T_STAGES)}
         d.update(launches=ln.value, decode_steps=st.value, decode_alg_bytes=by.value)
         return d
@@ -509,18 +569,18 @@ class Whisper:
     def span_begin(self, replica: int = 0):
         """CUDA event on the engine stream: start of a device-timed region (bench.py)."""
         rep = self._replicas[replica]
-        _check(rep._lib.b2w_span_begin(rep._h))
+        _check(rep._lib.b2w_span_begin(rep.handle))
 
     def span_end(self, replica: int = 0) -> float:
         """Second event + wait; milliseconds between the two events on the engine stream."""
         rep = self._replicas[replica]
         ms = C.c_double()
-        _check(rep._lib.b2w_span_end(rep._h, C.byref(ms)))
+        _check(rep._lib.b2w_span_end(rep.handle, C.byref(ms)))
         return ms.value
 
     def sync(self):
         for r in self._replicas:
-            _check(r._lib.b2w_model_sync(r._h))
+            _check(r._lib.b2w_model_sync(r.handle))
 
     def debug_logits(self, enc: StorageView, tokens: np.ndarray) -> np.ndarray:
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
@@ -528,7 +588,7 @@ class Whisper:
         out = np.empty((B, n, self.dims.n_vocab), dtype=np.float32)
         rep = self._replica_for(enc)
         with rep.lock:
-            _check(rep._lib.b2w_debug_logits(rep._h, enc._handle, _ptr(tokens), n, B, _ptr(out)))
+            _check(rep._lib.b2w_debug_logits(rep.handle, enc._handle, _ptr(tokens), n, B, _ptr(out)))
         return out
 
 
@@ -537,7 +597,7 @@ class Whisper:
         out = np.empty(int(n), dtype=np.float32)
         rep = self._replicas[replica]
         with rep.lock:
-            _check(rep._lib.b2w_debug_fetch(rep._h, int(which), _ptr(out), int(n)))
+            _check(rep._lib.b2w_debug_fetch(rep.handle, int(which), _ptr(out), int(n)))
         return out
 
 

@@ -163,3 +163,52 @@ def test_ct2_model_bin_round_trip(tmp_path):
     assert np.all(np.abs(w8[k] - w[k]) <= 0.5 * step + 1e-7)
     with pytest.raises(ValueError):
         ct2_format.read_model_bin(b"\\xff\\xff\\xff\\xff garbage")
+
+
+def test_unloaded_model_is_never_dereferenced():
+    """StorageViews that outlive unload_model() used to free into a destroyed native model.  Pure host logic here (no
+    GPU): a replica hands its live outputs back before it is destroyed, and every later call raises instead of passing NULL."""
+    import ctypes
+    import gc
+
+    from faster_whisper_b200 import engine as E
+
+    class FakeLib:
+        def __init__(self):
+            self.freed, self.destroyed = [], []
+
+        def b2w_encoded_free(self, h):
+            assert not self.destroyed, "encoder output freed after its model"
+            self.freed.append(h)
+
+        def b2w_model_destroy(self, h):
+            self.destroyed.append(h)
+
+    rep = E._Replica.__new__(E._Replica)
+    rep._lib, rep.device, rep._h = FakeLib(), 0, ctypes.c_void_p(1234)
+    import threading
+
+    rep.lock, rep._out_lock, rep._outputs = threading.Lock(), threading.Lock(), {}
+    old_lib, E._lib = E._lib, rep._lib
+    try:
+        a = E.StorageView(handle=ctypes.c_void_p(1), shape=(1, 1500, 8))
+        b = E.StorageView(handle=ctypes.c_void_p(2), shape=(1, 1500, 8))
+        for sv in (a, b):
+            sv._replica = rep
+            rep.track_output(sv)
+        del b, sv
+        gc.collect()
+        assert len(rep._lib.freed) == 1 and len(rep._outputs) == 1
+        rep.close()
+        assert len(rep._lib.freed) == 2 and rep._lib.destroyed and a._handle is None
+        with pytest.raises(ValueError):
+            a.numpy()
+        with pytest.raises(RuntimeError, match="unloaded"):
+            rep.handle
+        del a
+        gc.collect()
+        assert len(rep._lib.freed) == 2  # nothing is freed into the destroyed model
+        rep.close()  # idempotent
+        assert len(rep._lib.destroyed) == 1
+    finally:
+        E._lib = old_lib
