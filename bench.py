@@ -5,8 +5,10 @@
     python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference path (rank 0 only)
 
 A *step* is one pass of the hot path over one batch of synthetic 30 s chunks on every GPU:
-``--workload single`` (default, BASELINE.json configs[1]) = one chunk, beam_size=5;
-``--workload batched`` (configs[2]/[4]) = 16 chunks through one generate() call.  Weak scaling: per-GPU work is fixed.
+``--workload batched`` (default, BASELINE.json configs[2], the configuration configs[4] shards) = 16 chunks through one
+generate() call (``--compute-type int8_float16`` = configs[3]); ``--workload single`` (configs[1]) = one chunk, beam_size=5.
+The default line also carries the single-chunk measurement of the same process under ``single_chunk``.
+Weak scaling: per-GPU work is fixed.
 Decode length is pinned: prompt of 4 tokens, exactly 128 new tokens (EOT in suppress_tokens).
 
 Prints ONE JSON line (rank 0).  ``value`` = audio seconds per second through the engine calls (encode_audio + generate; the
@@ -125,7 +127,7 @@ def host_threads(cap: int = 16) -> int:
 class CpuPath:
     """The oracle's restatement of the reference path on the host cores (weights and model built once)."""
 
-    def __init__(self, model_name: str, beam: int, sample_tokens: int, seed: int, threads: int):
+    def __init__(self, model_name: str, beam: int, sample_tokens: int, seed: int, threads: int, int8: bool = True):
         import torch
 
         from faster_whisper_b200.config import MODEL_DIMS, special_tokens
@@ -136,7 +138,12 @@ class CpuPath:
         self.threads, self.beam, self.sample_tokens = threads, beam, sample_tokens
         self.dims = MODEL_DIMS[model_name]
         self.st = special_tokens(self.dims.n_vocab)
-        self.orc = WhisperOracle(self.dims.to_dict(), make_weights(self.dims, seed=seed), self.st.to_dict())
+        self.int8 = int8
+        try:
+            self.orc = WhisperOracle(self.dims.to_dict(), make_weights(self.dims, seed=seed), self.st.to_dict(), int8_dynamic=int8)
+        except Exception:  # noqa: BLE001 - no quantised engine in this torch build: fall back to fp32 and say so
+            self.int8 = False
+            self.orc = WhisperOracle(self.dims.to_dict(), make_weights(self.dims, seed=seed), self.st.to_dict())
         self.audio = synthetic_audio(0, 30.0)
 
     def run(self):
@@ -154,14 +161,17 @@ class CpuPath:
         t3 = time.perf_counter()
         per_tok = (t3 - t2) / (sample_tokens + len(prompt) - 1)
         total = (t1 - t0) + (t2 - t1) + per_tok * (NEW_TOKENS + len(prompt) - 1)
-        return dict(value=30.0 / total, unit="audio-s/s", cores=self.threads, kind="port",
+        prec = "dynamic-int8 linears (torch.ao, per-tensor weights)" if self.int8 else "fp32"
+        return dict(value=30.0 / total, unit="audio-s/s", cores=self.threads, kind="port", host_cores_available=os.cpu_count(),
+                    precision="int8" if self.int8 else "f32",
                     sample=(f"1 chunk of 30 s: log-mel {1e3 * (t1 - t0):.0f} ms + encoder {1e3 * (t2 - t1):.0f} ms measured in full; beam-{beam} "
-                            f"decode measured for {sample_tokens} new tokens ({1e3 * per_tok:.0f} ms/position) and extrapolated to {NEW_TOKENS}; "
-                            "fp32 torch CPU restatement of the reference path, not CTranslate2 int8"))
+                            f"decode measured for {sample_tokens} new tokens ({1e3 * per_tok:.0f} ms/position) and scaled to {NEW_TOKENS}; "
+                            f"torch CPU restatement of the reference path with {prec} on {self.threads} threads — an approximation of the "
+                            "reference's CTranslate2 int8 CPU path, which cannot be installed here"))
 
 
-def cpu_baseline(model_name: str, beam: int, sample_tokens: int, seed: int, threads: int):
-    return CpuPath(model_name, beam, sample_tokens, seed, threads).run()
+def cpu_baseline(model_name: str, beam: int, sample_tokens: int, seed: int, threads: int, int8: bool = True):
+    return CpuPath(model_name, beam, sample_tokens, seed, threads, int8).run()
 
 
 def run_reference(args):
@@ -170,7 +180,7 @@ def run_reference(args):
         return
     threads = host_threads()
     t0 = time.perf_counter()
-    path = CpuPath(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, threads)
+    path = CpuPath(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, threads, args.cpu_precision == "int8")
     for _ in range(min(args.warmup, 1)):
         path.run()
     vals = []
@@ -182,26 +192,31 @@ def run_reference(args):
     v = float(np.mean(vals))
     cb["value"] = v
     line = dict(metric=METRIC, value=v, unit="audio-s/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=30.0 / v * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
+                ms_per_step=30.0 / v * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="int8" if path.int8 else "f32", data="synthetic", impl="reference",
                 config={"workload": workload_name(args), "model": args.model, "timed_samples": len(vals),
-                        "note": "CPU port of the reference path on rank 0's host cores"},
+                        "note": "CPU port of the reference path on rank 0's host cores; one 30 s chunk per step (per-chunk throughput "
+                                "does not depend on the batch on the CPU), decode sample scaled to the pinned length"},
                 cpu_baseline=cb, e2e={"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 wall_s=time.perf_counter() - t0)
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    if args.workload == "single":
-        return f"{args.model} fp16 beam_size={args.beam_size}, single 30 s chunk per step, prompt 4 + {NEW_TOKENS} new tokens (configs[1])"
-    return (f"{args.model} fp16 beam_size={args.beam_size}, BatchedInferencePipeline batch_size={args.batch_size}, "
-            f"{args.batch_size} x 30 s chunks per step, prompt 4 + {NEW_TOKENS} new tokens (configs[2])")
+def workload_name(args, workload=None):
+    workload = workload or args.workload
+    prec = "fp16" if not args.compute_type.startswith("int8") else "int8 weights (per-channel, fp16 activations)"
+    if workload == "single":
+        return f"{args.model} {prec} beam_size={args.beam_size}, single 30 s chunk per step, prompt 4 + {NEW_TOKENS} new tokens (configs[1])"
+    cfg = "configs[3]" if args.compute_type.startswith("int8") else "configs[2]"
+    return (f"{args.model} {prec} beam_size={args.beam_size}, BatchedInferencePipeline batch_size={args.batch_size}, "
+            f"{args.batch_size} x 30 s chunks per step, prompt 4 + {NEW_TOKENS} new tokens ({cfg})")
 
 
 # ----------------------------------------------------------------------------------------------------------------
 def run_engine(args):
     rank, local_rank, world = dist_env()
     use_dist = world > 1
+    dist = None
     if use_dist:
         import torch
         import torch.distributed as dist
@@ -222,105 +237,122 @@ def run_engine(args):
     dims = MODEL_DIMS[args.model]
     st = special_tokens(dims.n_vocab)
     t_load = time.perf_counter()
-    model = WhisperModel(args.model, device="cuda", device_index=local_rank, compute_type="float16", synthetic_seed=args.seed)
+    model = WhisperModel(args.model, device="cuda", device_index=local_rank, compute_type=args.compute_type, synthetic_seed=args.seed)
     eng = model.model
     t_load = time.perf_counter() - t_load
     pipe = BatchedInferencePipeline(model)
-    B = 1 if args.workload == "single" else args.batch_size
-    chunks = [synthetic_audio(rank * 1000 + i, 30.0) for i in range(B)]
-    audio = np.concatenate(chunks)
-    clips = [{"start": 30.0 * i, "end": 30.0 * (i + 1)} for i in range(B)]
     prompt = [st.sot, st.lang_begin, st.transcribe, st.no_timestamps] if dims.is_multilingual else [st.sot, st.no_timestamps]
     suppress = sorted({st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech})
-
-    def engine_step():
-        enc = eng.encode_audio(chunks)
-        res = eng.generate(enc, [prompt] * B, beam_size=args.beam_size, max_length=len(prompt) + NEW_TOKENS, suppress_tokens=suppress,
-                           return_scores=True, return_no_speech_prob=True)
-        assert all(len(r.sequences_ids[0]) == NEW_TOKENS for r in res)
-        return res
-
-    def api_step():
-        segs, _ = pipe.transcribe(audio, language="en", beam_size=args.beam_size, batch_size=B, vad_filter=False, clip_timestamps=clips,
-                                  max_new_tokens=NEW_TOKENS, suppress_tokens=[-1, st.eot], without_timestamps=True)
-        n = sum(len(s.tokens) for s in segs)
-        assert n == NEW_TOKENS * B, n
-        return n
+    pk = peaks()
 
     def barrier():
         eng.sync()
         if use_dist:
             dist.barrier()
 
-    def timed(fn, steps):
-        """K steps between barrier + sync on both sides, timed on the device: CUDA events recorded on the engine's stream
-        before the first and after the last step (host work between launches is inside the span); max over ranks."""
-        barrier()
-        t0 = time.perf_counter()
-        eng.span_begin()
-        for _ in range(steps):
-            fn()
-        dt = eng.span_end() * 1e-3
-        eng.sync()
-        wall = time.perf_counter() - t0
-        if use_dist:
-            t = torch.tensor([dt, wall], device="cuda" if dist.get_backend() == "nccl" else "cpu")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt, wall = float(t[0].item()), float(t[1].item())
-        timed.wall.append(wall)
-        return dt
+    def measure(workload: str, steps: int, warmup: int, sample_clocks: bool):
+        """One workload: W warm-up steps, K steps through the engine calls, K steps through the public API."""
+        B = 1 if workload == "single" else args.batch_size
+        chunks = [synthetic_audio(rank * 1000 + i, 30.0) for i in range(B)]
+        audio = np.concatenate(chunks)
+        clips = [{"start": 30.0 * i, "end": 30.0 * (i + 1)} for i in range(B)]
+        walls = []
 
-    timed.wall = []
+        def engine_step():
+            enc = eng.encode_audio(chunks)
+            res = eng.generate(enc, [prompt] * B, beam_size=args.beam_size, max_length=len(prompt) + NEW_TOKENS, suppress_tokens=suppress,
+                               return_scores=True, return_no_speech_prob=True)
+            assert all(len(r.sequences_ids[0]) == NEW_TOKENS for r in res)
+            return res
 
-    for _ in range(max(args.warmup, 3)):
-        engine_step()
-    api_step()
-    eng.timing(enable=True, reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    dt = timed(engine_step, args.steps)
-    stats = eng.timing()
-    eng.timing(enable=False)
-    dt_api = timed(api_step, args.steps)
-    clocks = sampler.stop()
+        def api_step():
+            segs, _ = pipe.transcribe(audio, language="en", beam_size=args.beam_size, batch_size=B, vad_filter=False, clip_timestamps=clips,
+                                      max_new_tokens=NEW_TOKENS, suppress_tokens=[-1, st.eot], without_timestamps=True)
+            n = sum(len(s.tokens) for s in segs)
+            assert n == NEW_TOKENS * B, n
+            return n
 
-    audio_s = 30.0 * B * args.steps * world
-    value = audio_s / dt
-    e2e_value = audio_s / dt_api
-    pk = peaks()
-    dec_ms = stats["decode_ms"]
-    steps_dec = max(1, stats["decode_steps"])
-    ach = stats["decode_alg_bytes"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
-    enc_flops = enc_flops_per_chunk(dims) * B * args.steps
-    enc_tf = enc_flops / (stats["encoder_ms"] * 1e-3) / 1e12 if stats["encoder_ms"] > 0 else 0.0
+        def timed(fn):
+            """K steps between barrier + sync on both sides, timed on the device: CUDA events recorded on the engine's stream
+            before the first and after the last step (host work between launches is inside the span); max over ranks."""
+            barrier()
+            t0 = time.perf_counter()
+            eng.span_begin()
+            for _ in range(steps):
+                fn()
+            dt = eng.span_end() * 1e-3
+            eng.sync()
+            wall = time.perf_counter() - t0
+            if use_dist:
+                import torch
+
+                t = torch.tensor([dt, wall], device="cuda" if dist.get_backend() == "nccl" else "cpu")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt, wall = float(t[0].item()), float(t[1].item())
+            walls.append(wall)
+            return dt
+
+        for _ in range(max(warmup, 3)):
+            engine_step()
+        api_step()
+        eng.timing(enable=True, reset=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        dt = timed(engine_step)
+        stats = eng.timing()
+        eng.timing(enable=False)
+        dt_api = timed(api_step)
+        clocks = sampler.stop() if sampler else None
+
+        audio_s = 30.0 * B * steps * world
+        R = B * args.beam_size
+        dec_ms = stats["decode_ms"]
+        steps_dec = max(1, stats["decode_steps"])
+        ach = stats["decode_alg_bytes"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+        enc_flops = enc_flops_per_chunk(dims) * B * steps
+        enc_tf = enc_flops / (stats["encoder_ms"] * 1e-3) / 1e12 if stats["encoder_ms"] > 0 else 0.0
+        kernel = "dstep_kernel" if R <= 8 else "bstep_kernel"
+        traffic, traffic_note = ncu_traffic(kernel)
+        return dict(
+            B=B, value=audio_s / dt, e2e_value=audio_s / dt_api, ms_per_step=dt / steps * 1e3, e2e_ms_per_step=dt_api / steps * 1e3,
+            rtf=dt / audio_s * world, h2d=int(audio.nbytes), d2h=int(B * (448 * 4 + 16)), launches=int(stats["launches"]), clocks=clocks,
+            stages_ms={k[:-3]: round(v / steps, 3) for k, v in stats.items() if k.endswith("_ms") and v > 0},
+            device_ms_per_step=round(sum(v for k, v in stats.items() if k.endswith("_ms")) / steps, 3),
+            host_wall_ms_per_step=[round(w / steps * 1e3, 3) for w in walls],
+            roofline={"bound": "hbm",
+                      "kernel": f"decode step = {kernel} (persistent cooperative kernel: weight stream + self/cross attention + logits) + 2 search kernels",
+                      "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "peak_source": pk["source"],
+                      "traffic": traffic, "traffic_source": traffic_note, "ms_per_decode_step": dec_ms / steps_dec,
+                      "alg_bytes_per_step": stats["decode_alg_bytes"] / steps_dec},
+            roofline_encoder={"bound": "tensor", "achieved": enc_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": enc_tf / pk["tflops"],
+                              "flops_per_chunk": enc_flops_per_chunk(dims), "ms_per_chunk": stats["encoder_ms"] / (B * steps)})
+
+    m = measure(args.workload, args.steps, args.warmup, True)
+    B = m["B"]
     line = dict(
-        metric=METRIC, value=value, unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-        ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
-        rtf=dt / audio_s * world,
+        metric=METRIC, value=m["value"], unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=m["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="int8" if args.compute_type.startswith("int8") else "f16", data="synthetic", rtf=m["rtf"],
         config={"workload": workload_name(args), "model": args.model, "global_batch": B * world, "beam_size": args.beam_size,
-                "new_tokens": NEW_TOKENS, "parallelism": f"chunk-parallel replicas x{world}",
+                "new_tokens": NEW_TOKENS, "parallelism": f"chunk-parallel replicas x{world}", "compute_type": args.compute_type,
                 "l2": "working set per step (3.1 GB weights + 0.25 GB/chunk cross-KV) exceeds the 126 MB L2; no flush needed",
                 "weights": f"synthetic seed {args.seed}, exact {args.model} shapes", "load_s": round(t_load, 1)},
-        e2e={"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(audio.nbytes), "d2h_bytes_per_step": int(B * (448 * 4 + 16)),
-             "api": "BatchedInferencePipeline.transcribe(ndarray, clip_timestamps=..., batch_size=%d)" % B, "ms_per_step": dt_api / args.steps * 1e3},
-        gpu_launches=int(stats["launches"]),
-        clocks=clocks,
-        stages_ms={k[:-3]: round(v / args.steps, 3) for k, v in stats.items() if k.endswith("_ms") and v > 0},
-        device_ms_per_step=round(sum(v for k, v in stats.items() if k.endswith("_ms")) / args.steps, 3),
+        e2e={"value": m["e2e_value"], "unit": "audio-s/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+             "api": "BatchedInferencePipeline.transcribe(ndarray, clip_timestamps=..., batch_size=%d)" % B, "ms_per_step": m["e2e_ms_per_step"]},
+        gpu_launches=m["launches"], clocks=m["clocks"], stages_ms=m["stages_ms"], device_ms_per_step=m["device_ms_per_step"],
         timing="value/e2e: CUDA events on the engine stream around the K steps (barrier + sync on both sides, max over ranks); stages_ms/roofline: per-stage CUDA events on the same stream",
-        host_wall_ms_per_step=[round(w / args.steps * 1e3, 3) for w in timed.wall],
-        roofline={"bound": "hbm", "kernel": ("decode step = dstep_kernel (persistent: weight stream + self/cross attention + logits) + search kernels"
-                                             if B * args.beam_size <= 8 else
-                                             "decode step (CUDA graph: gemm_tc/skinny_gemm weight stream + self/cross attention + search)"),
-                  "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "peak_source": pk["source"],
-                  "traffic": ncu_traffic(B * args.beam_size <= 8), "ms_per_decode_step": dec_ms / steps_dec,
-                  "alg_bytes_per_step": stats["decode_alg_bytes"] / steps_dec},
-        roofline_encoder={"bound": "tensor", "achieved": enc_tf, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": enc_tf / pk["tflops"],
-                          "flops_per_chunk": enc_flops_per_chunk(dims), "ms_per_chunk": stats["encoder_ms"] / (B * args.steps)},
+        host_wall_ms_per_step=m["host_wall_ms_per_step"], roofline=m["roofline"], roofline_encoder=m["roofline_encoder"],
     )
+    if args.workload == "batched" and not args.no_secondary:
+        # configs[1] measured in the same process, so both configurations are driver-measured in one line
+        s1 = measure("single", args.steps, args.warmup, False)
+        line["single_chunk"] = {"workload": workload_name(args, "single"), "value": s1["value"], "unit": "audio-s/s", "ms_per_step": s1["ms_per_step"],
+                                "e2e": {"value": s1["e2e_value"], "unit": "audio-s/s", "ms_per_step": s1["e2e_ms_per_step"]},
+                                "stages_ms": s1["stages_ms"], "roofline": s1["roofline"], "roofline_encoder": s1["roofline_encoder"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (the other ranks would idle at the barrier)
         try:
-            line["cpu_baseline"] = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, host_threads())
+            line["cpu_baseline"] = cpu_baseline(args.model, args.beam_size, args.cpu_sample_tokens, args.seed, host_threads(), args.cpu_precision == "int8")
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     if use_dist:
@@ -330,15 +362,29 @@ def run_engine(args):
         print(json.dumps(line), flush=True)
 
 
-def ncu_traffic(persistent: bool):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json).  The file records the sha256 of the kernel's source at capture time: when the source has
+    changed since, the number is stale and is NOT reported (traffic = null, and a loud note on stderr)."""
+    import hashlib
+
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        return d.get("dstep_kernel" if persistent else "decode_graph")
-    except (OSError, ValueError):
-        return None
+        ent = d.get(kernel)
+        if not ent:
+            return None, "no capture committed for " + kernel
+        src = os.path.join(ROOT, "faster_whisper_b200", "csrc", ent["source_file"])
+        with open(src, "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+        if sha != ent.get("source_sha16"):
+            sys.stderr.write(f"[bench] profiles/r2_ncu_traffic.json is STALE for {kernel}: {ent['source_file']} changed since the ncu capture "
+                             f"({ent.get('source_sha16')} -> {sha}); roofline.traffic is reported as null\n")
+            return None, "stale: source changed since the capture"
+        return ent["dram_bytes_per_launch"], ent.get("capture", "profiles/")
+    except (OSError, ValueError, KeyError) as e:
+        return None, f"unavailable: {e}"
 
 
 def enc_flops_per_chunk(dims) -> float:
@@ -354,12 +400,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="single", choices=["single", "batched"])
+    ap.add_argument("--workload", default="batched", choices=["single", "batched"])
+    ap.add_argument("--compute-type", default="float16", choices=["float16", "int8_float16", "int8"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the single-chunk measurement that rides along with the batched line")
+    ap.add_argument("--cpu-precision", default="int8", choices=["int8", "fp32"])
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--beam-size", type=int, default=5)
     ap.add_argument("--batch-size", type=int, default=16)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-sample-tokens", type=int, default=6)
+    ap.add_argument("--cpu-sample-tokens", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,12 +116,18 @@ class WhisperOracle:
     """float32 Whisper with CTranslate2 decoding semantics."""
 
     def __init__(self, dims: dict, weights: Dict[str, np.ndarray], tokens: dict,
-                 suppress_ids_begin: Optional[Sequence[int]] = None, num_threads: Optional[int] = None):
+                 suppress_ids_begin: Optional[Sequence[int]] = None, num_threads: Optional[int] = None, int8_dynamic: bool = False):
+        """``int8_dynamic``: bench.py's CPU arm only — every linear layer (and the output embedding) runs as a torch dynamic-int8
+        linear (per-tensor int8 weights, activations quantised per call), the closest stand-in available here for the reference's
+        ``compute_type="int8"`` CPU path (CTranslate2 itself cannot be installed).  Parity tests never set it."""
         if num_threads:
             torch.set_num_threads(num_threads)
         self.dims = dict(dims)
         self.tok = dict(tokens)
         self.w = {k: _t(v) for k, v in weights.items()}
+        self.q: Dict[str, torch.nn.Module] = {}
+        if int8_dynamic:
+            self._quantize_linears()
         self.n_head = self.dims["n_text_head"]
         self.n_audio_head = self.dims["n_audio_head"]
         self.n_vocab = self.dims["n_vocab"]
@@ -133,7 +139,26 @@ class WhisperOracle:
         return F.layer_norm(x, (x.shape[-1],), self.w[prefix + ".weight"], self.w[prefix + ".bias"], 1e-5)
 
     def _lin(self, x, prefix, bias=True):
+        if prefix in self.q:
+            return self.q[prefix](x)
         return F.linear(x, self.w[prefix + ".weight"], self.w.get(prefix + ".bias") if bias else None)
+
+    def _quantize_linears(self):
+        import torch.ao.nn.quantized.dynamic as nnqd
+
+        def make(wt, bias):
+            lin = torch.nn.Linear(wt.shape[1], wt.shape[0], bias=bias is not None)
+            lin.weight = torch.nn.Parameter(wt, requires_grad=False)
+            if bias is not None:
+                lin.bias = torch.nn.Parameter(bias, requires_grad=False)
+            lin.qconfig = torch.ao.quantization.default_dynamic_qconfig
+            return nnqd.Linear.from_float(lin)
+
+        for name in list(self.w):
+            if name.endswith(".weight") and self.w[name].ndim == 2 and (".attn." in name or ".cross_attn." in name or ".mlp." in name):
+                prefix = name[: -len(".weight")]
+                self.q[prefix] = make(self.w[name], self.w.get(prefix + ".bias"))
+        self.q["__logits__"] = make(self.w["decoder.token_embedding.weight"], None)
 
     @staticmethod
     def _split_heads(x, n_head):
@@ -207,14 +232,18 @@ class WhisperOracle:
             x = x + self._lin(a, p + ".attn.out")
             h = self._ln(x, p + ".cross_attn_ln")
             xk, xv = xkv[i]
-            a, att = self._mha(self._lin(h, p + ".cross_attn.query"), xk[row2chunk], xv[row2chunk], self.n_head)
+            if xk.shape[0] == 1:  # every row reads the same chunk: broadcast instead of materialising one K/V copy per beam
+                xk_r, xv_r = xk.expand(x.shape[0], -1, -1), xv.expand(x.shape[0], -1, -1)
+            else:
+                xk_r, xv_r = xk[row2chunk], xv[row2chunk]
+            a, att = self._mha(self._lin(h, p + ".cross_attn.query"), xk_r, xv_r, self.n_head)
             if want_cross_att:
                 cross_atts.append(att)
             x = x + self._lin(a, p + ".cross_attn.out")
             h = self._ln(x, p + ".mlp_ln")
             x = x + self._lin(F.gelu(self._lin(h, p + ".mlp.0")), p + ".mlp.2")
         x = self._ln(x, "decoder.ln")
-        logits = x @ w["decoder.token_embedding.weight"].t()
+        logits = self.q["__logits__"](x) if "__logits__" in self.q else x @ w["decoder.token_embedding.weight"].t()
         return (logits, cross_atts) if want_cross_att else logits
 
     # ---- logits processors (CT2 semantics, CPU ordering: DisableTokens writes immediately) --------
