@@ -116,7 +116,7 @@ __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
   const int K = j == 5 ? 4 * d : d;
   BsRange r;
   r.KA = K >> 6;
-  const long long A = (long long)((N + 127) >> 7) * r.KA;
+  const unsigned A = (unsigned)((N + 127) >> 7) * (unsigned)r.KA;  // <= 800 atoms x 148 CTAs: 32-bit products
   r.a0 = (int)(A * blockIdx.x / gridDim.x);
   r.a1 = (int)(A * (blockIdx.x + 1) / gridDim.x);
   r.nseg = 0;
@@ -190,7 +190,7 @@ __device__ __forceinline__ int bs_xtasks_of_cta(int xtasks) {
 __device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer, int task, unsigned char* kvbuf, uint64_t* bar) {
   const int split = task % kDsXSplits, rest = task / kDsXSplits;
   const int h = rest % a.H, b = rest / a.H, T = a.T;
-  const int k0 = (int)((long long)T * split / kDsXSplits), k1 = (int)((long long)T * (split + 1) / kDsXSplits), nk = k1 - k0;
+  const int k0 = T * split / kDsXSplits, k1 = T * (split + 1) / kDsXSplits, nk = k1 - k0;
   const DecBindings bd = *a.bind;
   const long long per = (long long)bd.B_total * a.H * T * 64;
   const long long off = (((long long)(bd.chunk0 + b) * a.H + h) * T + k0) * 64;
@@ -304,7 +304,8 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
 //               segments of n-block 0 also accumulate sum(x), sum(x^2) of their K slice into `st`
 //   X == false: source = fp16 activations [R][ld]
 template <bool X>
-__device__ __forceinline__ void bs_stage(const BStepArgs& a, const BsRange& rg, const void* src, int ld, float* st, unsigned char* xs) {
+__device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
+  const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
   const int NP = a.NP, R = a.R, tid = threadIdx.x;
   const int per_atom = NP * 8, natoms = rg.a1 - rg.a0, total = natoms * per_atom;
   constexpr int UNR = X ? 6 : 8;
@@ -374,12 +375,12 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   int N, ldo;
   const float* bias = nullptr;
   switch (j) {
-    case 0: out = a.qkv32; N = 3 * d; ldo = 3 * d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
-    case 1: out = a.x; N = d; ldo = d; bias = lay.bias[1]; bs_stage<false>(a, rg, a.ao, d, nullptr, U); break;
-    case 2: out = a.cq32; N = d; ldo = d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
-    case 3: out = a.x; N = d; ldo = d; bias = lay.bias[3]; bs_stage<false>(a, rg, a.ao, d, nullptr, U); break;
-    case 4: out = a.h32; N = 4 * d; ldo = 4 * d; bs_stage<true>(a, rg, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
-    default: out = a.x; N = d; ldo = d; bias = lay.bias[5]; bs_stage<false>(a, rg, a.h16, 4 * d, nullptr, U); break;
+    case 0: out = a.qkv32; N = 3 * d; ldo = 3 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
+    case 1: out = a.x; N = d; ldo = d; bias = lay.bias[1]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
+    case 2: out = a.cq32; N = d; ldo = d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
+    case 3: out = a.x; N = d; ldo = d; bias = lay.bias[3]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
+    case 4: out = a.h32; N = 4 * d; ldo = 4 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
+    default: out = a.x; N = d; ldo = d; bias = lay.bias[5]; bs_stage<false>(a, s, a.h16, 4 * d, nullptr, U); break;
   }
   fence_proxy_async();
   bs_sync();
@@ -567,7 +568,7 @@ __device__ __noinline__ void bs_cross_attn_task(const BStepArgs& a, BsShared& sh
   const int g = lane >> 2, t = lane & 3;
   const int split = task % S, rest = task / S, h = rest % a.H, b = rest / a.H;
   const int nq = a.rows_per_chunk, row0 = b * a.rows_per_chunk, d = a.d;
-  const int k0 = (int)((long long)T * split / S), k1 = (int)((long long)T * (split + 1) / S), nk = k1 - k0;
+  const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
   const int nkp = (nk + 15) & ~15;
   __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
   __half* vt = kt + kDsXKeysMax * 64;
@@ -1007,7 +1008,14 @@ void bstep_row_sums(const __half* W, int N, int K, float* out, cudaStream_t s) {
 
 static size_t bstep_smem_bytes(const BStepArgs& a) { return (size_t)kBsSlots * kBsAtomBytes + kBsKvBytes + (size_t)a.u_bytes + 1024; }
 
-void bstep_configure() { B2W_CUDA(cudaFuncSetAttribute(bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024)); }
+// dynamic + static shared memory of a CTA is capped at 227 KB (232 448 B) on sm_100
+static int bstep_max_dynamic_smem() {
+  cudaFuncAttributes fa;
+  B2W_CUDA(cudaFuncGetAttributes(&fa, bstep_kernel));
+  return 232448 - (int)fa.sharedSizeBytes;
+}
+
+void bstep_configure() { B2W_CUDA(cudaFuncSetAttribute(bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bstep_max_dynamic_smem())); }
 
 int bstep_phase_count(int L) { return 3 + 9 * L; }
 
@@ -1037,7 +1045,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
   if ((size_t)(d / 64) * NPh * 128 > (size_t)kBsKvBytes + a.u_bytes) return false;
   const size_t smem = bstep_smem_bytes(a);
-  if (smem > 224 * 1024) return false;
+  if (smem > (size_t)bstep_max_dynamic_smem()) return false;
   int per_sm = 0;
   B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bstep_kernel, kBsLaunch, smem));
   return per_sm >= 1;

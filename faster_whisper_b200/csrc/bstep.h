@@ -11,9 +11,10 @@ constexpr int kBsMaxRows = 80;
 // three matrices that consume a LayerNorm, the row sums of the (LayerNorm-folded, fp16-rounded) weights — the mean term of the
 // deferred normalisation  y = rstd * (W x - mean * rowsum(W)) + b.
 struct BLayer {
-  const __half* wt[6];
+  const void* wt[6];      // fp16 atoms (16 KB) or, with w8, int8 atoms (8 KB: [128 channels][64 K] bytes holding q + 128)
   const float* bias[6];
-  const float* wsum[3];  // qkv, cross_q, ffn1
+  const float* wsum[3];   // qkv, cross_q, ffn1
+  const float* scale[6];  // w8: per-output-channel de-quantisation scales (applied to the fp32 accumulator in the epilogue)
 };
 
 struct BStepArgs {
@@ -21,8 +22,10 @@ struct BStepArgs {
   int L;
   const __half* tok_emb;
   const float* pos_emb;
-  const __half* logit_atoms;  // (LayerNorm-folded) output embedding as an atom stream, rows padded to a multiple of 128
+  const void* logit_atoms;    // (LayerNorm-folded) output embedding as an atom stream, rows padded to a multiple of 128
   const float* logit_bias;    // [vpad]
+  const float* logit_scale;   // [vpad] (w8)
+  int w8;                     // 1: int8 atom streams, widened to fp16 UMMA tiles in shared memory by the compute warps
   int R, NP;                  // rows, rows padded to the UMMA N (multiple of 16)
   int d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk;
   int u_bytes;                // size of the multi-purpose shared-memory region
@@ -54,6 +57,10 @@ struct BStepArgs {
 size_t bstep_atoms_bytes(int N, int K);
 void bstep_pack_atoms(const __half* W, int N, int K, __half* out, cudaStream_t s);
 void bstep_row_sums(const __half* W, int N, int K, float* out, cudaStream_t s);
+// int8 variants: q holds the biased bytes (q + 128) of W[N][K] quantised per output channel with `scale`
+size_t bstep_atoms_bytes_i8(int N, int K);
+void bstep_pack_atoms_i8(const unsigned char* q, int N, int K, unsigned char* out, cudaStream_t s);
+void bstep_row_sums_i8(const unsigned char* q, const float* scale, int N, int K, float* out, cudaStream_t s);
 
 void bstep_configure();
 bool bstep_supported(int num_sms, BStepArgs& a);  // fills a.NP / a.u_bytes; false when the shape cannot run here
