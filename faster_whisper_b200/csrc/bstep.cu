@@ -43,7 +43,8 @@ constexpr int kBsXQ = 8;          // rows per chunk the cross-attention task han
 constexpr int kBsScLd = kDsXKeysMax + 4;
 constexpr int kBsPLd = kDsXKeysMax + 8;
 constexpr int kBsQLd = 96;
-constexpr int kBsXScratch = kBsXQ * kBsQLd * 2 + kBsXQ * kBsScLd * 4 + kBsXQ * kBsPLd * 2 + 2 * kBsXQ * 64 * 4 + 64;
+constexpr int kBsXGroups = 4;     // (chunk, head) groups one CTA's run of cross-attention tiles may touch
+constexpr int kBsXScratch = kBsXGroups * kBsXQ * kBsQLd * 2 + kBsXQ * kBsScLd * 4 + kBsXQ * kBsPLd * 2 + 2 * kBsXQ * 64 * 4 + 3 * kBsXQ * 4 + 32;
 constexpr int kBsTmemCols = 256;  // two accumulators, 128 columns apart
 
 __host__ __device__ __forceinline__ int bs_ceil16(int v) { return (v + 15) & ~15; }
@@ -84,6 +85,7 @@ struct BsShared {
   unsigned epoch;
   int prof_i;
   int flag;
+  unsigned ticks[6 * 8];     // B2W_DSTEP_PROF: cycles of CTA 0 per GEMM kind: [stage, wait acc, epilogue, bulk wait, count]
   int acc_par[2];            // parity of the next acc_full wait (compute side)
   uint32_t tmem_base;
   uint64_t wfull[kBsSlots];  // weight atom landed (TMA complete_tx)
@@ -182,8 +184,11 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
     for (int ka = 0; ka < KA; ++ka) push(base + ((size_t)nb * KA + ka) * kBsAtomBytes);
 }
 
-__device__ __forceinline__ int bs_xtasks_of_cta(int xtasks) {
-  return (int)blockIdx.x < xtasks ? (xtasks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+// cross-attention tiles (group-major: tile = (chunk * H + head) * splits + split) are dealt out as contiguous runs ("stream-K")
+__device__ __forceinline__ void bs_xrange(const BStepArgs& a, int& t0, int& t1) {
+  const unsigned NT = (unsigned)(kDsXSplits * a.H * a.n_chunks);
+  t0 = (int)(NT * blockIdx.x / gridDim.x);
+  t1 = (int)(NT * (blockIdx.x + 1) / gridDim.x);
 }
 
 // TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf (one thread).
@@ -202,12 +207,13 @@ __device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer,
   ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, bar);
 }
 
-// K/V producer: tile k of this CTA (task blockIdx.x + k * grid) goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile
+// K/V producer: the k-th tile of this CTA's run goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile
 // of a layer is fetched as soon as the previous layer released it; buffer 1 lives in the multi-purpose region and is opened
 // by the compute warps when the cross-attention phase starts.
 __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, unsigned char* kv0, unsigned char* kv1) {
-  const int xtasks = kDsXSplits * a.H * a.n_chunks;
-  const int nt = bs_xtasks_of_cta(xtasks);
+  int t0, t1;
+  bs_xrange(a, t0, t1);
+  const int nt = t1 - t0;
   if (nt == 0) return;
   const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
 #pragma unroll 1
@@ -223,7 +229,7 @@ __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, un
         const int u = l * n_odd + (k >> 1);
         mbar_wait(&sh.kvfree[1], (uint32_t)(u & 1));
       }
-      bs_issue_cross_kv(a, l, blockIdx.x + k * gridDim.x, buf ? kv1 : kv0, &sh.kvfull[buf]);
+      bs_issue_cross_kv(a, l, t0 + k, buf ? kv1 : kv0, &sh.kvfull[buf]);
     }
   }
 }
@@ -366,10 +372,20 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
 }
 
 // One GEMM phase (compute warps): stage -> signal the MMA thread -> drain the accumulators into L2 with bulk reductions.
+#define BS_TICK(point)                                                   \
+  do {                                                                   \
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
+      const long long _now = clock64();                                  \
+      sh.ticks[j * 8 + (point)] += (unsigned)(_now - tp);                \
+      tp = _now;                                                         \
+    }                                                                    \
+  } while (0)
+
 __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U) {
   const BsRange rg = bs_range(a, s);
   if (rg.a1 <= rg.a0) return;
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long tp = clock64();
   const BLayer& lay = sh.lay[l];
   float* out;
   int N, ldo;
@@ -385,10 +401,12 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   fence_proxy_async();
   bs_sync();
   if (tid == 0) mbar_arrive(&sh.xs_ready);
+  BS_TICK(0);
   // all accumulators of the phase must be complete before the staging tile (which aliases the activation tiles) is written
   for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
   tc_fence_after();
   bs_sync();
+  BS_TICK(1);
   if (tid == 0)
     for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
   float* stg = reinterpret_cast<float*>(U);  // [NP][128] fp32
@@ -417,174 +435,166 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
     if (sg + 1 < rg.nseg) bs_sync();
   }
   tc_fence_before();
+  BS_TICK(2);
   if (tid < a.R) {
     bs_bulk_wait_all();
     bs_fence_async_all();
   }
+  BS_TICK(3);
+  if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[j * 8 + 7] += 1;
 }
 
-// Masked self-attention: one (row, head) task per half-warp.  q, k, v of the new token come from the raw QKV sums (deferred
-// LayerNorm + bias applied here), k and v are rounded to fp16 and written to the paged cache; the history is gathered through
-// the beam ancestry table (one key per lane for the scores, 4 output dims per lane for P V).
+// Masked self-attention: one (row, head) task per warp.  q, k, v of the new token come from the raw QKV sums (deferred LayerNorm +
+// bias applied here); k and v are rounded to fp16 and written to the paged cache.  The history is gathered through the beam
+// ancestry table in blocks of 32 keys with an online softmax: per block ONE memory round trip — lane j fetches the K row of key
+// j (8 x 16 B) while all 32 V rows of the block are fetched 4 B per lane (lane = 2 output dims), all loads in flight together.
 __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, l16 = lane & 15;
-  const int worker = warp * 2 + hw;
-  const unsigned hmask = hw ? 0xffff0000u : 0x0000ffffu;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
-  float* sc = reinterpret_cast<float*>(U) + worker * n_ctx;
-  float* qs = reinterpret_cast<float*>(U) + 16 * n_ctx + worker * 64;
-  uint8_t* sl = U + (size_t)(16 * n_ctx + 16 * 64) * 4 + worker * n_ctx;
+  float* qs = reinterpret_cast<float*>(U) + warp * 64;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
   __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
-  const int ntasks = H * a.R, e0 = 4 * l16;
+  const int ntasks = H * a.R, e0 = 2 * lane;
+  const long long pos_stride = (long long)a.slots * d;
 #pragma unroll 1
-  for (int t0 = (blockIdx.x * kBsWarps + warp) * 2; t0 < ntasks; t0 += gridDim.x * kBsWarps * 2) {
-    const int task = t0 + hw;
-    if (task >= ntasks) continue;  // the other half-warp keeps going: every sync below is half-warp scoped
+  for (int task = blockIdx.x * kBsWarps + warp; task < ntasks; task += gridDim.x * kBsWarps) {
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
+    // ---- everything that does not depend on anything else is requested first: ancestry slots, raw q/k/v, statistics ----
+    const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
+    uint32_t slots[4] = {0u, 0u, 0u, 0u};  // n_ctx <= 448 = 14 blocks of 32 keys, one byte per block
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+      const int jj = 32 * i + lane;
+      const uint32_t sv = (jj < pos) ? (uint32_t)anc[jj] : 0u;
+      slots[i >> 2] |= sv << (8 * (i & 3));
+    }
     float mean, rstd;
     bs_row_stats(st, r, d, mean, rstd);
     const float* raw = a.qkv32 + (long long)r * 3 * d + h * 64 + e0;
-    const float4 rq = __ldcg(reinterpret_cast<const float4*>(raw)), rk = __ldcg(reinterpret_cast<const float4*>(raw + d)),
-                 rv = __ldcg(reinterpret_cast<const float4*>(raw + 2 * d));
+    const float2 rq = __ldcg(reinterpret_cast<const float2*>(raw)), rk = __ldcg(reinterpret_cast<const float2*>(raw + d)),
+                 rv = __ldcg(reinterpret_cast<const float2*>(raw + 2 * d));
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
-    const float4 wq = __ldg(reinterpret_cast<const float4*>(ws)), wk = __ldg(reinterpret_cast<const float4*>(ws + d)),
-                 wv = __ldg(reinterpret_cast<const float4*>(ws + 2 * d));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(bs)), bk = __ldg(reinterpret_cast<const float4*>(bs + d)),
-                 bvv = __ldg(reinterpret_cast<const float4*>(bs + 2 * d));
+    const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),
+                 wv = __ldg(reinterpret_cast<const float2*>(ws + 2 * d));
+    const float2 bq = __ldg(reinterpret_cast<const float2*>(bs)), bk = __ldg(reinterpret_cast<const float2*>(bs + d)),
+                 bvv = __ldg(reinterpret_cast<const float2*>(bs + 2 * d));
     const float mr = mean * rstd;
 #define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
-    float4 qv = make_float4(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y), BS_FIX(rq.z, wq.z, bq.z), BS_FIX(rq.w, wq.w, bq.w));
-    const float4 kv = make_float4(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y), BS_FIX(rk.z, wk.z, bk.z), BS_FIX(rk.w, wk.w, bk.w));
-    const float4 vv = make_float4(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y), BS_FIX(rv.z, wv.z, bvv.z), BS_FIX(rv.w, wv.w, bvv.w));
-#undef BS_FIX
     // q is rounded to fp16 like the other decode paths (they store q as fp16), then pre-scaled by 1/8
-    {
-      const __half2 q01 = __floats2half2_rn(qv.x, qv.y), q23 = __floats2half2_rn(qv.z, qv.w);
-      const float2 f01 = __half22float2(q01), f23 = __half22float2(q23);
-      qv = make_float4(f01.x * 0.125f, f01.y * 0.125f, f23.x * 0.125f, f23.y * 0.125f);
-    }
-    const __half2 k01 = __floats2half2_rn(kv.x, kv.y), k23 = __floats2half2_rn(kv.z, kv.w);
-    const __half2 v01 = __floats2half2_rn(vv.x, vv.y), v23 = __floats2half2_rn(vv.z, vv.w);
+    const __half2 q16 = __floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y));
+    const __half2 k16 = __floats2half2_rn(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y));
+    const __half2 v16 = __floats2half2_rn(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y));
+#undef BS_FIX
+    const float2 qf = __half22float2(q16), kf = __half22float2(k16), vf = __half22float2(v16);
     const long long self_off = (((long long)ri.chunk * n_ctx + pos) * a.slots + ri.slot) * d + h * 64 + e0;
-    *reinterpret_cast<uint2*>(kc + self_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&k01), *reinterpret_cast<const uint32_t*>(&k23));
-    *reinterpret_cast<uint2*>(vc + self_off) = make_uint2(*reinterpret_cast<const uint32_t*>(&v01), *reinterpret_cast<const uint32_t*>(&v23));
-    *reinterpret_cast<float4*>(qs + e0) = qv;
-    float sself;
-    {
-      const float2 ka = __half22float2(k01), kb = __half22float2(k23);
-      sself = qv.x * ka.x + qv.y * ka.y + qv.z * kb.x + qv.w * kb.y;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) sself += __shfl_xor_sync(hmask, sself, o);
-    }
-    __syncwarp(hmask);
-    const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
-    float mx = sself;
+    *reinterpret_cast<__half2*>(kc + self_off) = k16;
+    *reinterpret_cast<__half2*>(vc + self_off) = v16;
+    *reinterpret_cast<float2*>(qs + e0) = make_float2(qf.x * 0.125f, qf.y * 0.125f);
+    float m_run = warp_sum(qf.x * 0.125f * kf.x + qf.y * 0.125f * kf.y);  // the new token's own key
+    float l_run = 1.f;
+    float2 acc = vf;
+    __syncwarp();
+    const __half* kbase = kc + (long long)ri.chunk * n_ctx * pos_stride + h * 64;
+    const __half* vbase = vc + (long long)ri.chunk * n_ctx * pos_stride + h * 64 + e0;
 #pragma unroll 1
-    for (int j0 = 0; j0 < pos; j0 += 16) {
-      const int jj = j0 + l16;
-      if (jj < pos) {
-        const int slot = anc[jj];
-        sl[jj] = (uint8_t)slot;
-        const uint4* kp = reinterpret_cast<const uint4*>(kc + (((long long)ri.chunk * n_ctx + jj) * a.slots + slot) * d + h * 64);
-        uint4 kr[8];
+    for (int blk = 0; blk * 32 < pos; ++blk) {
+      const int bw = blk >> 2;
+      const uint32_t word = bw == 0 ? slots[0] : (bw == 1 ? slots[1] : (bw == 2 ? slots[2] : slots[3]));
+      const int slot = (int)((word >> (8 * (blk & 3))) & 255u);
+      const int j = blk * 32 + lane;
+      const bool valid = j < pos;
+      uint4 kr[8];
+      {
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)(valid ? j : 0) * pos_stride + (long long)slot * d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) kr[i] = __ldcg(kp + i);
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * i), qb = *reinterpret_cast<const float4*>(qs + 8 * i + 4);
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].y)),
-                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].w));
-          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
-          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
-        }
-        const float sv = s0 + s1;
-        sc[jj] = sv;
-        mx = fmaxf(mx, sv);
+        for (int i = 0; i < 8; ++i) kr[i] = valid ? __ldcg(kp + i) : make_uint4(0u, 0u, 0u, 0u);
       }
-    }
+      uint32_t vr[32];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(hmask, mx, o));
-    __syncwarp(hmask);
-    float sum = 0.f;
-    for (int jj = l16; jj < pos; jj += 16) {
-      const float p = __expf(sc[jj] - mx);
-      sc[jj] = p;
-      sum += p;
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(hmask, sum, o);
-    const float pself = __expf(sself - mx);
-    sum += pself;
-    __syncwarp(hmask);
-    float4 acc;
-    {
-      const float2 va = __half22float2(v01), vb = __half22float2(v23);
-      acc = make_float4(pself * va.x, pself * va.y, pself * vb.x, pself * vb.y);
-    }
-    const __half* vbase = vc + (long long)ri.chunk * n_ctx * a.slots * d + h * 64 + e0;
-    const long long pos_stride = (long long)a.slots * d;
-#pragma unroll 1
-    for (int j0 = 0; j0 < pos; j0 += 8) {
-      uint2 vr[8];
-      float pj[8];
+      for (int i = 0; i < 32; ++i) {
+        const int jj = blk * 32 + i;
+        const int si = __shfl_sync(0xffffffffu, slot, i);
+        vr[i] = (jj < pos) ? __ldcg(reinterpret_cast<const uint32_t*>(vbase + (long long)jj * pos_stride + (long long)si * d)) : 0u;
+      }
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int jj = j0 + i;
-        pj[i] = 0.f;
-        vr[i] = make_uint2(0u, 0u);
-        if (jj < pos) {
-          pj[i] = sc[jj];
-          vr[i] = __ldcg(reinterpret_cast<const uint2*>(vbase + jj * pos_stride + (long long)sl[jj] * d));
-        }
+        const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * i), qb = *reinterpret_cast<const float4*>(qs + 8 * i + 4);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].y)),
+                     f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].w));
+        s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
+        s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
       }
+      const float sv = valid ? s0 + s1 : -INFINITY;
+      const float m_new = fmaxf(m_run, warp_max(sv));
+      const float alpha = __expf(m_run - m_new);
+      const float p = valid ? __expf(sv - m_new) : 0.f;
+      l_run = fmaf(l_run, alpha, warp_sum(p));
+      acc.x *= alpha;
+      acc.y *= alpha;
+      m_run = m_new;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 va = __half22float2(*reinterpret_cast<const __half2*>(&vr[i].x)), vb = __half22float2(*reinterpret_cast<const __half2*>(&vr[i].y));
-        acc.x = fmaf(pj[i], va.x, acc.x);
-        acc.y = fmaf(pj[i], va.y, acc.y);
-        acc.z = fmaf(pj[i], vb.x, acc.z);
-        acc.w = fmaf(pj[i], vb.y, acc.w);
+      for (int i = 0; i < 32; ++i) {
+        const float pi = __shfl_sync(0xffffffffu, p, i);
+        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[i]));
+        acc.x = fmaf(pi, vv2.x, acc.x);
+        acc.y = fmaf(pi, vv2.y, acc.y);
       }
     }
-    const float inv = 1.f / sum;
-    *reinterpret_cast<uint2*>(a.ao + (long long)r * d + h * 64 + e0) = make_uint2(pack_half2(acc.x * inv, acc.y * inv), pack_half2(acc.z * inv, acc.w * inv));
-    __syncwarp(hmask);  // sc / qs / sl are reused by this half-warp's next task
+    const float inv = 1.f / l_run;
+    *reinterpret_cast<uint32_t*>(a.ao + (long long)r * d + h * 64 + e0) = pack_half2(acc.x * inv, acc.y * inv);
+    __syncwarp();  // qs is reused by this warp's next task
   }
 }
 
-// Beam-shared cross attention: one (key split, head, chunk) task for all rows of the chunk (<= 8); the last split of a
-// (chunk, head) group to finish combines.  Same math as dstep.cu's task (S = K Q^T and O^T = V^T P^T on mma.sync from the
-// XOR-swizzled K/V tile); the query comes from the raw cross-q sums with the deferred LayerNorm + bias applied here.
-__device__ __noinline__ void bs_cross_attn_task(const BStepArgs& a, BsShared& sh, int layer, int task, uint32_t full_parity, uint64_t* full_bar,
-                                                unsigned char* kvbuf, unsigned char* scratch) {
+// Beam-shared cross attention, stream-K over key tiles.  The 1500 keys of a (chunk, head) group are 7 tiles of ~214 keys; all
+// tiles of the step form one sequence (group-major) that is cut into equal contiguous runs, one per CTA.  A CTA walks its run with
+// an online softmax: scores S = K Q^T and O^T = V^T P^T on mma.sync from the XOR-swizzled K/V tile (as dstep.cu), running max /
+// sum per query in shared memory, output accumulators in registers across the tiles of a group.  A group that lies entirely inside
+// one run is written straight to `ao`; a group cut by a run boundary leaves one partial record per piece and the piece that
+// completes the group (ticket = tiles done) merges them.  With 16 chunks a run is ~15 tiles: two groups whole, two cut.
+__device__ __forceinline__ bool bs_piece_starts_at(int t, unsigned NT) {  // is tile t the first tile of some CTA's run?
+  const unsigned G = gridDim.x;
+  const unsigned c = ((unsigned)(t + 1) * G + NT - 1) / NT - 1;
+  return (int)(NT * c / G) == t;
+}
+
+__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* kv0, unsigned char* U) {
+  int t0, t1;
+  bs_xrange(a, t0, t1);
+  const int nt = t1 - t0;
+  if (nt == 0) return;
+  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
   const int T = a.T, S = kDsXSplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int split = task % S, rest = task / S, h = rest % a.H, b = rest / a.H;
-  const int nq = a.rows_per_chunk, row0 = b * a.rows_per_chunk, d = a.d;
-  const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
-  const int nkp = (nk + 15) & ~15;
-  __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
-  __half* vt = kt + kDsXKeysMax * 64;
-  __half* qs = reinterpret_cast<__half*>(scratch);                // [8][96], pre-scaled by 1/8
-  float* sc = reinterpret_cast<float*>(qs + kBsXQ * kBsQLd);      // [8][kBsScLd]
-  __half* pr = reinterpret_cast<__half*>(sc + kBsXQ * kBsScLd);   // [8][kBsPLd]
-  float* wred = reinterpret_cast<float*>(pr + kBsXQ * kBsPLd);    // [2][8][64]
-  float* stat = wred + 2 * kBsXQ * 64;                            // [8][2]
-  const BLayer& lay = sh.lay[layer];
-  if (tid < 64) {
-    const int q = tid >> 3, c = tid & 7;
+  const int nq = a.rows_per_chunk, d = a.d;
+  const unsigned NT = (unsigned)(S * a.H * a.n_chunks);
+  unsigned char* kv1 = U;
+  unsigned char* scratch = U + kBsKvBytes;
+  __half* qs_all = reinterpret_cast<__half*>(scratch);                       // [kBsXGroups][8][96], pre-scaled by 1/8
+  float* sc = reinterpret_cast<float*>(qs_all + kBsXGroups * kBsXQ * kBsQLd);  // [8][kBsScLd]
+  __half* pr = reinterpret_cast<__half*>(sc + kBsXQ * kBsScLd);               // [8][kBsPLd]
+  float* wred = reinterpret_cast<float*>(pr + kBsXQ * kBsPLd);                // [2][8][64]
+  float* mrun = wred + 2 * kBsXQ * 64;                                        // [8]
+  float* lrun = mrun + kBsXQ;                                                 // [8]
+  float* alpha = lrun + kBsXQ;                                                // [8]
+  const BLayer& lay = sh.lay[l];
+  if (tid == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now
+  // ---- queries of every group this run touches, in one round trip (deferred LayerNorm + bias, fp16 rounding, then the exact 1/8) ----
+  const int g_first = t0 / S, n_groups = (t1 - 1) / S - g_first + 1;
+  for (int idx = tid; idx < n_groups * 64; idx += kBsThreads) {
+    const int gi = idx >> 6, q = (idx & 63) >> 3, c = idx & 7;
+    const int grp = g_first + gi, h = grp % a.H, b = grp / a.H;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (q < nq) {
-      const int r = row0 + q;
+      const int r = b * nq + q;
       float mean, rstd;
-      bs_row_stats(a.stats + (long long)(3 * layer + 1) * a.R * 2, r, d, mean, rstd);
+      bs_row_stats(a.stats + (long long)(3 * l + 1) * a.R * 2, r, d, mean, rstd);
       const float mr = mean * rstd;
       const float* raw = a.cq32 + (long long)r * d + h * 64 + c * 8;
       const float* ws = lay.wsum[1] + h * 64 + c * 8;
@@ -593,7 +603,6 @@ __device__ __noinline__ void bs_cross_attn_task(const BStepArgs& a, BsShared& sh
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(ws)), w1 = __ldg(reinterpret_cast<const float4*>(ws) + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(bs)), b1 = __ldg(reinterpret_cast<const float4*>(bs) + 1);
 #define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
-      // fp16 rounding of q first (as the other decode paths store it), then the exact 1/8 scale
       __half2 hq[4] = {__floats2half2_rn(BS_FIX(r0.x, w0.x, b0.x), BS_FIX(r0.y, w0.y, b0.y)), __floats2half2_rn(BS_FIX(r0.z, w0.z, b0.z), BS_FIX(r0.w, w0.w, b0.w)),
                        __floats2half2_rn(BS_FIX(r1.x, w1.x, b1.x), BS_FIX(r1.y, w1.y, b1.y)), __floats2half2_rn(BS_FIX(r1.z, w1.z, b1.z), BS_FIX(r1.w, w1.w, b1.w))};
 #undef BS_FIX
@@ -602,162 +611,208 @@ __device__ __noinline__ void bs_cross_attn_task(const BStepArgs& a, BsShared& sh
       for (int i = 0; i < 4; ++i) hq[i] = __hmul2(hq[i], sc8);
       v = make_uint4(*reinterpret_cast<uint32_t*>(&hq[0]), *reinterpret_cast<uint32_t*>(&hq[1]), *reinterpret_cast<uint32_t*>(&hq[2]), *reinterpret_cast<uint32_t*>(&hq[3]));
     }
-    *reinterpret_cast<uint4*>(qs + q * kBsQLd + c * 8) = v;
+    *reinterpret_cast<uint4*>(qs_all + (gi * kBsXQ + q) * kBsQLd + c * 8) = v;
   }
-  mbar_wait(full_bar, full_parity);
-  // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite (after the tile has landed: the TMA never writes them)
-  for (int i = tid; i < (nkp - nk) * 8; i += kBsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
-  bs_sync();
-  // ---- scores ----
-#pragma unroll 1
-  for (int tile = warp; tile * 16 < nkp; tile += kBsWarps) {
-    const int rg = tile * 16 + g, swz = (k0 + rg) & 7;  // rows rg and rg + 8 share the swizzle
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c2 = 0; c2 < 2; ++c2) {
-      const int pc = ((4 * c2 + t) ^ swz) << 3;
-      const uint4 wa = *reinterpret_cast<const uint4*>(kt + rg * 64 + pc);
-      const uint4 wb = *reinterpret_cast<const uint4*>(kt + (rg + 8) * 64 + pc);
-      const uint4 xv = *reinterpret_cast<const uint4*>(qs + g * kBsQLd + 32 * c2 + 8 * t);
-      ds_mma(acc, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
-      ds_mma(acc, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
-    }
-    sc[(2 * t) * kBsScLd + rg] = acc[0];
-    sc[(2 * t + 1) * kBsScLd + rg] = acc[1];
-    sc[(2 * t) * kBsScLd + rg + 8] = acc[2];
-    sc[(2 * t + 1) * kBsScLd + rg + 8] = acc[3];
-  }
-  bs_sync();
-  {  // one warp per query: partial softmax statistics, probabilities as fp16
-    const int q = warp;
-    if (q < nq) {
-      float mx = -INFINITY;
-      for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kBsScLd + j]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < nkp; j += 32) {
-        const float p = j < nk ? __expf(sc[q * kBsScLd + j] - mx) : 0.f;
-        const __half ph = __float2half_rn(p);
-        pr[q * kBsPLd + j] = ph;
-        sum += __half2float(ph);
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) {
-        stat[q * 2] = mx;
-        stat[q * 2 + 1] = sum;
-      }
-    } else {
-      for (int j = lane; j < nkp; j += 32) pr[q * kBsPLd + j] = __float2half_rn(0.f);
-    }
-  }
-  bs_sync();
-  {  // ---- O^T = V^T P^T: warp -> (16 output dims, half of the key tiles) ----
-    const int dtile = warp & 3, khalf = warp >> 2;
-    const int mi = lane >> 3, r8 = lane & 7;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int tile = khalf; tile * 16 < nkp; tile += 2) {
-      const int row = tile * 16 + 8 * (mi >> 1) + r8;
-      const int pc = ((2 * dtile + (mi & 1)) ^ ((k0 + row) & 7)) << 3;
-      uint32_t a0, a1, a2, a3;
-      ds_ldmatrix_x4_trans(a0, a1, a2, a3, vt + row * 64 + pc);
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + tile * 16 + 2 * t);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + tile * 16 + 2 * t + 8);
-      ds_mma(acc, a0, a1, a2, a3, b0, b1);
-    }
-    float* w = wred + khalf * (kBsXQ * 64);
-    w[(2 * t) * 64 + 16 * dtile + g] = acc[0];
-    w[(2 * t + 1) * 64 + 16 * dtile + g] = acc[1];
-    w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
-    w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
-  }
-  bs_sync();  // the K/V tile is dead from here on (the caller releases the buffer)
-  const long long group = (long long)b * a.H + h;
-  float* part = a.xpart + (group * S + split) * (kBsXQ * 66);
-#pragma unroll 1
-  for (int i = tid; i < nq * 64; i += kBsThreads) {
-    const int q = i >> 6, e = i & 63;
-    __stcg(part + q * 66 + e, wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]);
-  }
-  if (tid < nq) {
-    __stcg(part + tid * 66 + 64, stat[tid * 2]);
-    __stcg(part + tid * 66 + 65, stat[tid * 2 + 1]);
-  }
-  bs_sync();
-  if (tid == 0) {
-    int ticket;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(a.xcounters + group) : "memory");
-    sh.flag = (ticket == S - 1);
-    if (sh.flag) a.xcounters[group] = 0;
-  }
-  bs_sync();
-  if (sh.flag) {
-    const float* pg = a.xpart + group * S * (kBsXQ * 66);
-#pragma unroll 1
-    for (int i = tid; i < nq * 64; i += kBsThreads) {
-      const int q = i >> 6, e = i & 63;
-      float pm[8], pl[8], pa[8];
-#pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        const bool on = s2 < S;
-        const float* base = pg + ((on ? s2 : 0) * kBsXQ + q) * 66;
-        pm[s2] = on ? __ldcg(base + 64) : -INFINITY;
-        pl[s2] = on ? __ldcg(base + 65) : 0.f;
-        pa[s2] = on ? __ldcg(base + e) : 0.f;
-      }
-      float M = pm[0];
-#pragma unroll
-      for (int s2 = 1; s2 < 8; ++s2) M = fmaxf(M, pm[s2]);
-      float num = 0.f, den = 0.f;
-#pragma unroll
-      for (int s2 = 0; s2 < 8; ++s2) {
-        const float w = (s2 < S) ? __expf(pm[s2] - M) : 0.f;
-        num = fmaf(w, pa[s2], num);
-        den = fmaf(w, pl[s2], den);
-      }
-      a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
-    }
-  }
-  bs_sync();
-}
-
-__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* kv0, unsigned char* U) {
-  const int xtasks = kDsXSplits * a.H * a.n_chunks;
-  const int nt = bs_xtasks_of_cta(xtasks);
-  if (nt == 0) return;
-  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
-  unsigned char* kv1 = U;
-  unsigned char* scratch = U + kBsKvBytes;
-  if (threadIdx.x == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now
+  for (int i = tid; i < kBsXQ * kBsPLd; i += kBsThreads) pr[i] = __float2half_rn(0.f);  // rows >= nq stay zero for the whole phase
+  const int dtile = warp & 3, khalf = warp >> 2;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int piece_first = 0;  // split index of the first tile of the current piece
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
+    const int tile = t0 + k, grp = tile / S, split = tile - grp * S, gi = grp - g_first;
+    const int h = grp % a.H, b = grp / a.H, row0 = b * nq;
     const int buf = k & 1;
+    unsigned char* kvbuf = buf ? kv1 : kv0;
     const int u = l * (buf ? n_odd : n_even) + (k >> 1);
-    bs_cross_attn_task(a, sh, l, blockIdx.x + k * gridDim.x, (uint32_t)(u & 1), &sh.kvfull[buf], buf ? kv1 : kv0, scratch);
+    const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
+    const int nkp = (nk + 15) & ~15;
+    __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
+    __half* vt = kt + kDsXKeysMax * 64;
+    const __half* qs = qs_all + gi * kBsXQ * kBsQLd;
+    if (k == 0 || split == 0) {  // a new piece starts: reset the running softmax state
+      piece_first = split;
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      if (tid < kBsXQ) {
+        mrun[tid] = -INFINITY;
+        lrun[tid] = 0.f;
+      }
+    }
+    mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
+    // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite (the TMA never writes them)
+    for (int i = tid; i < (nkp - nk) * 8; i += kBsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    bs_sync();
+    // ---- scores ----
+#pragma unroll 1
+    for (int kt16 = warp; kt16 * 16 < nkp; kt16 += kBsWarps) {
+      const int rg = kt16 * 16 + g, swz = (k0 + rg) & 7;  // rows rg and rg + 8 share the swizzle
+      float sa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int pc = ((4 * c2 + t) ^ swz) << 3;
+        const uint4 wa = *reinterpret_cast<const uint4*>(kt + rg * 64 + pc);
+        const uint4 wb = *reinterpret_cast<const uint4*>(kt + (rg + 8) * 64 + pc);
+        const uint4 xv = *reinterpret_cast<const uint4*>(qs + g * kBsQLd + 32 * c2 + 8 * t);
+        ds_mma(sa, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
+        ds_mma(sa, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+      }
+      sc[(2 * t) * kBsScLd + rg] = sa[0];
+      sc[(2 * t + 1) * kBsScLd + rg] = sa[1];
+      sc[(2 * t) * kBsScLd + rg + 8] = sa[2];
+      sc[(2 * t + 1) * kBsScLd + rg + 8] = sa[3];
+    }
+    bs_sync();
+    {  // one warp per query: online-softmax update, probabilities as fp16
+      const int q = warp;
+      if (q < nq) {
+        float mx = -INFINITY;
+        for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kBsScLd + j]);
+        mx = warp_max(mx);
+        const float m_old = mrun[q], m_new = fmaxf(m_old, mx);
+        float sum = 0.f;
+        for (int j = lane; j < nkp; j += 32) {
+          const float pv = j < nk ? __expf(sc[q * kBsScLd + j] - m_new) : 0.f;
+          const __half ph = __float2half_rn(pv);
+          pr[q * kBsPLd + j] = ph;
+          sum += __half2float(ph);
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) {
+          const float al = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
+          mrun[q] = m_new;
+          lrun[q] = fmaf(lrun[q], al, sum);
+          alpha[q] = al;
+        }
+      } else if (lane == 0) {
+        alpha[q] = 1.f;
+      }
+    }
+    bs_sync();
+    {  // ---- O^T (+)= V^T P^T: warp -> (16 output dims, half of the key tiles); accumulators rescaled by the softmax update ----
+      const int mi = lane >> 3, r8 = lane & 7;
+      const float al0 = alpha[2 * t], al1 = alpha[2 * t + 1];
+      acc[0] *= al0;
+      acc[1] *= al1;
+      acc[2] *= al0;
+      acc[3] *= al1;
+#pragma unroll 1
+      for (int kt16 = khalf; kt16 * 16 < nkp; kt16 += 2) {
+        const int row = kt16 * 16 + 8 * (mi >> 1) + r8;
+        const int pc = ((2 * dtile + (mi & 1)) ^ ((k0 + row) & 7)) << 3;
+        uint32_t a0, a1, a2, a3;
+        ds_ldmatrix_x4_trans(a0, a1, a2, a3, vt + row * 64 + pc);
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + kt16 * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + kt16 * 16 + 2 * t + 8);
+        ds_mma(acc, a0, a1, a2, a3, b0, b1);
+      }
+    }
+    const bool piece_ends = (k == nt - 1 || split == S - 1);
+    if (piece_ends) {
+      float* w = wred + khalf * (kBsXQ * 64);
+      w[(2 * t) * 64 + 16 * dtile + g] = acc[0];
+      w[(2 * t + 1) * 64 + 16 * dtile + g] = acc[1];
+      w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
+      w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
+    }
+    bs_sync();  // the K/V tile is dead from here on
     // release the tile: buffer 0 always (the producer may fetch the next layer's first tile), buffer 1 only for another tile of this phase
-    if (threadIdx.x == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+    if (tid == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+    if (!piece_ends) continue;
+    const int n_piece = split - piece_first + 1;
+    if (n_piece == S) {  // the whole group was handled here: normalise and write
+      for (int i = tid; i < nq * 64; i += kBsThreads) {
+        const int q = i >> 6, e = i & 63;
+        a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn((wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]) / lrun[q]);
+      }
+    } else {
+      float* part = a.xpart + ((long long)grp * S + piece_first) * (kBsXQ * 66);
+      for (int i = tid; i < nq * 64; i += kBsThreads) {
+        const int q = i >> 6, e = i & 63;
+        __stcg(part + q * 66 + e, wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]);
+      }
+      if (tid < nq) {
+        __stcg(part + tid * 66 + 64, mrun[tid]);
+        __stcg(part + tid * 66 + 65, lrun[tid]);
+      }
+      bs_sync();
+      if (tid == 0) {
+        int ticket;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(ticket) : "l"(a.xcounters + grp), "r"(n_piece) : "memory");
+        sh.flag = (ticket + n_piece == S);
+        if (sh.flag) a.xcounters[grp] = 0;
+      }
+      bs_sync();
+      if (sh.flag) {  // this piece completed the group: merge the pieces (their first splits are where some CTA's run starts, or 0)
+        const float* pg = a.xpart + (long long)grp * S * (kBsXQ * 66);
+        unsigned present = 1u;
+        for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2, NT) ? (1u << s2) : 0u;
+#pragma unroll 1
+        for (int i = tid; i < nq * 64; i += kBsThreads) {
+          const int q = i >> 6, e = i & 63;
+          float pm[8], pl[8], pa[8];
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2) {
+            const bool on = s2 < S && ((present >> s2) & 1u);
+            const float* base = pg + ((on ? s2 : 0) * kBsXQ + q) * 66;
+            pm[s2] = on ? __ldcg(base + 64) : -INFINITY;
+            pl[s2] = on ? __ldcg(base + 65) : 0.f;
+            pa[s2] = on ? __ldcg(base + e) : 0.f;
+          }
+          float M = pm[0];
+#pragma unroll
+          for (int s2 = 1; s2 < 8; ++s2) M = fmaxf(M, pm[s2]);
+          float num = 0.f, den = 0.f;
+#pragma unroll
+          for (int s2 = 0; s2 < 8; ++s2) {
+            const float wgt = (pm[s2] == -INFINITY) ? 0.f : __expf(pm[s2] - M);
+            num = fmaf(wgt, pa[s2], num);
+            den = fmaf(wgt, pl[s2], den);
+          }
+          a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
+        }
+      }
+    }
+    bs_sync();  // wred / running statistics are reused by the next piece
   }
 }
 
-// h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums
+// h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums.
+// Three float4 per thread are in flight together (one memory round trip for a CTA's whole slice at 80 rows).
 __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l) {
   const int d = a.d, R = a.R;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l + 2) * R * 2;
   const int per_row = d;  // float4 units per row of 4d
-  const int total = R * per_row;
-  for (int i = blockIdx.x * kBsThreads + threadIdx.x; i < total; i += gridDim.x * kBsThreads) {
-    const int r = i / per_row, n = (i - r * per_row) * 4;
-    float mean, rstd;
-    bs_row_stats(st, r, d, mean, rstd);
-    const float mr = mean * rstd;
-    float4* hp = reinterpret_cast<float4*>(a.h32 + (long long)r * 4 * d + n);
-    const float4 hv = __ldcg(hp);
-    const float4 w = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n)), bb = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
-    const float y0 = gelu_erf(fmaf(rstd, hv.x, fmaf(-mr, w.x, bb.x))), y1 = gelu_erf(fmaf(rstd, hv.y, fmaf(-mr, w.y, bb.y)));
-    const float y2 = gelu_erf(fmaf(rstd, hv.z, fmaf(-mr, w.z, bb.z))), y3 = gelu_erf(fmaf(rstd, hv.w, fmaf(-mr, w.w, bb.w)));
-    *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
-    __stcg(hp, make_float4(0.f, 0.f, 0.f, 0.f));
+  const int total = R * per_row, stride = gridDim.x * kBsThreads;
+  constexpr int UNR = 3;
+#pragma unroll 1
+  for (int i0 = blockIdx.x * kBsThreads + threadIdx.x; i0 < total; i0 += UNR * stride) {
+    float4 hv[UNR], w[UNR], bb[UNR];
+    float2 sv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + u * stride;
+      if (i < total) {
+        const int r = i / per_row, n = (i - r * per_row) * 4;
+        hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + (long long)r * 4 * d + n));
+        w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
+        bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
+        sv[u] = __ldcg(reinterpret_cast<const float2*>(st) + r);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int i = i0 + u * stride;
+      if (i < total) {
+        const int r = i / per_row, n = (i - r * per_row) * 4;
+        const float mean = sv[u].x / d;
+        const float rstd = rsqrtf(fmaxf(sv[u].y / d - mean * mean, 0.f) + 1e-5f);
+        const float mr = mean * rstd;
+        const float y0 = gelu_erf(fmaf(rstd, hv[u].x, fmaf(-mr, w[u].x, bb[u].x))), y1 = gelu_erf(fmaf(rstd, hv[u].y, fmaf(-mr, w[u].y, bb[u].y)));
+        const float y2 = gelu_erf(fmaf(rstd, hv[u].z, fmaf(-mr, w[u].z, bb[u].z))), y3 = gelu_erf(fmaf(rstd, hv[u].w, fmaf(-mr, w[u].w, bb[u].w)));
+        *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+        __stcg(reinterpret_cast<float4*>(a.h32 + (long long)r * 4 * d + n), make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+    }
   }
 }
 
@@ -883,6 +938,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       sh.epoch = 0;
       sh.prof_i = 1;
       sh.acc_par[0] = sh.acc_par[1] = 0;
+      for (int i = 0; i < 6 * 8; ++i) sh.ticks[i] = 0;
       for (int i = 0; i < kBsSlots; ++i) {
         mbar_init(&sh.wfull[i], 1);
         mbar_init(&sh.wempty[i], 1);
@@ -955,7 +1011,11 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       bs_grid_barrier(a, sh);
     }
     if (run) bs_logits_phase(a, sh, kv0);
-    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+      a.prof[sh.prof_i] = ds_globaltimer();
+      for (int k = 0; k < 6; ++k)
+        for (int p2 = 0; p2 < 8; ++p2) a.prof[3000 + k * 16 + (p2 == 7 ? 15 : p2)] += sh.ticks[k * 8 + p2];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1023,7 +1083,11 @@ size_t bstep_xpart_floats(const BStepArgs& a) { return (size_t)a.n_chunks * a.H 
 
 bool bstep_supported(int num_sms, BStepArgs& a) {
   if (a.R < 1 || a.R > kBsMaxRows || a.d % 64 != 0 || a.d > 1280 || a.d != 64 * a.H || a.L > 32 || a.rows_per_chunk > kBsXQ || num_sms < 8) return false;
-  if ((a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || a.vpad % 4 != 0) return false;
+  if ((a.T + kDsXSplits - 1) / kDsXSplits + 1 > kDsXKeysMax || a.vpad % 4 != 0 || a.n_ctx > 448) return false;
+  {  // a CTA's run of cross-attention tiles may touch at most kBsXGroups (chunk, head) groups
+    const int NT = kDsXSplits * a.H * a.n_chunks, run = (NT + num_sms - 1) / num_sms;
+    if ((run + kDsXSplits - 1) / kDsXSplits + 1 > kBsXGroups) return false;
+  }
   a.NP = bs_ceil16(a.R);
   const int d = a.d, G = num_sms;
   // activation tiles of the busiest GEMM phase (an even share of the atoms, rounded up) and the condition for two segments
@@ -1039,7 +1103,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
   u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
-  u = std::max(u, (size_t)(16 * a.n_ctx + 16 * 64) * 4 + (size_t)16 * a.n_ctx);              // self-attention scores / q / slots
+  u = std::max(u, (size_t)kBsWarps * 64 * 4);                                                // self-attention: one query per warp
   a.u_bytes = (int)((u + 1023) & ~size_t(1023));
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);

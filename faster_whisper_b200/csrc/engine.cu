@@ -1237,6 +1237,18 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       for (int ph = 0; ph < 9; ++ph)
         fprintf(stderr, "[bstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
                 wait[ph] / L / 1e3, L);
+      {
+        std::vector<unsigned long long> f(6 * 16);
+        B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
+        static const char* kinds[6] = {"qkv", "out", "cross_q", "cross_out", "ffn1", "ffn2"};
+        for (int k = 0; k < 6; ++k) {
+          const double cnt = (double)f[k * 16 + 15];
+          if (cnt > 0)
+            fprintf(stderr, "[bstep prof]   %-9s cycles (CTA 0): stage %.0f  mma-wait %.0f  epilogue %.0f  bulk-wait %.0f\n", kinds[k], f[k * 16] / cnt,
+                    f[k * 16 + 1] / cnt, f[k * 16 + 2] / cnt, f[k * 16 + 3] / cnt);
+        }
+      }
     }
     if (m->d_prof && use_dstep) {
       B2W_CUDA(cudaStreamSynchronize(s));
