@@ -106,10 +106,13 @@ __device__ __forceinline__ int bs_gemm_phase_index(int s) {
   const int ph = j == 0 ? 0 : (j == 1 ? 2 : (j == 2 ? 3 : (j == 3 ? 5 : (j == 4 ? 6 : 8))));
   return 1 + 9 * l + ph;
 }
-struct BsRange {
+struct BsRange {  // scalars only: arrays indexed at run time would live in local memory (and the L1 next to 220 KB of smem is tiny)
   int a0, a1, KA;
   int nseg;
-  int nb[2], ka0[2], n[2];
+  int nb0, nb1, ka00, ka01, n0, n1;
+  __device__ __forceinline__ int nb(int sg) const { return sg ? nb1 : nb0; }
+  __device__ __forceinline__ int ka0(int sg) const { return sg ? ka01 : ka00; }
+  __device__ __forceinline__ int n(int sg) const { return sg ? n1 : n0; }
 };
 // atoms of GEMM s owned by this CTA, cut at n-block boundaries (at most two segments: an even share is shorter than one n-block's K)
 __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
@@ -122,15 +125,18 @@ __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
   r.a0 = (int)(A * blockIdx.x / gridDim.x);
   r.a1 = (int)(A * (blockIdx.x + 1) / gridDim.x);
   r.nseg = 0;
-  int cur = r.a0;
-  while (cur < r.a1 && r.nseg < 2) {
-    const int nb = cur / r.KA, ka = cur - nb * r.KA;
-    const int n = min(r.a1 - cur, r.KA - ka);
-    r.nb[r.nseg] = nb;
-    r.ka0[r.nseg] = ka;
-    r.n[r.nseg] = n;
-    r.nseg += 1;
-    cur += n;
+  r.nb0 = r.nb1 = r.ka00 = r.ka01 = r.n0 = r.n1 = 0;
+  if (r.a1 > r.a0) {
+    r.nb0 = r.a0 / r.KA;
+    r.ka00 = r.a0 - r.nb0 * r.KA;
+    r.n0 = min(r.a1 - r.a0, r.KA - r.ka00);
+    r.nseg = 1;
+    if (r.a0 + r.n0 < r.a1) {
+      r.nb1 = r.nb0 + 1;
+      r.ka01 = 0;
+      r.n1 = min(r.a1 - r.a0 - r.n0, r.KA);
+      r.nseg = 2;
+    }
   }
   return r;
 }
@@ -263,7 +269,7 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
 #pragma unroll 1
     for (int sg = 0; sg < r.nseg; ++sg) {
 #pragma unroll 1
-      for (int i = 0; i < r.n[sg]; ++i) {
+      for (int i = 0; i < r.n(sg); ++i) {
         atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
         local += 1;
       }
@@ -328,10 +334,10 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
       if constexpr (X) v1[u] = make_uint4(0u, 0u, 0u, 0u);
       if (q < total) {
         const int i = q / per_atom, rem = q - i * per_atom, r = rem >> 3, c = rem & 7;
-        const int sg = i < rg.n[0] ? 0 : 1;
-        const int ka = sg == 0 ? rg.ka0[0] + i : i - rg.n[0];
+        const int sg = i < rg.n(0) ? 0 : 1;
+        const int ka = sg == 0 ? rg.ka0(0) + i : i - rg.n(0);
         dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
-        meta[u] = r | ((X && rg.nb[sg] == 0) ? 256 : 0);
+        meta[u] = r | ((X && rg.nb(sg) == 0) ? 256 : 0);
         if (r < R) {
           if constexpr (X) {
             const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (long long)r * ld + ka * 64 + c * 8);
@@ -413,8 +419,8 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   const int q = warp & 3, ch = warp >> 2, half_cols = a.NP >> 1;
 #pragma unroll 1
   for (int sg = 0; sg < rg.nseg; ++sg) {
-    const int n_glob = rg.nb[sg] * 128 + q * 32 + lane;
-    const float bv = (bias && rg.ka0[sg] == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
+    const int n_glob = rg.nb(sg) * 128 + q * 32 + lane;
+    const float bv = (bias && rg.ka0(sg) == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
 #pragma unroll 1
     for (int c = 0; c < half_cols; c += 8) {
@@ -427,8 +433,8 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
     fence_proxy_async();
     bs_sync();
     if (tid < a.R) {
-      const int nvalid = min(128, N - rg.nb[sg] * 128);
-      bs_bulk_reduce_f32(out + (long long)tid * ldo + rg.nb[sg] * 128, stg + tid * 128, (uint32_t)nvalid * 4u);
+      const int nvalid = min(128, N - rg.nb(sg) * 128);
+      bs_bulk_reduce_f32(out + (long long)tid * ldo + rg.nb(sg) * 128, stg + tid * 128, (uint32_t)nvalid * 4u);
       bs_bulk_commit();
       if (sg + 1 < rg.nseg) bs_bulk_wait_read();
     }
@@ -446,18 +452,22 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
 
 // Masked self-attention: one (row, head) task per warp.  q, k, v of the new token come from the raw QKV sums (deferred LayerNorm +
 // bias applied here); k and v are rounded to fp16 and written to the paged cache.  The history is gathered through the beam
-// ancestry table in blocks of 32 keys with an online softmax: per block ONE memory round trip — lane j fetches the K row of key
-// j (8 x 16 B) while all 32 V rows of the block are fetched 4 B per lane (lane = 2 output dims), all loads in flight together.
+// ancestry table in blocks of 32 keys with an online softmax.  Per block ONE memory round trip and no data registers: lane j
+// copies the K and V rows of key j into the warp's shared-memory tile with cp.async (16 x 16 B); the K tile is XOR-swizzled so
+// that "lane = key" reads are conflict-free, the V tile is read "lane = 2 output dims".
+constexpr int kBsSelfTile = 2 * 32 * 64 * 2;  // K + V tile of one warp (8 KB)
 __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
-  float* qs = reinterpret_cast<float*>(U) + warp * 64;
+  __half* kt = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [32 keys][64], 16-byte chunks at chunk ^ (key & 7)
+  __half* vt = kt + 32 * 64;                                               // [32 keys][64]
+  float* qs = reinterpret_cast<float*>(U + (size_t)kBsWarps * kBsSelfTile) + warp * 64;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
   __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
   const int ntasks = H * a.R, e0 = 2 * lane;
-  const long long pos_stride = (long long)a.slots * d;
+  const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
 #pragma unroll 1
   for (int task = blockIdx.x * kBsWarps + warp; task < ntasks; task += gridDim.x * kBsWarps) {
     const int r = task / H, h = task - r * H;
@@ -491,16 +501,16 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     const __half2 v16 = __floats2half2_rn(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y));
 #undef BS_FIX
     const float2 qf = __half22float2(q16), kf = __half22float2(k16), vf = __half22float2(v16);
-    const long long self_off = (((long long)ri.chunk * n_ctx + pos) * a.slots + ri.slot) * d + h * 64 + e0;
+    const long long chunk_off = (long long)ri.chunk * n_ctx * pos_stride + h * 64;
+    const long long self_off = chunk_off + (long long)pos * pos_stride + ri.slot * d + e0;
     *reinterpret_cast<__half2*>(kc + self_off) = k16;
     *reinterpret_cast<__half2*>(vc + self_off) = v16;
     *reinterpret_cast<float2*>(qs + e0) = make_float2(qf.x * 0.125f, qf.y * 0.125f);
     float m_run = warp_sum(qf.x * 0.125f * kf.x + qf.y * 0.125f * kf.y);  // the new token's own key
     float l_run = 1.f;
     float2 acc = vf;
-    __syncwarp();
-    const __half* kbase = kc + (long long)ri.chunk * n_ctx * pos_stride + h * 64;
-    const __half* vbase = vc + (long long)ri.chunk * n_ctx * pos_stride + h * 64 + e0;
+    const __half* kbase = kc + chunk_off;
+    const __half* vbase = vc + chunk_off;
 #pragma unroll 1
     for (int blk = 0; blk * 32 < pos; ++blk) {
       const int bw = blk >> 2;
@@ -508,27 +518,35 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       const int slot = (int)((word >> (8 * (blk & 3))) & 255u);
       const int j = blk * 32 + lane;
       const bool valid = j < pos;
-      uint4 kr[8];
-      {
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)(valid ? j : 0) * pos_stride + (long long)slot * d);
+      const int nvalid = min(32, pos - blk * 32);
+      __syncwarp();  // the previous block's tile (and qs of a new task) is no longer being read
+      if (valid) {
+        const int off = j * pos_stride + slot * d;  // elements; < 2^31 for every supported shape
+        const __half* ks = kbase + off;
+        const __half* vs = vbase + off;
+        __half* kd = kt + lane * 64;
+        __half* vd = vt + lane * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) kr[i] = valid ? __ldcg(kp + i) : make_uint4(0u, 0u, 0u, 0u);
+        for (int c = 0; c < 8; ++c) {
+          ds_cp_async16(kd + ((c ^ (lane & 7)) << 3), ks + c * 8);
+          ds_cp_async16(vd + (c << 3), vs + c * 8);
+        }
       }
-      uint32_t vr[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int jj = blk * 32 + i;
-        const int si = __shfl_sync(0xffffffffu, slot, i);
-        vr[i] = (jj < pos) ? __ldcg(reinterpret_cast<const uint32_t*>(vbase + (long long)jj * pos_stride + (long long)si * d)) : 0u;
-      }
+      ds_cp_commit();
+      ds_cp_wait_all();
+      __syncwarp();
       float s0 = 0.f, s1 = 0.f;
+      {
+        const uint4* kp = reinterpret_cast<const uint4*>(kt + lane * 64);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * i), qb = *reinterpret_cast<const float4*>(qs + 8 * i + 4);
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].y)),
-                     f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr[i].w));
-        s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
-        s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
+        for (int c = 0; c < 8; ++c) {
+          const uint4 kr = kp[c ^ (lane & 7)];
+          const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * c), qb = *reinterpret_cast<const float4*>(qs + 8 * c + 4);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr.y)),
+                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr.w));
+          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
+          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
+        }
       }
       const float sv = valid ? s0 + s1 : -INFINITY;
       const float m_new = fmaxf(m_run, warp_max(sv));
@@ -538,17 +556,17 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       acc.x *= alpha;
       acc.y *= alpha;
       m_run = m_new;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      const __half2* vrow = reinterpret_cast<const __half2*>(vt) + lane;
+#pragma unroll 4
+      for (int i = 0; i < nvalid; ++i) {
         const float pi = __shfl_sync(0xffffffffu, p, i);
-        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[i]));
+        const float2 vv2 = __half22float2(vrow[i * 32]);
         acc.x = fmaf(pi, vv2.x, acc.x);
         acc.y = fmaf(pi, vv2.y, acc.y);
       }
     }
     const float inv = 1.f / l_run;
     *reinterpret_cast<uint32_t*>(a.ao + (long long)r * d + h * 64 + e0) = pack_half2(acc.x * inv, acc.y * inv);
-    __syncwarp();  // qs is reused by this warp's next task
   }
 }
 
@@ -790,14 +808,12 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
     float2 sv[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int i = i0 + u * stride;
-      if (i < total) {
-        const int r = i / per_row, n = (i - r * per_row) * 4;
-        hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + (long long)r * 4 * d + n));
-        w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
-        bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
-        sv[u] = __ldcg(reinterpret_cast<const float2*>(st) + r);
-      }
+      const int i = min(i0 + u * stride, total - 1);  // clamped: the loads are unconditional, only the stores are predicated
+      const int r = i / per_row, n = (i - r * per_row) * 4;
+      hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + (long long)r * 4 * d + n));
+      w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
+      bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
+      sv[u] = __ldcg(reinterpret_cast<const float2*>(st) + r);
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -1103,7 +1119,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
   u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
-  u = std::max(u, (size_t)kBsWarps * 64 * 4);                                                // self-attention: one query per warp
+  u = std::max(u, (size_t)kBsWarps * (kBsSelfTile + 64 * 4));                                // self-attention: K/V tile + query per warp
   a.u_bytes = (int)((u + 1023) & ~size_t(1023));
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
