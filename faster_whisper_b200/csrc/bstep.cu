@@ -85,7 +85,7 @@ struct BsShared {
   unsigned epoch;
   int prof_i;
   int flag;
-  unsigned ticks[6 * 8];     // B2W_DSTEP_PROF: cycles of CTA 0 per GEMM kind: [stage, wait acc, epilogue, bulk wait, count]
+  unsigned ticks[8 * 8];     // B2W_DSTEP_PROF: cycles of CTA 0 per GEMM kind: [stage, wait acc, epilogue, bulk wait, count]
   int acc_par[2];            // parity of the next acc_full wait (compute side)
   uint32_t tmem_base;
   uint64_t wfull[kBsSlots];  // weight atom landed (TMA complete_tx)
@@ -305,6 +305,12 @@ __device__ __forceinline__ void bs_zero_f32(float* p, long long n) {  // all com
     __stcg(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
+// The fp32 split-K accumulation buffers (x, qkv32, cq32, h32) are stored n-block-major: element (row r, channel n) lives at
+// ((n >> 7) * R + r) * 128 + (n & 127), so that the [R x 128] output tile of a GEMM segment is ONE contiguous block and its
+// reduction into L2 is a single cp.reduce.async.bulk (bulk instructions are warp-uniform: one per row would serialise 80 issues).
+__device__ __forceinline__ long long bs_bidx(int R, int r, int n) { return ((long long)(n >> 7) * R + r) * 128 + (n & 127); }
+__host__ __device__ __forceinline__ long long bs_bsize(int R, int N) { return (long long)((N + 127) >> 7) * R * 128; }
+
 __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, float& mean, float& rstd) {
   const float2 s = __ldcg(reinterpret_cast<const float2*>(st) + r);
   mean = s.x / d;
@@ -320,7 +326,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
   const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
   const int NP = a.NP, R = a.R, tid = threadIdx.x;
   const int per_atom = NP * 8, natoms = rg.a1 - rg.a0, total = natoms * per_atom;
-  constexpr int UNR = X ? 6 : 8;
+  constexpr int UNR = 8;
 #pragma unroll 1
   for (int base = tid; base < total; base += kBsThreads * UNR) {
     uint4 v0[UNR], v1[X ? UNR : 1];
@@ -340,7 +346,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
         meta[u] = r | ((X && rg.nb(sg) == 0) ? 256 : 0);
         if (r < R) {
           if constexpr (X) {
-            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (long long)r * ld + ka * 64 + c * 8);
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
             const float4 f0 = __ldcg(p), f1 = __ldcg(p + 1);
             v0[u] = *reinterpret_cast<const uint4*>(&f0);
             v1[u] = *reinterpret_cast<const uint4*>(&f1);
@@ -354,19 +360,21 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
     for (int u = 0; u < UNR; ++u) {
       if constexpr (X) {
         const float4 f0 = *reinterpret_cast<const float4*>(&v0[u]), f1 = *reinterpret_cast<const float4*>(&v1[u]);
-        float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
-        float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
-        // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-        const int r = meta[u] & 255;
-        if ((meta[u] & 256) && (tid & 7) == 0 && r < R && dst[u] >= 0) {
-          atomicAdd(st + 2 * r, s1);
-          atomicAdd(st + 2 * r + 1, s2);
+        if (__any_sync(0xffffffffu, meta[u] & 256)) {  // only the segments of n-block 0 contribute LayerNorm statistics
+          float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
+          float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
+          // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+          const int r = meta[u] & 255;
+          if ((meta[u] & 256) && (tid & 7) == 0 && r < R && dst[u] >= 0) {
+            atomicAdd(st + 2 * r, s1);
+            atomicAdd(st + 2 * r + 1, s2);
+          }
         }
         if (dst[u] >= 0)
           *reinterpret_cast<uint4*>(xs + dst[u]) = make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
@@ -378,6 +386,15 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
 }
 
 // One GEMM phase (compute warps): stage -> signal the MMA thread -> drain the accumulators into L2 with bulk reductions.
+#define BS_ATICK(kind, point, tp)                                        \
+  do {                                                                   \
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
+      const long long _now = clock64();                                  \
+      sh.ticks[(kind) * 8 + (point)] += (unsigned)(_now - (tp));         \
+      (tp) = _now;                                                       \
+    }                                                                    \
+  } while (0)
+
 #define BS_TICK(point)                                                   \
   do {                                                                   \
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -394,15 +411,15 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   long long tp = clock64();
   const BLayer& lay = sh.lay[l];
   float* out;
-  int N, ldo;
+  int N;
   const float* bias = nullptr;
   switch (j) {
-    case 0: out = a.qkv32; N = 3 * d; ldo = 3 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
-    case 1: out = a.x; N = d; ldo = d; bias = lay.bias[1]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
-    case 2: out = a.cq32; N = d; ldo = d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
-    case 3: out = a.x; N = d; ldo = d; bias = lay.bias[3]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
-    case 4: out = a.h32; N = 4 * d; ldo = 4 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
-    default: out = a.x; N = d; ldo = d; bias = lay.bias[5]; bs_stage<false>(a, s, a.h16, 4 * d, nullptr, U); break;
+    case 0: out = a.qkv32; N = 3 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
+    case 1: out = a.x; N = d; bias = lay.bias[1]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
+    case 2: out = a.cq32; N = d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
+    case 3: out = a.x; N = d; bias = lay.bias[3]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
+    case 4: out = a.h32; N = 4 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
+    default: out = a.x; N = d; bias = lay.bias[5]; bs_stage<false>(a, s, a.h16, 4 * d, nullptr, U); break;
   }
   fence_proxy_async();
   bs_sync();
@@ -432,9 +449,8 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
     }
     fence_proxy_async();
     bs_sync();
-    if (tid < a.R) {
-      const int nvalid = min(128, N - rg.nb(sg) * 128);
-      bs_bulk_reduce_f32(out + (long long)tid * ldo + rg.nb(sg) * 128, stg + tid * 128, (uint32_t)nvalid * 4u);
+    if (tid == 0) {  // rows 0 .. R-1 of the staging tile = the segment's contiguous [R x 128] block of the n-block-major output
+      bs_bulk_reduce_f32(out + (long long)rg.nb(sg) * a.R * 128, stg, (uint32_t)a.R * 512u);
       bs_bulk_commit();
       if (sg + 1 < rg.nseg) bs_bulk_wait_read();
     }
@@ -442,7 +458,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   }
   tc_fence_before();
   BS_TICK(2);
-  if (tid < a.R) {
+  if (tid == 0) {
     bs_bulk_wait_all();
     bs_fence_async_all();
   }
@@ -473,6 +489,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
+    long long tp = clock64();
     // ---- everything that does not depend on anything else is requested first: ancestry slots, raw q/k/v, statistics ----
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
     uint32_t slots[4] = {0u, 0u, 0u, 0u};  // n_ctx <= 448 = 14 blocks of 32 keys, one byte per block
@@ -484,9 +501,9 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     }
     float mean, rstd;
     bs_row_stats(st, r, d, mean, rstd);
-    const float* raw = a.qkv32 + (long long)r * 3 * d + h * 64 + e0;
-    const float2 rq = __ldcg(reinterpret_cast<const float2*>(raw)), rk = __ldcg(reinterpret_cast<const float2*>(raw + d)),
-                 rv = __ldcg(reinterpret_cast<const float2*>(raw + 2 * d));
+    const float2 rq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0))),
+                 rk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0))),
+                 rv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
     const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),
@@ -511,6 +528,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     float2 acc = vf;
     const __half* kbase = kc + chunk_off;
     const __half* vbase = vc + chunk_off;
+    BS_ATICK(6, 0, tp);
 #pragma unroll 1
     for (int blk = 0; blk * 32 < pos; ++blk) {
       const int bw = blk >> 2;
@@ -533,8 +551,10 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
         }
       }
       ds_cp_commit();
+      BS_ATICK(6, 1, tp);
       ds_cp_wait_all();
       __syncwarp();
+      BS_ATICK(6, 2, tp);
       float s0 = 0.f, s1 = 0.f;
       {
         const uint4* kp = reinterpret_cast<const uint4*>(kt + lane * 64);
@@ -564,6 +584,8 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
         acc.x = fmaf(pi, vv2.x, acc.x);
         acc.y = fmaf(pi, vv2.y, acc.y);
       }
+      BS_ATICK(6, 3, tp);
+      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
     }
     const float inv = 1.f / l_run;
     *reinterpret_cast<uint32_t*>(a.ao + (long long)r * d + h * 64 + e0) = pack_half2(acc.x * inv, acc.y * inv);
@@ -614,7 +636,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       float mean, rstd;
       bs_row_stats(a.stats + (long long)(3 * l + 1) * a.R * 2, r, d, mean, rstd);
       const float mr = mean * rstd;
-      const float* raw = a.cq32 + (long long)r * d + h * 64 + c * 8;
+      const float* raw = a.cq32 + bs_bidx(a.R, r, h * 64 + c * 8);
       const float* ws = lay.wsum[1] + h * 64 + c * 8;
       const float* bs = lay.bias[2] + h * 64 + c * 8;
       const float4 r0 = __ldcg(reinterpret_cast<const float4*>(raw)), r1 = __ldcg(reinterpret_cast<const float4*>(raw) + 1);
@@ -655,7 +677,9 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
         lrun[tid] = 0.f;
       }
     }
+    long long tp = clock64();
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
+    BS_ATICK(7, 0, tp);
     // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite (the TMA never writes them)
     for (int i = tid; i < (nkp - nk) * 8; i += kBsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
     bs_sync();
@@ -734,6 +758,8 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     bs_sync();  // the K/V tile is dead from here on
     // release the tile: buffer 0 always (the producer may fetch the next layer's first tile), buffer 1 only for another tile of this phase
     if (tid == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+    BS_ATICK(7, 1, tp);
+    if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[7 * 8 + 7] += 1;
     if (!piece_ends) continue;
     const int n_piece = split - piece_first + 1;
     if (n_piece == S) {  // the whole group was handled here: normalise and write
@@ -790,6 +816,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       }
     }
     bs_sync();  // wred / running statistics are reused by the next piece
+    BS_ATICK(7, 2, tp);
   }
 }
 
@@ -810,7 +837,7 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
     for (int u = 0; u < UNR; ++u) {
       const int i = min(i0 + u * stride, total - 1);  // clamped: the loads are unconditional, only the stores are predicated
       const int r = i / per_row, n = (i - r * per_row) * 4;
-      hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + (long long)r * 4 * d + n));
+      hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + bs_bidx(R, r, n)));
       w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
       bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
       sv[u] = __ldcg(reinterpret_cast<const float2*>(st) + r);
@@ -826,7 +853,7 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
         const float y0 = gelu_erf(fmaf(rstd, hv[u].x, fmaf(-mr, w[u].x, bb[u].x))), y1 = gelu_erf(fmaf(rstd, hv[u].y, fmaf(-mr, w[u].y, bb[u].y)));
         const float y2 = gelu_erf(fmaf(rstd, hv[u].z, fmaf(-mr, w[u].z, bb[u].z))), y3 = gelu_erf(fmaf(rstd, hv[u].w, fmaf(-mr, w[u].w, bb[u].w)));
         *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
-        __stcg(reinterpret_cast<float4*>(a.h32 + (long long)r * 4 * d + n), make_float4(0.f, 0.f, 0.f, 0.f));
+        __stcg(reinterpret_cast<float4*>(a.h32 + bs_bidx(R, r, n)), make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }
@@ -837,13 +864,12 @@ __device__ __noinline__ void bs_final_ln_phase(const BStepArgs& a, float* red) {
   const int r = blockIdx.x, d = a.d, tid = threadIdx.x;
   if (r >= a.R) return;
   const int n4 = d >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)r * d);
   float4 v[2];
   float su = 0.f;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int idx = tid + i * kBsThreads;
-    v[i] = idx < n4 ? __ldcg(xr + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = idx < n4 ? __ldcg(reinterpret_cast<const float4*>(a.x + bs_bidx(a.R, r, idx * 4))) : make_float4(0.f, 0.f, 0.f, 0.f);
     su += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   su = warp_sum(su);
@@ -954,7 +980,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       sh.epoch = 0;
       sh.prof_i = 1;
       sh.acc_par[0] = sh.acc_par[1] = 0;
-      for (int i = 0; i < 6 * 8; ++i) sh.ticks[i] = 0;
+      for (int i = 0; i < 8 * 8; ++i) sh.ticks[i] = 0;
       for (int i = 0; i < kBsSlots; ++i) {
         mbar_init(&sh.wfull[i], 1);
         mbar_init(&sh.wempty[i], 1);
@@ -988,11 +1014,11 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       tok = tok < 0 ? 0 : (tok >= a.n_vocab ? a.n_vocab - 1 : tok);
       const int pos = sh.rows[r].pos;
       for (int i = threadIdx.x; i < d; i += kBsThreads)
-        __stcg(a.x + (long long)r * d + i, __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
+        __stcg(a.x + bs_bidx(a.R, r, i), __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
     }
-    bs_zero_f32(a.qkv32, (long long)a.R * 3 * a.d);
-    bs_zero_f32(a.cq32, (long long)a.R * a.d);
-    bs_zero_f32(a.h32, (long long)a.R * 4 * a.d);
+    bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));
+    bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));
+    bs_zero_f32(a.h32, bs_bsize(a.R, 4 * a.d));
     bs_zero_f32(a.stats, (long long)((3 * L * a.R * 2 + 3) & ~3));
     bool run = bs_enabled(a, ++phase);  // phase 0 done after the barrier; `phase` is the index of the next one
     bs_grid_barrier(a, sh);
@@ -1004,13 +1030,13 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
           case 0: bs_gemm_phase(a, sh, 6 * l + 0, U); break;
           case 1: bs_self_attn_phase(a, sh, l, U); break;
           case 2:
-            bs_zero_f32(a.qkv32, (long long)a.R * 3 * a.d);  // consumed by the self-attention of this layer
+            bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer
             bs_gemm_phase(a, sh, 6 * l + 1, U);
             break;
           case 3: bs_gemm_phase(a, sh, 6 * l + 2, U); break;
           case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
           case 5:
-            bs_zero_f32(a.cq32, (long long)a.R * a.d);  // consumed by the cross attention of this layer
+            bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer
             bs_gemm_phase(a, sh, 6 * l + 3, U);
             break;
           case 6: bs_gemm_phase(a, sh, 6 * l + 4, U); break;
@@ -1029,7 +1055,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
     if (run) bs_logits_phase(a, sh, kv0);
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
       a.prof[sh.prof_i] = ds_globaltimer();
-      for (int k = 0; k < 6; ++k)
+      for (int k = 0; k < 8; ++k)
         for (int p2 = 0; p2 < 8; ++p2) a.prof[3000 + k * 16 + (p2 == 7 ? 15 : p2)] += sh.ticks[k * 8 + p2];
     }
   }

@@ -687,15 +687,16 @@ constexpr int kMaxRows = 80;
 static void ensure_decoder_ws(Model* m, int chunks, int slots) {
   const int dt = m->cfg.n_text_state, L = m->cfg.n_text_layer, n_ctx = m->cfg.n_text_ctx;
   if (!m->d_x) {
-    m->d_x = dalloc<float>((size_t)kMaxRows * dt);
+    const size_t dt128 = (size_t)ceil_div(dt, 128) * 128;  // the many-row step kernel keeps its fp32 buffers n-block-major (128-channel blocks)
+    m->d_x = dalloc<float>((size_t)kMaxRows * dt128);
     m->d_xn = dalloc<__half>((size_t)kMaxRows * dt);
     m->d_q = dalloc<__half>((size_t)kMaxRows * dt);
     m->d_ao = dalloc<__half>((size_t)kMaxRows * dt);
     m->d_h = dalloc<__half>((size_t)kMaxRows * 4 * dt);
     m->d_logits = dalloc<float>((size_t)kMaxRows * m->vpad);
-    m->d_qkv32 = dalloc<float>((size_t)kMaxRows * 3 * dt);
-    m->d_cq32 = dalloc<float>((size_t)kMaxRows * dt);
-    m->d_h32 = dalloc<float>((size_t)kMaxRows * 4 * dt);
+    m->d_qkv32 = dalloc<float>((size_t)kMaxRows * ceil_div(3 * dt, 128) * 128);
+    m->d_cq32 = dalloc<float>((size_t)kMaxRows * dt128);
+    m->d_h32 = dalloc<float>((size_t)kMaxRows * ceil_div(4 * dt, 128) * 128);
     m->d_h16 = dalloc<__half>((size_t)kMaxRows * 4 * dt);
     m->d_xn16 = dalloc<__half>((size_t)kMaxRows * dt);
     m->d_stats = dalloc<float>((size_t)3 * L * kMaxRows * 2 + 4);
@@ -1238,9 +1239,16 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         fprintf(stderr, "[bstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
                 wait[ph] / L / 1e3, L);
       {
-        std::vector<unsigned long long> f(6 * 16);
+        std::vector<unsigned long long> f(8 * 16);
         B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
+        if (f[6 * 16 + 15] > 0)
+          fprintf(stderr, "[bstep prof]   self-attn cycles per 32-key block (CTA 0 warp 0): issue %.0f  copy-wait %.0f  compute %.0f; prologue per task total %.0f over %llu blocks\n",
+                  (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], (double)f[6 * 16 + 3] / f[6 * 16 + 15], (double)f[6 * 16],
+                  f[6 * 16 + 15]);
+        if (f[7 * 16 + 15] > 0)
+          fprintf(stderr, "[bstep prof]   cross-attn cycles per tile (CTA 0): tile-wait %.0f  compute %.0f; piece ends total %.0f over %llu tiles\n",
+                  (double)f[7 * 16] / f[7 * 16 + 15], (double)f[7 * 16 + 1] / f[7 * 16 + 15], (double)f[7 * 16 + 2], f[7 * 16 + 15]);
         static const char* kinds[6] = {"qkv", "out", "cross_q", "cross_out", "ffn1", "ffn2"};
         for (int k = 0; k < 6; ++k) {
           const double cnt = (double)f[k * 16 + 15];

@@ -120,6 +120,12 @@ def main():
     def rows(key):
         return np.stack([refs[r // K][key] for r in range(R)])
 
+    def fetch_blocked(which, n_cols):
+        """fp32 accumulate buffers are n-block-major: [(n >> 7)][row][n & 127]."""
+        nb = (n_cols + 127) // 128
+        raw = eng.debug_fetch(which, nb * R * 128).reshape(nb, R, 128)
+        return raw.transpose(1, 0, 2).reshape(R, nb * 128)[:, :n_cols]
+
     def fixed(raw, stats_slot, lname, wname, bname, stats):
         p_ln_g, p_ln_b = w64[lname + ".weight"], w64[lname + ".bias"]
         Ws = w64[wname] if isinstance(wname, str) else np.concatenate([w64[x] for x in wname])
@@ -138,25 +144,25 @@ def main():
         eng.generate(enc, [toks] * B, beam_size=K, max_length=len(toks) + 1, return_scores=True)
         st_raw = eng.debug_fetch(7, 3 * L * R * 2).reshape(3 * L, R, 2).astype(np.float64)
         if p == 1:
-            got, want, label = eng.debug_fetch(0, R * d).reshape(R, d), rows("embed"), "embed x"
+            got, want, label = fetch_blocked(0, d), rows("embed"), "embed x"
         elif p <= 1 + 9 * L:
             l, ph = divmod(p - 2, 9)
             blk = f"decoder.blocks.{l}"
             label = f"L{l} {names[ph]}"
             want = rows((l, ph))
             if ph == 0:
-                raw = eng.debug_fetch(1, R * 3 * d).reshape(R, 3 * d).astype(np.float64)
+                raw = fetch_blocked(1, 3 * d).astype(np.float64)
                 got = fixed(raw, 3 * l, blk + ".attn_ln", [blk + ".attn.query.weight", blk + ".attn.key.weight", blk + ".attn.value.weight"],
                             [blk + ".attn.query.bias", blk + ".attn.key.bias", blk + ".attn.value.bias"], st_raw)
             elif ph in (1, 4):
                 got = eng.debug_fetch(4, R * d).reshape(R, d)
             elif ph in (2, 5, 8):
-                got = eng.debug_fetch(0, R * d).reshape(R, d)
+                got = fetch_blocked(0, d)
             elif ph == 3:
-                raw = eng.debug_fetch(2, R * d).reshape(R, d).astype(np.float64)
+                raw = fetch_blocked(2, d).astype(np.float64)
                 got = fixed(raw, 3 * l + 1, blk + ".cross_attn_ln", blk + ".cross_attn.query.weight", blk + ".cross_attn.query.bias", st_raw)
             elif ph == 6:
-                raw = eng.debug_fetch(3, R * 4 * d).reshape(R, 4 * d).astype(np.float64)
+                raw = fetch_blocked(3, 4 * d).astype(np.float64)
                 got = fixed(raw, 3 * l + 2, blk + ".mlp_ln", blk + ".mlp.0.weight", blk + ".mlp.0.bias", st_raw)
             else:
                 got = eng.debug_fetch(5, R * 4 * d).reshape(R, 4 * d)
