@@ -40,11 +40,9 @@ constexpr int kBsWarps = 8;
 constexpr int kBsSlots = 5;       // weight-atom ring
 constexpr int kBsKvBytes = 2 * kDsXKeysMax * 64 * 2;  // one cross-attention K + V tile (57 344 B)
 constexpr int kBsXQ = 8;          // rows per chunk the cross-attention task handles
-constexpr int kBsScLd = kDsXKeysMax + 4;
-constexpr int kBsPLd = kDsXKeysMax + 8;
 constexpr int kBsQLd = 96;
 constexpr int kBsXGroups = 4;     // (chunk, head) groups one CTA's run of cross-attention tiles may touch
-constexpr int kBsXScratch = kBsXGroups * kBsXQ * kBsQLd * 2 + kBsXQ * kBsScLd * 4 + kBsXQ * kBsPLd * 2 + 2 * kBsXQ * 64 * 4 + 3 * kBsXQ * 4 + 32;
+constexpr int kBsXScratch = kBsXGroups * kBsXQ * kBsQLd * 2 + kBsWarps * kBsXQ * 66 * 4 + 64;  // queries + per-warp partials of a piece
 constexpr int kBsTmemCols = 256;  // two accumulators, 128 columns apart
 
 __host__ __device__ __forceinline__ int bs_ceil16(int v) { return (v + 15) & ~15; }
@@ -325,6 +323,7 @@ template <bool X>
 __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
   const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
   const int NP = a.NP, R = a.R, tid = threadIdx.x;
+  const int nblocks = (((s % 6) == 0 ? 3 * a.d : ((s % 6) == 4 ? 4 * a.d : a.d)) + 127) >> 7;
   const int per_atom = NP * 8, natoms = rg.a1 - rg.a0, total = natoms * per_atom;
   constexpr int UNR = 8;
 #pragma unroll 1
@@ -343,7 +342,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
         const int sg = i < rg.n(0) ? 0 : 1;
         const int ka = sg == 0 ? rg.ka0(0) + i : i - rg.n(0);
         dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
-        meta[u] = r | ((X && rg.nb(sg) == 0) ? 256 : 0);
+        meta[u] = r | ((X && rg.nb(sg) == ka % nblocks) ? 256 : 0);  // every k-atom is accounted once, the duty spread over the n-blocks
         if (r < R) {
           if constexpr (X) {
             const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
@@ -468,16 +467,16 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
 
 // Masked self-attention: one (row, head) task per warp.  q, k, v of the new token come from the raw QKV sums (deferred LayerNorm +
 // bias applied here); k and v are rounded to fp16 and written to the paged cache.  The history is gathered through the beam
-// ancestry table in blocks of 32 keys with an online softmax.  Per block ONE memory round trip and no data registers: lane j
-// copies the K and V rows of key j into the warp's shared-memory tile with cp.async (16 x 16 B); the K tile is XOR-swizzled so
-// that "lane = key" reads are conflict-free, the V tile is read "lane = 2 output dims".
-constexpr int kBsSelfTile = 2 * 32 * 64 * 2;  // K + V tile of one warp (8 KB)
+// ancestry table in blocks of 32 keys with an online softmax, ONE memory round trip per block and no shared-memory staging:
+//   * scores on mma.sync: the K rows are loaded straight from the cache as k-permuted 16-byte B fragments (thread (g, t) reads
+//     chunks t and 4 + t of key 8 n + g), the query is the A fragment (row 0 real), so lanes 0-3 end up with the 32 scores;
+//   * P V on the FMA pipe with "lane = 2 output dims": the 32 V rows of the block are 32 coalesced 4-byte loads per lane, issued
+//     together with the K loads; probabilities are broadcast with shuffles.
 __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
-  __half* kt = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [32 keys][64], 16-byte chunks at chunk ^ (key & 7)
-  __half* vt = kt + 32 * 64;                                               // [32 keys][64]
-  float* qs = reinterpret_cast<float*>(U + (size_t)kBsWarps * kBsSelfTile) + warp * 64;
+  __half* qs = reinterpret_cast<__half*>(U) + warp * 64;  // the task's query (fp16, pre-scaled by 1/8)
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
@@ -512,8 +511,8 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
                  bvv = __ldg(reinterpret_cast<const float2*>(bs + 2 * d));
     const float mr = mean * rstd;
 #define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
-    // q is rounded to fp16 like the other decode paths (they store q as fp16), then pre-scaled by 1/8
-    const __half2 q16 = __floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y));
+    // q is rounded to fp16 like the other decode paths (they store q as fp16); the 1/8 scale is exact in fp16
+    const __half2 q16 = __hmul2(__floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y)), __floats2half2_rn(0.125f, 0.125f));
     const __half2 k16 = __floats2half2_rn(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y));
     const __half2 v16 = __floats2half2_rn(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y));
 #undef BS_FIX
@@ -522,65 +521,81 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     const long long self_off = chunk_off + (long long)pos * pos_stride + ri.slot * d + e0;
     *reinterpret_cast<__half2*>(kc + self_off) = k16;
     *reinterpret_cast<__half2*>(vc + self_off) = v16;
-    *reinterpret_cast<float2*>(qs + e0) = make_float2(qf.x * 0.125f, qf.y * 0.125f);
-    float m_run = warp_sum(qf.x * 0.125f * kf.x + qf.y * 0.125f * kf.y);  // the new token's own key
+    __syncwarp();  // the previous task's fragment reads of qs are done
+    *reinterpret_cast<__half2*>(qs + e0) = q16;
+    float m_run = warp_sum(qf.x * kf.x + qf.y * kf.y);  // the new token's own key
     float l_run = 1.f;
     float2 acc = vf;
+    __syncwarp();
+    // A fragments of S = q K^T (k-permuted 16-byte chunks t and 4 + t); only accumulator row 0 is a real query
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = make_uint4(0u, 0u, 0u, 0u);
+    if (g == 0) {
+      qa = *reinterpret_cast<const uint4*>(qs + 8 * t);
+      qb = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
+    }
     const __half* kbase = kc + chunk_off;
-    const __half* vbase = vc + chunk_off;
+    const __half* vbase = vc + chunk_off + e0;
     BS_ATICK(6, 0, tp);
 #pragma unroll 1
     for (int blk = 0; blk * 32 < pos; ++blk) {
       const int bw = blk >> 2;
       const uint32_t word = bw == 0 ? slots[0] : (bw == 1 ? slots[1] : (bw == 2 ? slots[2] : slots[3]));
-      const int slot = (int)((word >> (8 * (blk & 3))) & 255u);
-      const int j = blk * 32 + lane;
-      const bool valid = j < pos;
-      const int nvalid = min(32, pos - blk * 32);
-      __syncwarp();  // the previous block's tile (and qs of a new task) is no longer being read
-      if (valid) {
-        const int off = j * pos_stride + slot * d;  // elements; < 2^31 for every supported shape
-        const __half* ks = kbase + off;
-        const __half* vs = vbase + off;
-        __half* kd = kt + lane * 64;
-        __half* vd = vt + lane * 64;
+      const int slot = (int)((word >> (8 * (blk & 3))) & 255u);  // slot of key blk * 32 + lane
+      const int j0 = blk * 32;
+      // ---- all loads of the block: 8 K fragments (16 B) + 32 V words (4 B) per lane ----
+      uint4 kf4[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          ds_cp_async16(kd + ((c ^ (lane & 7)) << 3), ks + c * 8);
-          ds_cp_async16(vd + (c << 3), vs + c * 8);
-        }
+      for (int nt = 0; nt < 4; ++nt) {
+        const int jj = j0 + 8 * nt + g;
+        const int sj = __shfl_sync(0xffffffffu, slot, 8 * nt + g);
+        const bool ok = jj < pos;
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (ok ? jj * pos_stride + sj * d : 0));
+        kf4[2 * nt] = ok ? __ldcg(kp + t) : make_uint4(0u, 0u, 0u, 0u);
+        kf4[2 * nt + 1] = ok ? __ldcg(kp + 4 + t) : make_uint4(0u, 0u, 0u, 0u);
       }
-      ds_cp_commit();
+      uint32_t vr[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int si = __shfl_sync(0xffffffffu, slot, i);
+        vr[i] = (j0 + i < pos) ? __ldcg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
+      }
       BS_ATICK(6, 1, tp);
-      ds_cp_wait_all();
-      __syncwarp();
-      BS_ATICK(6, 2, tp);
-      float s0 = 0.f, s1 = 0.f;
-      {
-        const uint4* kp = reinterpret_cast<const uint4*>(kt + lane * 64);
+      // ---- scores: row 0 of four m16n8 accumulators (keys j0 + 8 nt + 2 t, + 1 in lanes 0-3) ----
+      float sacc[4][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 kr = kp[c ^ (lane & 7)];
-          const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * c), qb = *reinterpret_cast<const float4*>(qs + 8 * c + 4);
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr.y)),
-                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr.w));
-          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
-          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
-        }
+      for (int nt = 0; nt < 4; ++nt) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+        ds_mma(sacc[nt], qa.x, 0u, qa.y, 0u, kf4[2 * nt].x, kf4[2 * nt].y);
+        ds_mma(sacc[nt], qa.z, 0u, qa.w, 0u, kf4[2 * nt].z, kf4[2 * nt].w);
+        ds_mma(sacc[nt], qb.x, 0u, qb.y, 0u, kf4[2 * nt + 1].x, kf4[2 * nt + 1].y);
+        ds_mma(sacc[nt], qb.z, 0u, qb.w, 0u, kf4[2 * nt + 1].z, kf4[2 * nt + 1].w);
       }
-      const float sv = valid ? s0 + s1 : -INFINITY;
-      const float m_new = fmaxf(m_run, warp_max(sv));
+      BS_ATICK(6, 2, tp);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        sacc[nt][0] = (g == 0 && j0 + 8 * nt + 2 * t < pos) ? sacc[nt][0] : -INFINITY;
+        sacc[nt][1] = (g == 0 && j0 + 8 * nt + 2 * t + 1 < pos) ? sacc[nt][1] : -INFINITY;
+        mx = fmaxf(mx, fmaxf(sacc[nt][0], sacc[nt][1]));
+      }
+      mx = warp_max(mx);
+      const float m_new = fmaxf(m_run, mx);
       const float alpha = __expf(m_run - m_new);
-      const float p = valid ? __expf(sv - m_new) : 0.f;
-      l_run = fmaf(l_run, alpha, warp_sum(p));
+      float ps = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        sacc[nt][0] = __expf(sacc[nt][0] - m_new);  // 0 for masked keys and for the lanes that hold no real score
+        sacc[nt][1] = __expf(sacc[nt][1] - m_new);
+        ps += sacc[nt][0] + sacc[nt][1];
+      }
+      l_run = fmaf(l_run, alpha, warp_sum(ps));
       acc.x *= alpha;
       acc.y *= alpha;
       m_run = m_new;
-      const __half2* vrow = reinterpret_cast<const __half2*>(vt) + lane;
-#pragma unroll 4
-      for (int i = 0; i < nvalid; ++i) {
-        const float pi = __shfl_sync(0xffffffffu, p, i);
-        const float2 vv2 = __half22float2(vrow[i * 32]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {  // key j0 + i: probability in lane (i & 7) >> 1, register sacc[i >> 3][i & 1]
+        const float pi = __shfl_sync(0xffffffffu, sacc[i >> 3][i & 1], (i & 7) >> 1);
+        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[i]));
         acc.x = fmaf(pi, vv2.x, acc.x);
         acc.y = fmaf(pi, vv2.y, acc.y);
       }
@@ -616,15 +631,10 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
   const unsigned NT = (unsigned)(S * a.H * a.n_chunks);
   unsigned char* kv1 = U;
   unsigned char* scratch = U + kBsKvBytes;
-  __half* qs_all = reinterpret_cast<__half*>(scratch);                       // [kBsXGroups][8][96], pre-scaled by 1/8
-  float* sc = reinterpret_cast<float*>(qs_all + kBsXGroups * kBsXQ * kBsQLd);  // [8][kBsScLd]
-  __half* pr = reinterpret_cast<__half*>(sc + kBsXQ * kBsScLd);               // [8][kBsPLd]
-  float* wred = reinterpret_cast<float*>(pr + kBsXQ * kBsPLd);                // [2][8][64]
-  float* mrun = wred + 2 * kBsXQ * 64;                                        // [8]
-  float* lrun = mrun + kBsXQ;                                                 // [8]
-  float* alpha = lrun + kBsXQ;                                                // [8]
+  __half* qs_all = reinterpret_cast<__half*>(scratch);                          // [kBsXGroups][8][96], pre-scaled by 1/8
+  float* mb = reinterpret_cast<float*>(qs_all + kBsXGroups * kBsXQ * kBsQLd);  // [8 warps][8 queries][64 + m + l]
   const BLayer& lay = sh.lay[l];
-  if (tid == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now
+  if (lane == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now (one arrival per warp)
   // ---- queries of every group this run touches, in one round trip (deferred LayerNorm + bias, fp16 rounding, then the exact 1/8) ----
   const int g_first = t0 / S, n_groups = (t1 - 1) / S - g_first + 1;
   for (int idx = tid; idx < n_groups * 64; idx += kBsThreads) {
@@ -653,130 +663,132 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     }
     *reinterpret_cast<uint4*>(qs_all + (gi * kBsXQ + q) * kBsQLd + c * 8) = v;
   }
-  for (int i = tid; i < kBsXQ * kBsPLd; i += kBsThreads) pr[i] = __float2half_rn(0.f);  // rows >= nq stay zero for the whole phase
-  const int dtile = warp & 3, khalf = warp >> 2;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int piece_first = 0;  // split index of the first tile of the current piece
+  bs_sync();
+  // per-thread state of the current piece: query row g (the accumulator rows g + 8 are padding), this warp's share of the keys
+  float m_run = -INFINITY, l_run = 0.f;
+  float oacc[8][4];
+  uint4 qf0 = make_uint4(0u, 0u, 0u, 0u), qf1 = make_uint4(0u, 0u, 0u, 0u);
+  int piece_first = 0;
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
     const int tile = t0 + k, grp = tile / S, split = tile - grp * S, gi = grp - g_first;
-    const int h = grp % a.H, b = grp / a.H, row0 = b * nq;
     const int buf = k & 1;
     unsigned char* kvbuf = buf ? kv1 : kv0;
     const int u = l * (buf ? n_odd : n_even) + (k >> 1);
     const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
-    const int nkp = (nk + 15) & ~15;
-    __half* kt = reinterpret_cast<__half*>(kvbuf);  // [224][64] swizzled
-    __half* vt = kt + kDsXKeysMax * 64;
-    const __half* qs = qs_all + gi * kBsXQ * kBsQLd;
-    if (k == 0 || split == 0) {  // a new piece starts: reset the running softmax state
+    const __half* kt = reinterpret_cast<const __half*>(kvbuf);  // [224][64], 16-byte chunks at chunk ^ (encoder position & 7)
+    __half* vt = reinterpret_cast<__half*>(kvbuf) + kDsXKeysMax * 64;
+    if (k == 0 || split == 0) {  // a new piece starts
       piece_first = split;
-      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-      if (tid < kBsXQ) {
-        mrun[tid] = -INFINITY;
-        lrun[tid] = 0.f;
-      }
+      m_run = -INFINITY;
+      l_run = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+      const __half* qs = qs_all + (gi * kBsXQ + g) * kBsQLd;  // k-permuted A fragments: 16-byte chunk 4 c2 + t of query row g
+      qf0 = *reinterpret_cast<const uint4*>(qs + 8 * t);
+      qf1 = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
     }
     long long tp = clock64();
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
     BS_ATICK(7, 0, tp);
-    // rows [nk, nkp) of V are multiplied by zero probabilities: make them finite (the TMA never writes them)
-    for (int i = tid; i < (nkp - nk) * 8; i += kBsThreads) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
-    bs_sync();
-    // ---- scores ----
+    const int ngroups16 = (nk + 15) >> 4;
 #pragma unroll 1
-    for (int kt16 = warp; kt16 * 16 < nkp; kt16 += kBsWarps) {
-      const int rg = kt16 * 16 + g, swz = (k0 + rg) & 7;  // rows rg and rg + 8 share the swizzle
-      float sa[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int pc = ((4 * c2 + t) ^ swz) << 3;
-        const uint4 wa = *reinterpret_cast<const uint4*>(kt + rg * 64 + pc);
-        const uint4 wb = *reinterpret_cast<const uint4*>(kt + (rg + 8) * 64 + pc);
-        const uint4 xv = *reinterpret_cast<const uint4*>(qs + g * kBsQLd + 32 * c2 + 8 * t);
-        ds_mma(sa, wa.x, wb.x, wa.y, wb.y, xv.x, xv.y);
-        ds_mma(sa, wa.z, wb.z, wa.w, wb.w, xv.z, xv.w);
+    for (int g16 = warp; g16 < ngroups16; g16 += kBsWarps) {
+      const int kb = g16 * 16;
+      if (kb + 16 > nk) {  // the tail rows of V are multiplied by zero probabilities: make them finite (the TMA never writes them)
+        for (int i = lane; i < (kb + 16 - nk) * 8; i += 32) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
       }
-      sc[(2 * t) * kBsScLd + rg] = sa[0];
-      sc[(2 * t + 1) * kBsScLd + rg] = sa[1];
-      sc[(2 * t) * kBsScLd + rg + 8] = sa[2];
-      sc[(2 * t + 1) * kBsScLd + rg + 8] = sa[3];
-    }
-    bs_sync();
-    {  // one warp per query: online-softmax update, probabilities as fp16
-      const int q = warp;
-      if (q < nq) {
-        float mx = -INFINITY;
-        for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, sc[q * kBsScLd + j]);
-        mx = warp_max(mx);
-        const float m_old = mrun[q], m_new = fmaxf(m_old, mx);
-        float sum = 0.f;
-        for (int j = lane; j < nkp; j += 32) {
-          const float pv = j < nk ? __expf(sc[q * kBsScLd + j] - m_new) : 0.f;
-          const __half ph = __float2half_rn(pv);
-          pr[q * kBsPLd + j] = ph;
-          sum += __half2float(ph);
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) {
-          const float al = (m_old == -INFINITY) ? 0.f : __expf(m_old - m_new);
-          mrun[q] = m_new;
-          lrun[q] = fmaf(lrun[q], al, sum);
-          alpha[q] = al;
-        }
-      } else if (lane == 0) {
-        alpha[q] = 1.f;
+      // ---- S = Q K^T for 16 keys: rows = queries (g), columns = keys (two n8 tiles); 16-byte k-permuted fragments ----
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int key0 = kb + g, key1 = kb + 8 + g;
+        const int sw0 = (k0 + key0) & 7, sw1 = (k0 + key1) & 7;
+        const uint4 ka = *reinterpret_cast<const uint4*>(kt + key0 * 64 + ((t ^ sw0) << 3));
+        const uint4 kb4 = *reinterpret_cast<const uint4*>(kt + key0 * 64 + (((4 + t) ^ sw0) << 3));
+        const uint4 kc4 = *reinterpret_cast<const uint4*>(kt + key1 * 64 + ((t ^ sw1) << 3));
+        const uint4 kd = *reinterpret_cast<const uint4*>(kt + key1 * 64 + (((4 + t) ^ sw1) << 3));
+        ds_mma(s0, qf0.x, 0u, qf0.y, 0u, ka.x, ka.y);
+        ds_mma(s0, qf0.z, 0u, qf0.w, 0u, ka.z, ka.w);
+        ds_mma(s0, qf1.x, 0u, qf1.y, 0u, kb4.x, kb4.y);
+        ds_mma(s0, qf1.z, 0u, qf1.w, 0u, kb4.z, kb4.w);
+        ds_mma(s1, qf0.x, 0u, qf0.y, 0u, kc4.x, kc4.y);
+        ds_mma(s1, qf0.z, 0u, qf0.w, 0u, kc4.z, kc4.w);
+        ds_mma(s1, qf1.x, 0u, qf1.y, 0u, kd.x, kd.y);
+        ds_mma(s1, qf1.z, 0u, qf1.w, 0u, kd.z, kd.w);
       }
-    }
-    bs_sync();
-    {  // ---- O^T (+)= V^T P^T: warp -> (16 output dims, half of the key tiles); accumulators rescaled by the softmax update ----
+      // thread (g, t): query g, keys kb + 2t, kb + 2t + 1 (s0[0..1]) and kb + 8 + 2t, + 1 (s1[0..1])
+      const float v00 = (kb + 2 * t < nk) ? s0[0] : -INFINITY, v01 = (kb + 2 * t + 1 < nk) ? s0[1] : -INFINITY;
+      const float v10 = (kb + 8 + 2 * t < nk) ? s1[0] : -INFINITY, v11 = (kb + 9 + 2 * t < nk) ? s1[1] : -INFINITY;
+      float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = __expf(m_run - m_new);  // 0 for the first keys of a piece (m_run = -inf, m_new finite: every group holds a real key)
+      const __half2 p0 = __floats2half2_rn(__expf(v00 - m_new), __expf(v01 - m_new)), p1 = __floats2half2_rn(__expf(v10 - m_new), __expf(v11 - m_new));
+      const float2 pf0 = __half22float2(p0), pf1 = __half22float2(p1);
+      float ps = (pf0.x + pf0.y) + (pf1.x + pf1.y);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      l_run = fmaf(l_run, alpha, ps);
+      m_run = m_new;
+      const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(&p0), pa2 = *reinterpret_cast<const uint32_t*>(&p1);
+      // ---- O (+)= P V: A = P (rows = queries, 16 keys), B = V via ldmatrix.trans (keys x 8 dims per tile) ----
       const int mi = lane >> 3, r8 = lane & 7;
-      const float al0 = alpha[2 * t], al1 = alpha[2 * t + 1];
-      acc[0] *= al0;
-      acc[1] *= al1;
-      acc[2] *= al0;
-      acc[3] *= al1;
-#pragma unroll 1
-      for (int kt16 = khalf; kt16 * 16 < nkp; kt16 += 2) {
-        const int row = kt16 * 16 + 8 * (mi >> 1) + r8;
-        const int pc = ((2 * dtile + (mi & 1)) ^ ((k0 + row) & 7)) << 3;
-        uint32_t a0, a1, a2, a3;
-        ds_ldmatrix_x4_trans(a0, a1, a2, a3, vt + row * 64 + pc);
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + kt16 * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(pr + g * kBsPLd + kt16 * 16 + 2 * t + 8);
-        ds_mma(acc, a0, a1, a2, a3, b0, b1);
+      const int vkey = kb + 8 * (mi & 1) + r8, vsw = (k0 + vkey) & 7;
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ds_ldmatrix_x4_trans(b0, b1, b2, b3, vt + vkey * 64 + (((2 * dp + (mi >> 1)) ^ vsw) << 3));
+        oacc[2 * dp][0] *= alpha;
+        oacc[2 * dp][1] *= alpha;
+        oacc[2 * dp + 1][0] *= alpha;
+        oacc[2 * dp + 1][1] *= alpha;
+        ds_mma(oacc[2 * dp], pa0, 0u, pa2, 0u, b0, b1);
+        ds_mma(oacc[2 * dp + 1], pa0, 0u, pa2, 0u, b2, b3);
       }
     }
     const bool piece_ends = (k == nt - 1 || split == S - 1);
-    if (piece_ends) {
-      float* w = wred + khalf * (kBsXQ * 64);
-      w[(2 * t) * 64 + 16 * dtile + g] = acc[0];
-      w[(2 * t + 1) * 64 + 16 * dtile + g] = acc[1];
-      w[(2 * t) * 64 + 16 * dtile + g + 8] = acc[2];
-      w[(2 * t + 1) * 64 + 16 * dtile + g + 8] = acc[3];
+    if (piece_ends) {  // this warp's partial of the piece: accumulators relative to its own running max
+      float* w = mb + (warp * kBsXQ + g) * 66;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(w + 8 * dt + 2 * t) = make_float2(oacc[dt][0], oacc[dt][1]);
+      if (t == 0) {
+        w[64] = m_run;
+        w[65] = l_run;
+      }
     }
-    bs_sync();  // the K/V tile is dead from here on
-    // release the tile: buffer 0 always (the producer may fetch the next layer's first tile), buffer 1 only for another tile of this phase
-    if (tid == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+    // release the tile (one arrival per warp): buffer 0 always, buffer 1 only when another tile of this phase will use it
+    __syncwarp();
+    if (lane == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
     BS_ATICK(7, 1, tp);
     if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[7 * 8 + 7] += 1;
     if (!piece_ends) continue;
+    bs_sync();
+    const int h = grp % a.H, b = grp / a.H, row0 = b * nq;
     const int n_piece = split - piece_first + 1;
-    if (n_piece == S) {  // the whole group was handled here: normalise and write
-      for (int i = tid; i < nq * 64; i += kBsThreads) {
-        const int q = i >> 6, e = i & 63;
-        a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn((wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]) / lrun[q]);
+    float* part = a.xpart + ((long long)grp * S + piece_first) * (kBsXQ * 66);
+    // merge the eight warps' partials (flash-decoding combine); a whole group goes straight to `ao`, a cut one leaves a record
+    for (int i = tid; i < nq * 66; i += kBsThreads) {
+      const int q = i / 66, e = i - q * 66;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w8 = 0; w8 < kBsWarps; ++w8) M = fmaxf(M, mb[(w8 * kBsXQ + q) * 66 + 64]);
+      float den = 0.f, num = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < kBsWarps; ++w8) {
+        const float* wrow = mb + (w8 * kBsXQ + q) * 66;
+        const float wgt = (wrow[64] == -INFINITY) ? 0.f : __expf(wrow[64] - M);
+        den = fmaf(wgt, wrow[65], den);
+        num = fmaf(wgt, wrow[e < 64 ? e : 0], num);
       }
-    } else {
-      float* part = a.xpart + ((long long)grp * S + piece_first) * (kBsXQ * 66);
-      for (int i = tid; i < nq * 64; i += kBsThreads) {
-        const int q = i >> 6, e = i & 63;
-        __stcg(part + q * 66 + e, wred[q * 64 + e] + wred[(kBsXQ + q) * 64 + e]);
+      if (n_piece == S) {
+        if (e < 64) a.ao[(long long)(row0 + q) * d + h * 64 + e] = __float2half_rn(num / den);
+      } else {
+        __stcg(part + q * 66 + e, e < 64 ? num : (e == 64 ? M : den));
       }
-      if (tid < nq) {
-        __stcg(part + tid * 66 + 64, mrun[tid]);
-        __stcg(part + tid * 66 + 65, lrun[tid]);
-      }
+    }
+    if (n_piece != S) {
       bs_sync();
       if (tid == 0) {
         int ticket;
@@ -815,7 +827,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
         }
       }
     }
-    bs_sync();  // wred / running statistics are reused by the next piece
+    bs_sync();  // the per-warp partials are reused by the next piece
     BS_ATICK(7, 2, tp);
   }
 }
@@ -990,7 +1002,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
         mbar_init(&sh.acc_full[i], 1);
         mbar_init(&sh.acc_empty[i], 1);
         mbar_init(&sh.kvfull[i], 1);
-        mbar_init(&sh.kvfree[i], 1);
+        mbar_init(&sh.kvfree[i], kBsWarps);  // every compute warp releases a K/V buffer on its own
       }
       fence_mbar_init();
       if (a.prof && blockIdx.x == 0) a.prof[0] = ds_globaltimer();
@@ -1145,7 +1157,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
   u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
-  u = std::max(u, (size_t)kBsWarps * (kBsSelfTile + 64 * 4));                                // self-attention: K/V tile + query per warp
+  u = std::max(u, (size_t)kBsWarps * 64 * 2);                                                // self-attention: one fp16 query per warp
   a.u_bytes = (int)((u + 1023) & ~size_t(1023));
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
