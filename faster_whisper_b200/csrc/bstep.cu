@@ -319,68 +319,95 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
 //   X == true : source = fp32 residual stream (converted raw; the LayerNorm is applied by the consumer of the GEMM output);
 //               segments of n-block 0 also accumulate sum(x), sum(x^2) of their K slice into `st`
 //   X == false: source = fp16 activations [R][ld]
+constexpr int kBsStageUnr = 4;
+template <bool X>
+struct BsStageSet {  // one batch of staging chunks in flight (registers)
+  uint4 v0[kBsStageUnr], v1[X ? kBsStageUnr : 1];
+  int dst[kBsStageUnr], meta[kBsStageUnr];  // meta: row | (LayerNorm-statistics duty << 8)
+};
+
+template <bool X>
+__device__ __forceinline__ void bs_stage_load(BsStageSet<X>& S, const BStepArgs& a, const BsRange& rg, int nblocks, const void* src, int ld, int base, int total) {
+  const int NP = a.NP, R = a.R, per_atom = NP * 8;
+#pragma unroll
+  for (int u = 0; u < kBsStageUnr; ++u) {
+    const int q = base + u * kBsThreads;
+    S.dst[u] = -1;
+    S.meta[u] = 0;
+    S.v0[u] = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (X) S.v1[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (q < total) {
+      const int i = q / per_atom, rem = q - i * per_atom, r = rem >> 3, c = rem & 7;
+      const int sg = i < rg.n(0) ? 0 : 1;
+      const int ka = sg == 0 ? rg.ka0(0) + i : i - rg.n(0);
+      S.dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
+      S.meta[u] = r | ((X && rg.nb(sg) == ka % nblocks) ? 256 : 0);  // every k-atom is accounted once, the duty spread over the n-blocks
+      if (r < R) {
+        if constexpr (X) {
+          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
+          const float4 f0 = __ldcg(p), f1 = __ldcg(p + 1);
+          S.v0[u] = *reinterpret_cast<const uint4*>(&f0);
+          S.v1[u] = *reinterpret_cast<const uint4*>(&f1);
+        } else {
+          S.v0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
+        }
+      }
+    }
+  }
+}
+
+template <bool X>
+__device__ __forceinline__ void bs_stage_store(const BsStageSet<X>& S, const BStepArgs& a, float* st, unsigned char* xs) {
+  const int R = a.R, tid = threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kBsStageUnr; ++u) {
+    if constexpr (X) {
+      const float4 f0 = *reinterpret_cast<const float4*>(&S.v0[u]), f1 = *reinterpret_cast<const float4*>(&S.v1[u]);
+      if (__any_sync(0xffffffffu, S.meta[u] & 256)) {
+        float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
+        float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
+        // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+        const int r = S.meta[u] & 255;
+        if ((S.meta[u] & 256) && (tid & 7) == 0 && r < R && S.dst[u] >= 0) {
+          atomicAdd(st + 2 * r, s1);
+          atomicAdd(st + 2 * r + 1, s2);
+        }
+      }
+      if (S.dst[u] >= 0)
+        *reinterpret_cast<uint4*>(xs + S.dst[u]) = make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
+    } else {
+      if (S.dst[u] >= 0) *reinterpret_cast<uint4*>(xs + S.dst[u]) = S.v0[u];
+    }
+  }
+}
+
+// Stage this CTA's activation slices as UMMA B tiles: tile i = [NP rows][64 K values] fp16, 128-byte swizzle, rows >= R zero.
+//   X == true : source = fp32 residual stream, n-block-major (converted raw; the LayerNorm is applied by the consumer of the GEMM
+//               output); sum(x), sum(x^2) of every K slice are accumulated into `st` by exactly one of the CTAs that stage it
+//   X == false: source = fp16 activations [R][ld]
+// Software-pipelined: the loads of batch b + 1 are in flight while batch b is converted and stored (a post-barrier L2 read costs
+// ~2 500 cycles here, so a phase must not pay it once per batch).
 template <bool X>
 __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
   const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
-  const int NP = a.NP, R = a.R, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int nblocks = (((s % 6) == 0 ? 3 * a.d : ((s % 6) == 4 ? 4 * a.d : a.d)) + 127) >> 7;
-  const int per_atom = NP * 8, natoms = rg.a1 - rg.a0, total = natoms * per_atom;
-  constexpr int UNR = 8;
+  const int total = (rg.a1 - rg.a0) * a.NP * 8;
+  constexpr int STEP = kBsThreads * kBsStageUnr;
+  BsStageSet<X> A, B;
+  bs_stage_load<X>(A, a, rg, nblocks, src, ld, tid, total);
 #pragma unroll 1
-  for (int base = tid; base < total; base += kBsThreads * UNR) {
-    uint4 v0[UNR], v1[X ? UNR : 1];
-    int dst[UNR], meta[UNR];  // meta: row | (stats << 8)
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int q = base + u * kBsThreads;
-      dst[u] = -1;
-      meta[u] = 0;
-      v0[u] = make_uint4(0u, 0u, 0u, 0u);
-      if constexpr (X) v1[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (q < total) {
-        const int i = q / per_atom, rem = q - i * per_atom, r = rem >> 3, c = rem & 7;
-        const int sg = i < rg.n(0) ? 0 : 1;
-        const int ka = sg == 0 ? rg.ka0(0) + i : i - rg.n(0);
-        dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
-        meta[u] = r | ((X && rg.nb(sg) == ka % nblocks) ? 256 : 0);  // every k-atom is accounted once, the duty spread over the n-blocks
-        if (r < R) {
-          if constexpr (X) {
-            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
-            const float4 f0 = __ldcg(p), f1 = __ldcg(p + 1);
-            v0[u] = *reinterpret_cast<const uint4*>(&f0);
-            v1[u] = *reinterpret_cast<const uint4*>(&f1);
-          } else {
-            v0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if constexpr (X) {
-        const float4 f0 = *reinterpret_cast<const float4*>(&v0[u]), f1 = *reinterpret_cast<const float4*>(&v1[u]);
-        if (__any_sync(0xffffffffu, meta[u] & 256)) {  // only the segments of n-block 0 contribute LayerNorm statistics
-          float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
-          float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
-          // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-          const int r = meta[u] & 255;
-          if ((meta[u] & 256) && (tid & 7) == 0 && r < R && dst[u] >= 0) {
-            atomicAdd(st + 2 * r, s1);
-            atomicAdd(st + 2 * r + 1, s2);
-          }
-        }
-        if (dst[u] >= 0)
-          *reinterpret_cast<uint4*>(xs + dst[u]) = make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
-      } else {
-        if (dst[u] >= 0) *reinterpret_cast<uint4*>(xs + dst[u]) = v0[u];
-      }
-    }
+  for (int base = tid; base < total; base += 2 * STEP) {
+    bs_stage_load<X>(B, a, rg, nblocks, src, ld, base + STEP, total);
+    bs_stage_store<X>(A, a, st, xs);
+    bs_stage_load<X>(A, a, rg, nblocks, src, ld, base + 2 * STEP, total);
+    bs_stage_store<X>(B, a, st, xs);
   }
 }
 
@@ -495,7 +522,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
 #pragma unroll
     for (int i = 0; i < 14; ++i) {
       const int jj = 32 * i + lane;
-      const uint32_t sv = (jj < pos) ? (uint32_t)anc[jj] : 0u;
+      const uint32_t sv = (jj < pos) ? (uint32_t)__ldg(anc + jj) : 0u;
       slots[i >> 2] |= sv << (8 * (i & 3));
     }
     float mean, rstd;
@@ -550,14 +577,15 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
         const int sj = __shfl_sync(0xffffffffu, slot, 8 * nt + g);
         const bool ok = jj < pos;
         const uint4* kp = reinterpret_cast<const uint4*>(kbase + (ok ? jj * pos_stride + sj * d : 0));
-        kf4[2 * nt] = ok ? __ldcg(kp + t) : make_uint4(0u, 0u, 0u, 0u);
-        kf4[2 * nt + 1] = ok ? __ldcg(kp + 4 + t) : make_uint4(0u, 0u, 0u, 0u);
+        // history rows were written by earlier launches (this launch only writes position `pos`): the read-only path is safe
+        kf4[2 * nt] = ok ? __ldg(kp + t) : make_uint4(0u, 0u, 0u, 0u);
+        kf4[2 * nt + 1] = ok ? __ldg(kp + 4 + t) : make_uint4(0u, 0u, 0u, 0u);
       }
       uint32_t vr[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int si = __shfl_sync(0xffffffffu, slot, i);
-        vr[i] = (j0 + i < pos) ? __ldcg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
+        vr[i] = (j0 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
       }
       BS_ATICK(6, 1, tp);
       // ---- scores: row 0 of four m16n8 accumulators (keys j0 + 8 nt + 2 t, + 1 in lanes 0-3) ----
