@@ -140,7 +140,7 @@ __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
 }
 
 // Grid barrier (compute warps only): arrive = red.release (cumulative through bar.sync), wait = relaxed polling.
-__device__ __forceinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
+__device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
   bs_sync();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
@@ -296,7 +296,9 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
 }
 
 // ---- compute-warp phase functions ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bs_zero_f32(float* p, long long n) {  // all compute threads of all CTAs, n % 4 == 0
+// (all out of line: the phase loop of the kernel body must not spill — with 220 KB of shared memory the L1 is ~28 KB and local
+// memory lives in L2 for all practical purposes)
+__device__ __noinline__ void bs_zero_f32(float* p, long long n) {  // all compute threads of all CTAs, n % 4 == 0
   float4* p4 = reinterpret_cast<float4*>(p);
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * kBsThreads + threadIdx.x; i < n4; i += (long long)gridDim.x * kBsThreads)
@@ -309,6 +311,22 @@ __device__ __forceinline__ void bs_zero_f32(float* p, long long n) {  // all com
 __device__ __forceinline__ long long bs_bidx(int R, int r, int n) { return ((long long)(n >> 7) * R + r) * 128 + (n & 127); }
 __host__ __device__ __forceinline__ long long bs_bsize(int R, int N) { return (long long)((N + 127) >> 7) * R * 128; }
 
+// embed: x = tok_emb[token] + pos_emb[pos] (CTA r owns row r); zero the split-K accumulators and the LayerNorm statistics
+__device__ __noinline__ void bs_embed_phase(const BStepArgs& a, BsShared& sh) {
+  if ((int)blockIdx.x < a.R) {
+    const int r = blockIdx.x, d = a.d;
+    int tok = a.tokens_in[r];
+    tok = tok < 0 ? 0 : (tok >= a.n_vocab ? a.n_vocab - 1 : tok);
+    const int pos = sh.rows[r].pos;
+    for (int i = threadIdx.x; i < d; i += kBsThreads)
+      __stcg(a.x + bs_bidx(a.R, r, i), __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
+  }
+  bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));
+  bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));
+  bs_zero_f32(a.h32, bs_bsize(a.R, 4 * a.d));
+  bs_zero_f32(a.stats, (long long)((3 * a.L * a.R * 2 + 3) & ~3));
+}
+
 __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, float& mean, float& rstd) {
   const float2 s = __ldcg(reinterpret_cast<const float2*>(st) + r);
   mean = s.x / d;
@@ -319,95 +337,81 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
 //   X == true : source = fp32 residual stream (converted raw; the LayerNorm is applied by the consumer of the GEMM output);
 //               segments of n-block 0 also accumulate sum(x), sum(x^2) of their K slice into `st`
 //   X == false: source = fp16 activations [R][ld]
-constexpr int kBsStageUnr = 4;
-template <bool X>
-struct BsStageSet {  // one batch of staging chunks in flight (registers)
-  uint4 v0[kBsStageUnr], v1[X ? kBsStageUnr : 1];
-  int dst[kBsStageUnr], meta[kBsStageUnr];  // meta: row | (LayerNorm-statistics duty << 8)
-};
-
-template <bool X>
-__device__ __forceinline__ void bs_stage_load(BsStageSet<X>& S, const BStepArgs& a, const BsRange& rg, int nblocks, const void* src, int ld, int base, int total) {
-  const int NP = a.NP, R = a.R, per_atom = NP * 8;
-#pragma unroll
-  for (int u = 0; u < kBsStageUnr; ++u) {
-    const int q = base + u * kBsThreads;
-    S.dst[u] = -1;
-    S.meta[u] = 0;
-    S.v0[u] = make_uint4(0u, 0u, 0u, 0u);
-    if constexpr (X) S.v1[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (q < total) {
-      const int i = q / per_atom, rem = q - i * per_atom, r = rem >> 3, c = rem & 7;
-      const int sg = i < rg.n(0) ? 0 : 1;
-      const int ka = sg == 0 ? rg.ka0(0) + i : i - rg.n(0);
-      S.dst[u] = i * (NP * 128) + r * 128 + ((c ^ (r & 7)) << 4);
-      S.meta[u] = r | ((X && rg.nb(sg) == ka % nblocks) ? 256 : 0);  // every k-atom is accounted once, the duty spread over the n-blocks
-      if (r < R) {
-        if constexpr (X) {
-          const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
-          const float4 f0 = __ldcg(p), f1 = __ldcg(p + 1);
-          S.v0[u] = *reinterpret_cast<const uint4*>(&f0);
-          S.v1[u] = *reinterpret_cast<const uint4*>(&f1);
-        } else {
-          S.v0[u] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
-        }
-      }
-    }
-  }
-}
-
-template <bool X>
-__device__ __forceinline__ void bs_stage_store(const BsStageSet<X>& S, const BStepArgs& a, float* st, unsigned char* xs) {
-  const int R = a.R, tid = threadIdx.x;
-#pragma unroll
-  for (int u = 0; u < kBsStageUnr; ++u) {
-    if constexpr (X) {
-      const float4 f0 = *reinterpret_cast<const float4*>(&S.v0[u]), f1 = *reinterpret_cast<const float4*>(&S.v1[u]);
-      if (__any_sync(0xffffffffu, S.meta[u] & 256)) {
-        float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
-        float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
-        // the eight 16-byte chunks of a (tile, row) sit in eight consecutive lanes
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-        const int r = S.meta[u] & 255;
-        if ((S.meta[u] & 256) && (tid & 7) == 0 && r < R && S.dst[u] >= 0) {
-          atomicAdd(st + 2 * r, s1);
-          atomicAdd(st + 2 * r + 1, s2);
-        }
-      }
-      if (S.dst[u] >= 0)
-        *reinterpret_cast<uint4*>(xs + S.dst[u]) = make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
-    } else {
-      if (S.dst[u] >= 0) *reinterpret_cast<uint4*>(xs + S.dst[u]) = S.v0[u];
-    }
-  }
-}
-
 // Stage this CTA's activation slices as UMMA B tiles: tile i = [NP rows][64 K values] fp16, 128-byte swizzle, rows >= R zero.
 //   X == true : source = fp32 residual stream, n-block-major (converted raw; the LayerNorm is applied by the consumer of the GEMM
 //               output); sum(x), sum(x^2) of every K slice are accumulated into `st` by exactly one of the CTAs that stage it
 //   X == false: source = fp16 activations [R][ld]
-// Software-pipelined: the loads of batch b + 1 are in flight while batch b is converted and stored (a post-barrier L2 read costs
-// ~2 500 cycles here, so a phase must not pay it once per batch).
+// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); two tiles (<= 6 chunks per thread)
+// are in flight together.
 template <bool X>
 __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
   const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, NP = a.NP, R = a.R;
   const int nblocks = (((s % 6) == 0 ? 3 * a.d : ((s % 6) == 4 ? 4 * a.d : a.d)) + 127) >> 7;
-  const int total = (rg.a1 - rg.a0) * a.NP * 8;
-  constexpr int STEP = kBsThreads * kBsStageUnr;
-  BsStageSet<X> A, B;
-  bs_stage_load<X>(A, a, rg, nblocks, src, ld, tid, total);
+  const int natoms = rg.a1 - rg.a0;
+  const int c = tid & 7, r_lo = tid >> 3;
+  constexpr int PASSES = 3;  // 96 rows >= NP (<= 80)
 #pragma unroll 1
-  for (int base = tid; base < total; base += 2 * STEP) {
-    bs_stage_load<X>(B, a, rg, nblocks, src, ld, base + STEP, total);
-    bs_stage_store<X>(A, a, st, xs);
-    bs_stage_load<X>(A, a, rg, nblocks, src, ld, base + 2 * STEP, total);
-    bs_stage_store<X>(B, a, st, xs);
+  for (int i0 = 0; i0 < natoms; i0 += 2) {
+    uint4 v0[2][PASSES], v1[X ? 2 : 1][X ? PASSES : 1];
+    int duty[2];
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = i0 + ii;
+      const bool on = i < natoms;
+      const int sg = i < rg.n0 ? 0 : 1;
+      const int ka = sg == 0 ? rg.ka00 + i : i - rg.n0;
+      duty[ii] = (X && on && rg.nb(sg) == ka % nblocks) ? 1 : 0;  // every k-atom is accounted once, the duty spread over the n-blocks
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        const int r = r_lo + 32 * p;
+        v0[ii][p] = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (X) v1[ii][p] = make_uint4(0u, 0u, 0u, 0u);
+        if (on && r < R) {
+          if constexpr (X) {
+            const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
+            const float4 f0 = __ldcg(ptr), f1 = __ldcg(ptr + 1);
+            v0[ii][p] = *reinterpret_cast<const uint4*>(&f0);
+            v1[ii][p] = *reinterpret_cast<const uint4*>(&f1);
+          } else {
+            v0[ii][p] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii) {
+      const int i = i0 + ii;
+      if (i >= natoms) break;
+      unsigned char* tile = xs + (size_t)i * (NP * 128);
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        const int r = r_lo + 32 * p;
+        if constexpr (X) {
+          const float4 f0 = *reinterpret_cast<const float4*>(&v0[ii][p]), f1 = *reinterpret_cast<const float4*>(&v1[ii][p]);
+          if (duty[ii]) {  // uniform over the CTA
+            float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
+            float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
+            // the eight 16-byte chunks of a row sit in eight consecutive lanes
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+            if (c == 0 && r < R) {
+              atomicAdd(st + 2 * r, s1);
+              atomicAdd(st + 2 * r + 1, s2);
+            }
+          }
+          if (r < NP)
+            *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) =
+                make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
+        } else {
+          if (r < NP) *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v0[ii][p];
+        }
+      }
+    }
   }
 }
 
@@ -581,49 +585,54 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
         kf4[2 * nt] = ok ? __ldg(kp + t) : make_uint4(0u, 0u, 0u, 0u);
         kf4[2 * nt + 1] = ok ? __ldg(kp + 4 + t) : make_uint4(0u, 0u, 0u, 0u);
       }
-      uint32_t vr[32];
+      uint32_t va[16];  // V rows of keys j0 .. j0 + 15 (lane = 2 output dims); the second half is requested once the K fragments are consumed
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
+      for (int i = 0; i < 16; ++i) {
         const int si = __shfl_sync(0xffffffffu, slot, i);
-        vr[i] = (j0 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
+        va[i] = (j0 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
       }
       BS_ATICK(6, 1, tp);
       // ---- scores: row 0 of four m16n8 accumulators (keys j0 + 8 nt + 2 t, + 1 in lanes 0-3) ----
-      float sacc[4][4];
+      float p[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-        ds_mma(sacc[nt], qa.x, 0u, qa.y, 0u, kf4[2 * nt].x, kf4[2 * nt].y);
-        ds_mma(sacc[nt], qa.z, 0u, qa.w, 0u, kf4[2 * nt].z, kf4[2 * nt].w);
-        ds_mma(sacc[nt], qb.x, 0u, qb.y, 0u, kf4[2 * nt + 1].x, kf4[2 * nt + 1].y);
-        ds_mma(sacc[nt], qb.z, 0u, qb.w, 0u, kf4[2 * nt + 1].z, kf4[2 * nt + 1].w);
+        float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+        ds_mma(sacc, qa.x, 0u, qa.y, 0u, kf4[2 * nt].x, kf4[2 * nt].y);
+        ds_mma(sacc, qa.z, 0u, qa.w, 0u, kf4[2 * nt].z, kf4[2 * nt].w);
+        ds_mma(sacc, qb.x, 0u, qb.y, 0u, kf4[2 * nt + 1].x, kf4[2 * nt + 1].y);
+        ds_mma(sacc, qb.z, 0u, qb.w, 0u, kf4[2 * nt + 1].z, kf4[2 * nt + 1].w);
+        p[nt][0] = (g == 0 && j0 + 8 * nt + 2 * t < pos) ? sacc[0] : -INFINITY;
+        p[nt][1] = (g == 0 && j0 + 8 * nt + 2 * t + 1 < pos) ? sacc[1] : -INFINITY;
+      }
+      uint32_t vb[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int si = __shfl_sync(0xffffffffu, slot, 16 + i);
+        vb[i] = (j0 + 16 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + 16 + i) * pos_stride + si * d))) : 0u;
       }
       BS_ATICK(6, 2, tp);
       float mx = -INFINITY;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        sacc[nt][0] = (g == 0 && j0 + 8 * nt + 2 * t < pos) ? sacc[nt][0] : -INFINITY;
-        sacc[nt][1] = (g == 0 && j0 + 8 * nt + 2 * t + 1 < pos) ? sacc[nt][1] : -INFINITY;
-        mx = fmaxf(mx, fmaxf(sacc[nt][0], sacc[nt][1]));
-      }
+      for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(p[nt][0], p[nt][1]));
       mx = warp_max(mx);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = __expf(m_run - m_new);
       float ps = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        sacc[nt][0] = __expf(sacc[nt][0] - m_new);  // 0 for masked keys and for the lanes that hold no real score
-        sacc[nt][1] = __expf(sacc[nt][1] - m_new);
-        ps += sacc[nt][0] + sacc[nt][1];
+        p[nt][0] = __expf(p[nt][0] - m_new);  // 0 for masked keys and for the lanes that hold no real score
+        p[nt][1] = __expf(p[nt][1] - m_new);
+        ps += p[nt][0] + p[nt][1];
       }
       l_run = fmaf(l_run, alpha, warp_sum(ps));
       acc.x *= alpha;
       acc.y *= alpha;
       m_run = m_new;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {  // key j0 + i: probability in lane (i & 7) >> 1, register sacc[i >> 3][i & 1]
-        const float pi = __shfl_sync(0xffffffffu, sacc[i >> 3][i & 1], (i & 7) >> 1);
-        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vr[i]));
+      for (int i = 0; i < 32; ++i) {  // key j0 + i: probability in lane (i & 7) >> 1, register p[i >> 3][i & 1]
+        const float pi = __shfl_sync(0xffffffffu, p[i >> 3][i & 1], (i & 7) >> 1);
+        const uint32_t vw = i < 16 ? va[i & 15] : vb[i & 15];
+        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vw));
         acc.x = fmaf(pi, vv2.x, acc.x);
         acc.y = fmaf(pi, vv2.y, acc.y);
       }
@@ -1047,19 +1056,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
     if (threadIdx.x == kBsThreads + 64) bs_mma_thread(a, sh, ring, U, kv0);
   } else {
     int phase = 0;  // grid phases executed so far
-    // ---- embed: x = tok_emb[token] + pos_emb[pos]; zero the split-K accumulators and the LayerNorm statistics ----
-    if ((int)blockIdx.x < a.R) {
-      const int r = blockIdx.x, d = a.d;
-      int tok = a.tokens_in[r];
-      tok = tok < 0 ? 0 : (tok >= a.n_vocab ? a.n_vocab - 1 : tok);
-      const int pos = sh.rows[r].pos;
-      for (int i = threadIdx.x; i < d; i += kBsThreads)
-        __stcg(a.x + bs_bidx(a.R, r, i), __half2float(a.tok_emb[(long long)tok * d + i]) + a.pos_emb[(long long)pos * d + i]);
-    }
-    bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));
-    bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));
-    bs_zero_f32(a.h32, bs_bsize(a.R, 4 * a.d));
-    bs_zero_f32(a.stats, (long long)((3 * L * a.R * 2 + 3) & ~3));
+    bs_embed_phase(a, sh);
     bool run = bs_enabled(a, ++phase);  // phase 0 done after the barrier; `phase` is the index of the next one
     bs_grid_barrier(a, sh);
 #pragma unroll 1
