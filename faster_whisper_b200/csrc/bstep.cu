@@ -498,22 +498,24 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
 
 // Masked self-attention: one (row, head) task per warp.  q, k, v of the new token come from the raw QKV sums (deferred LayerNorm +
 // bias applied here); k and v are rounded to fp16 and written to the paged cache.  The history is gathered through the beam
-// ancestry table in blocks of 32 keys with an online softmax, ONE memory round trip per block and no shared-memory staging:
-//   * scores on mma.sync: the K rows are loaded straight from the cache as k-permuted 16-byte B fragments (thread (g, t) reads
-//     chunks t and 4 + t of key 8 n + g), the query is the A fragment (row 0 real), so lanes 0-3 end up with the 32 scores;
-//   * P V on the FMA pipe with "lane = 2 output dims": the 32 V rows of the block are 32 coalesced 4-byte loads per lane, issued
-//     together with the K loads; probabilities are broadcast with shuffles.
+// ancestry table in blocks of 16 keys with an online softmax.  The K and V rows of a block are copied into the warp's own
+// shared-memory tile with cp.async — COALESCED: eight lanes copy the eight 16-byte chunks of one 128-byte row, so an instruction
+// touches 4 cache lines, not 32 — and double buffered: the copies of block b + 1 are in flight while block b is scored.  With only
+// eight compute warps per SM this is what keeps enough bytes in flight (registers cannot: 64 data registers per block spill).
+constexpr int kBsSelfTile = 2 * 2 * 16 * 64 * 2;  // per warp: two buffers x (K + V) x 16 keys x 64 halves = 8 KB
 __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
-  __half* qs = reinterpret_cast<__half*>(U) + warp * 64;  // the task's query (fp16, pre-scaled by 1/8)
+  __half* tiles = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [buf][K|V][16 keys][64]; K chunks at chunk ^ (key & 7)
+  float* qs = reinterpret_cast<float*>(U + (size_t)kBsWarps * kBsSelfTile) + warp * 64;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
   __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
   const int ntasks = H * a.R, e0 = 2 * lane;
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
+  const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
+  const int kl = lane >> 1, khalf = lane & 1;     // score role: key of the block and which 32 dims
 #pragma unroll 1
   for (int task = blockIdx.x * kBsWarps + warp; task < ntasks; task += gridDim.x * kBsWarps) {
     const int r = task / H, h = task - r * H;
@@ -522,7 +524,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     long long tp = clock64();
     // ---- everything that does not depend on anything else is requested first: ancestry slots, raw q/k/v, statistics ----
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
-    uint32_t slots[4] = {0u, 0u, 0u, 0u};  // n_ctx <= 448 = 14 blocks of 32 keys, one byte per block
+    uint32_t slots[4] = {0u, 0u, 0u, 0u};  // lane holds the slot byte of key 32 i + lane for i < 14 (n_ctx <= 448)
 #pragma unroll
     for (int i = 0; i < 14; ++i) {
       const int jj = 32 * i + lane;
@@ -540,102 +542,95 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
                  wv = __ldg(reinterpret_cast<const float2*>(ws + 2 * d));
     const float2 bq = __ldg(reinterpret_cast<const float2*>(bs)), bk = __ldg(reinterpret_cast<const float2*>(bs + d)),
                  bvv = __ldg(reinterpret_cast<const float2*>(bs + 2 * d));
+    const long long chunk_off = (long long)ri.chunk * n_ctx * pos_stride + h * 64;
+    const __half* kbase = kc + chunk_off;
+    const __half* vbase = vc + chunk_off;
+    const int nblk = (pos + 15) >> 4;
+    // copies of block b into buffer b & 1 (keys 16 b + crow + 4 i, i < 4); one commit group per block
+    auto issue = [&](int b) {
+      __half* kd = tiles + (b & 1) * (2 * 16 * 64);
+      __half* vd = kd + 16 * 64;
+      const int w32 = b >> 1;  // which 32-key group holds the slot bytes
+      const uint32_t word = (w32 >> 2) == 0 ? slots[0] : ((w32 >> 2) == 1 ? slots[1] : ((w32 >> 2) == 2 ? slots[2] : slots[3]));
+      const uint32_t mine = (word >> (8 * (w32 & 3))) & 255u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int key = crow + 4 * i, j = 16 * b + key;
+        const int sj = (int)__shfl_sync(0xffffffffu, mine, 16 * (b & 1) + key);
+        if (j < pos) {
+          const int off = j * pos_stride + sj * d + cchunk * 8;  // elements; < 2^31 for every supported shape
+          ds_cp_async16(kd + key * 64 + ((cchunk ^ (key & 7)) << 3), kbase + off);
+          ds_cp_async16(vd + key * 64 + (cchunk << 3), vbase + off);
+        }
+      }
+      ds_cp_commit();
+    };
+    __syncwarp();  // the previous task's tiles and query are no longer being read
+    if (nblk > 0) issue(0);
     const float mr = mean * rstd;
 #define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
-    // q is rounded to fp16 like the other decode paths (they store q as fp16); the 1/8 scale is exact in fp16
-    const __half2 q16 = __hmul2(__floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y)), __floats2half2_rn(0.125f, 0.125f));
+    // q is rounded to fp16 like the other decode paths (they store q as fp16), then pre-scaled by 1/8
+    const __half2 q16 = __floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y));
     const __half2 k16 = __floats2half2_rn(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y));
     const __half2 v16 = __floats2half2_rn(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y));
 #undef BS_FIX
     const float2 qf = __half22float2(q16), kf = __half22float2(k16), vf = __half22float2(v16);
-    const long long chunk_off = (long long)ri.chunk * n_ctx * pos_stride + h * 64;
     const long long self_off = chunk_off + (long long)pos * pos_stride + ri.slot * d + e0;
     *reinterpret_cast<__half2*>(kc + self_off) = k16;
     *reinterpret_cast<__half2*>(vc + self_off) = v16;
-    __syncwarp();  // the previous task's fragment reads of qs are done
-    *reinterpret_cast<__half2*>(qs + e0) = q16;
-    float m_run = warp_sum(qf.x * kf.x + qf.y * kf.y);  // the new token's own key
+    *reinterpret_cast<float2*>(qs + e0) = make_float2(qf.x * 0.125f, qf.y * 0.125f);
+    float m_run = warp_sum(qf.x * 0.125f * kf.x + qf.y * 0.125f * kf.y);  // the new token's own key
     float l_run = 1.f;
     float2 acc = vf;
-    __syncwarp();
-    // A fragments of S = q K^T (k-permuted 16-byte chunks t and 4 + t); only accumulator row 0 is a real query
-    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = make_uint4(0u, 0u, 0u, 0u);
-    if (g == 0) {
-      qa = *reinterpret_cast<const uint4*>(qs + 8 * t);
-      qb = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
-    }
-    const __half* kbase = kc + chunk_off;
-    const __half* vbase = vc + chunk_off + e0;
     BS_ATICK(6, 0, tp);
 #pragma unroll 1
-    for (int blk = 0; blk * 32 < pos; ++blk) {
-      const int bw = blk >> 2;
-      const uint32_t word = bw == 0 ? slots[0] : (bw == 1 ? slots[1] : (bw == 2 ? slots[2] : slots[3]));
-      const int slot = (int)((word >> (8 * (blk & 3))) & 255u);  // slot of key blk * 32 + lane
-      const int j0 = blk * 32;
-      // ---- all loads of the block: 8 K fragments (16 B) + 32 V words (4 B) per lane ----
-      uint4 kf4[8];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int jj = j0 + 8 * nt + g;
-        const int sj = __shfl_sync(0xffffffffu, slot, 8 * nt + g);
-        const bool ok = jj < pos;
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (ok ? jj * pos_stride + sj * d : 0));
-        // history rows were written by earlier launches (this launch only writes position `pos`): the read-only path is safe
-        kf4[2 * nt] = ok ? __ldg(kp + t) : make_uint4(0u, 0u, 0u, 0u);
-        kf4[2 * nt + 1] = ok ? __ldg(kp + 4 + t) : make_uint4(0u, 0u, 0u, 0u);
+    for (int b = 0; b < nblk; ++b) {
+      if (b + 1 < nblk) {
+        issue(b + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
-      uint32_t va[16];  // V rows of keys j0 .. j0 + 15 (lane = 2 output dims); the second half is requested once the K fragments are consumed
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int si = __shfl_sync(0xffffffffu, slot, i);
-        va[i] = (j0 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + i) * pos_stride + si * d))) : 0u;
-      }
-      BS_ATICK(6, 1, tp);
-      // ---- scores: row 0 of four m16n8 accumulators (keys j0 + 8 nt + 2 t, + 1 in lanes 0-3) ----
-      float p[4][2];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        float sacc[4] = {0.f, 0.f, 0.f, 0.f};
-        ds_mma(sacc, qa.x, 0u, qa.y, 0u, kf4[2 * nt].x, kf4[2 * nt].y);
-        ds_mma(sacc, qa.z, 0u, qa.w, 0u, kf4[2 * nt].z, kf4[2 * nt].w);
-        ds_mma(sacc, qb.x, 0u, qb.y, 0u, kf4[2 * nt + 1].x, kf4[2 * nt + 1].y);
-        ds_mma(sacc, qb.z, 0u, qb.w, 0u, kf4[2 * nt + 1].z, kf4[2 * nt + 1].w);
-        p[nt][0] = (g == 0 && j0 + 8 * nt + 2 * t < pos) ? sacc[0] : -INFINITY;
-        p[nt][1] = (g == 0 && j0 + 8 * nt + 2 * t + 1 < pos) ? sacc[1] : -INFINITY;
-      }
-      uint32_t vb[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int si = __shfl_sync(0xffffffffu, slot, 16 + i);
-        vb[i] = (j0 + 16 + i < pos) ? __ldg(reinterpret_cast<const uint32_t*>(vbase + ((j0 + 16 + i) * pos_stride + si * d))) : 0u;
-      }
+      __syncwarp();
       BS_ATICK(6, 2, tp);
-      float mx = -INFINITY;
+      const __half* kt = tiles + (b & 1) * (2 * 16 * 64);
+      const __half* vt = kt + 16 * 64;
+      // ---- scores: lane = (key kl, 32-dim half khalf) ----
+      float s0 = 0.f, s1 = 0.f;
+      {
+        const uint4* kp = reinterpret_cast<const uint4*>(kt + kl * 64);
+        const float* qh = qs + 32 * khalf;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mx = fmaxf(mx, fmaxf(p[nt][0], p[nt][1]));
-      mx = warp_max(mx);
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = __expf(m_run - m_new);
-      float ps = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        p[nt][0] = __expf(p[nt][0] - m_new);  // 0 for masked keys and for the lanes that hold no real score
-        p[nt][1] = __expf(p[nt][1] - m_new);
-        ps += p[nt][0] + p[nt][1];
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint4 kr = kp[(4 * khalf + cc) ^ (kl & 7)];
+          const float4 qa = *reinterpret_cast<const float4*>(qh + 8 * cc), qb = *reinterpret_cast<const float4*>(qh + 8 * cc + 4);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr.y)),
+                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr.w));
+          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
+          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
+        }
       }
-      l_run = fmaf(l_run, alpha, warp_sum(ps));
+      float sv = s0 + s1;
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      const bool valid = 16 * b + kl < pos;
+      sv = valid ? sv : -INFINITY;
+      const float m_new = fmaxf(m_run, warp_max(sv));
+      const float alpha = __expf(m_run - m_new);
+      const float p = valid ? __expf(sv - m_new) : 0.f;
+      l_run = fmaf(l_run, alpha, warp_sum(khalf == 0 ? p : 0.f));
       acc.x *= alpha;
       acc.y *= alpha;
       m_run = m_new;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {  // key j0 + i: probability in lane (i & 7) >> 1, register p[i >> 3][i & 1]
-        const float pi = __shfl_sync(0xffffffffu, p[i >> 3][i & 1], (i & 7) >> 1);
-        const uint32_t vw = i < 16 ? va[i & 15] : vb[i & 15];
-        const float2 vv2 = __half22float2(*reinterpret_cast<const __half2*>(&vw));
+      const int nvalid = min(16, pos - 16 * b);
+      const __half2* vrow = reinterpret_cast<const __half2*>(vt) + lane;
+#pragma unroll 4
+      for (int i = 0; i < nvalid; ++i) {
+        const float pi = __shfl_sync(0xffffffffu, p, 2 * i);
+        const float2 vv2 = __half22float2(vrow[i * 32]);
         acc.x = fmaf(pi, vv2.x, acc.x);
         acc.y = fmaf(pi, vv2.y, acc.y);
       }
+      __syncwarp();  // the buffer may be refilled by the copies issued in the next iteration
       BS_ATICK(6, 3, tp);
       if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
     }
@@ -1182,7 +1177,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
   u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
-  u = std::max(u, (size_t)kBsWarps * 64 * 2);                                                // self-attention: one fp16 query per warp
+  u = std::max(u, (size_t)kBsWarps * (kBsSelfTile + 64 * 4));                                // self-attention: K/V tiles + query per warp
   a.u_bytes = (int)((u + 1023) & ~size_t(1023));
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);

@@ -1243,7 +1243,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
         if (f[6 * 16 + 15] > 0)
-          fprintf(stderr, "[bstep prof]   self-attn cycles per 32-key block (CTA 0 warp 0): issue %.0f  copy-wait %.0f  compute %.0f; prologue per task total %.0f over %llu blocks\n",
+          fprintf(stderr, "[bstep prof]   self-attn cycles per 16-key block (CTA 0 warp 0): (unused) %.0f  issue+copy-wait %.0f  compute %.0f; prologue per task total %.0f over %llu blocks\n",
                   (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], (double)f[6 * 16 + 3] / f[6 * 16 + 15], (double)f[6 * 16],
                   f[6 * 16 + 15]);
         if (f[7 * 16 + 15] > 0)
