@@ -506,8 +506,9 @@ constexpr int kBsSelfTile = 2 * 2 * 16 * 64 * 2;  // per warp: two buffers x (K 
 __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
-  __half* tiles = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [buf][K|V][16 keys][64]; K chunks at chunk ^ (key & 7)
-  float* qs = reinterpret_cast<float*>(U + (size_t)kBsWarps * kBsSelfTile) + warp * 64;
+  __half* tiles = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [buf][K|V][16 keys][64]; 16-byte chunks at chunk ^ (key & 7)
+  __half* qs = reinterpret_cast<__half*>(U + (size_t)kBsWarps * kBsSelfTile) + warp * 64;  // the task's query, fp16, pre-scaled by 1/8
+  const int g = lane >> 2, t = lane & 3;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
@@ -515,7 +516,6 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const int ntasks = H * a.R, e0 = 2 * lane;
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
-  const int kl = lane >> 1, khalf = lane & 1;     // score role: key of the block and which 32 dims
 #pragma unroll 1
   for (int task = blockIdx.x * kBsWarps + warp; task < ntasks; task += gridDim.x * kBsWarps) {
     const int r = task / H, h = task - r * H;
@@ -560,7 +560,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
         if (j < pos) {
           const int off = j * pos_stride + sj * d + cchunk * 8;  // elements; < 2^31 for every supported shape
           ds_cp_async16(kd + key * 64 + ((cchunk ^ (key & 7)) << 3), kbase + off);
-          ds_cp_async16(vd + key * 64 + (cchunk << 3), vbase + off);
+          ds_cp_async16(vd + key * 64 + ((cchunk ^ (key & 7)) << 3), vbase + off);
         }
       }
       ds_cp_commit();
@@ -569,8 +569,8 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     if (nblk > 0) issue(0);
     const float mr = mean * rstd;
 #define BS_FIX(raw_, w_, b_) fmaf(rstd, raw_, fmaf(-mr, w_, b_))
-    // q is rounded to fp16 like the other decode paths (they store q as fp16), then pre-scaled by 1/8
-    const __half2 q16 = __floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y));
+    // q is rounded to fp16 like the other decode paths (they store q as fp16); the 1/8 scale is exact in fp16
+    const __half2 q16 = __hmul2(__floats2half2_rn(BS_FIX(rq.x, wq.x, bq.x), BS_FIX(rq.y, wq.y, bq.y)), __floats2half2_rn(0.125f, 0.125f));
     const __half2 k16 = __floats2half2_rn(BS_FIX(rk.x, wk.x, bk.x), BS_FIX(rk.y, wk.y, bk.y));
     const __half2 v16 = __floats2half2_rn(BS_FIX(rv.x, wv.x, bvv.x), BS_FIX(rv.y, wv.y, bvv.y));
 #undef BS_FIX
@@ -578,10 +578,25 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     const long long self_off = chunk_off + (long long)pos * pos_stride + ri.slot * d + e0;
     *reinterpret_cast<__half2*>(kc + self_off) = k16;
     *reinterpret_cast<__half2*>(vc + self_off) = v16;
-    *reinterpret_cast<float2*>(qs + e0) = make_float2(qf.x * 0.125f, qf.y * 0.125f);
-    float m_run = warp_sum(qf.x * 0.125f * kf.x + qf.y * 0.125f * kf.y);  // the new token's own key
-    float l_run = 1.f;
-    float2 acc = vf;
+    *reinterpret_cast<__half2*>(qs + e0) = q16;
+    // online-softmax state, seeded with the new token's own key (p = 1): m uniform over the warp; the running sum and the output
+    // accumulators follow the m16n8 accumulator layout, whose row 0 (lanes 0-3) is the only real query
+    float m_run = warp_sum(qf.x * kf.x + qf.y * kf.y);
+    float l_part = lane == 0 ? 1.f : 0.f;
+    float oacc[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {  // dims 8 dt + 2 t, + 1 of v sit in lane 4 dt + t of the "lane = 2 dims" layout
+      const float ox = __shfl_sync(0xffffffffu, vf.x, 4 * dt + t), oy = __shfl_sync(0xffffffffu, vf.y, 4 * dt + t);
+      oacc[dt][0] = g == 0 ? ox : 0.f;
+      oacc[dt][1] = g == 0 ? oy : 0.f;
+      oacc[dt][2] = oacc[dt][3] = 0.f;
+    }
+    __syncwarp();
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = make_uint4(0u, 0u, 0u, 0u);  // A fragments of S = q K^T (k-permuted chunks t, 4 + t)
+    if (g == 0) {
+      qa = *reinterpret_cast<const uint4*>(qs + 8 * t);
+      qb = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
+    }
     BS_ATICK(6, 0, tp);
 #pragma unroll 1
     for (int b = 0; b < nblk; ++b) {
@@ -594,48 +609,71 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       __syncwarp();
       BS_ATICK(6, 2, tp);
       const __half* kt = tiles + (b & 1) * (2 * 16 * 64);
-      const __half* vt = kt + 16 * 64;
-      // ---- scores: lane = (key kl, 32-dim half khalf) ----
-      float s0 = 0.f, s1 = 0.f;
-      {
-        const uint4* kp = reinterpret_cast<const uint4*>(kt + kl * 64);
-        const float* qh = qs + 32 * khalf;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint4 kr = kp[(4 * khalf + cc) ^ (kl & 7)];
-          const float4 qa = *reinterpret_cast<const float4*>(qh + 8 * cc), qb = *reinterpret_cast<const float4*>(qh + 8 * cc + 4);
-          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&kr.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&kr.y)),
-                       f2 = __half22float2(*reinterpret_cast<const __half2*>(&kr.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&kr.w));
-          s0 = fmaf(qa.x, f0.x, fmaf(qa.y, f0.y, fmaf(qa.z, f1.x, fmaf(qa.w, f1.y, s0))));
-          s1 = fmaf(qb.x, f2.x, fmaf(qb.y, f2.y, fmaf(qb.z, f3.x, fmaf(qb.w, f3.y, s1))));
-        }
-      }
-      float sv = s0 + s1;
-      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-      const bool valid = 16 * b + kl < pos;
-      sv = valid ? sv : -INFINITY;
-      const float m_new = fmaxf(m_run, warp_max(sv));
-      const float alpha = __expf(m_run - m_new);
-      const float p = valid ? __expf(sv - m_new) : 0.f;
-      l_run = fmaf(l_run, alpha, warp_sum(khalf == 0 ? p : 0.f));
-      acc.x *= alpha;
-      acc.y *= alpha;
-      m_run = m_new;
+      __half* vt = tiles + (b & 1) * (2 * 16 * 64) + 16 * 64;
       const int nvalid = min(16, pos - 16 * b);
-      const __half2* vrow = reinterpret_cast<const __half2*>(vt) + lane;
-#pragma unroll 4
-      for (int i = 0; i < nvalid; ++i) {
-        const float pi = __shfl_sync(0xffffffffu, p, 2 * i);
-        const float2 vv2 = __half22float2(vrow[i * 32]);
-        acc.x = fmaf(pi, vv2.x, acc.x);
-        acc.y = fmaf(pi, vv2.y, acc.y);
+      if (nvalid < 16) {  // rows that were not copied are multiplied by zero probabilities: make them finite
+        for (int i = lane; i < (16 - nvalid) * 8; i += 32) *reinterpret_cast<uint4*>(vt + (nvalid + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+      }
+      // ---- S = q K^T: two n8 tiles (keys g and 8 + g), 16-byte k-permuted fragments ----
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const int sw = g;  // (key & 7) of both rows
+        const uint4 ka = *reinterpret_cast<const uint4*>(kt + g * 64 + ((t ^ sw) << 3));
+        const uint4 kb4 = *reinterpret_cast<const uint4*>(kt + g * 64 + (((4 + t) ^ sw) << 3));
+        const uint4 kc4 = *reinterpret_cast<const uint4*>(kt + (8 + g) * 64 + ((t ^ sw) << 3));
+        const uint4 kd = *reinterpret_cast<const uint4*>(kt + (8 + g) * 64 + (((4 + t) ^ sw) << 3));
+        ds_mma(s0, qa.x, 0u, qa.y, 0u, ka.x, ka.y);
+        ds_mma(s0, qa.z, 0u, qa.w, 0u, ka.z, ka.w);
+        ds_mma(s0, qb.x, 0u, qb.y, 0u, kb4.x, kb4.y);
+        ds_mma(s0, qb.z, 0u, qb.w, 0u, kb4.z, kb4.w);
+        ds_mma(s1, qa.x, 0u, qa.y, 0u, kc4.x, kc4.y);
+        ds_mma(s1, qa.z, 0u, qa.w, 0u, kc4.z, kc4.w);
+        ds_mma(s1, qb.x, 0u, qb.y, 0u, kd.x, kd.y);
+        ds_mma(s1, qb.z, 0u, qb.w, 0u, kd.z, kd.w);
+      }
+      // lanes 0-3 (row 0): keys 2 t, 2 t + 1 (s0[0..1]) and 8 + 2 t, 9 + 2 t (s1[0..1]) of the block
+      const bool row0 = g == 0;
+      const float v00 = (row0 && 2 * t < nvalid) ? s0[0] : -INFINITY, v01 = (row0 && 2 * t + 1 < nvalid) ? s0[1] : -INFINITY;
+      const float v10 = (row0 && 8 + 2 * t < nvalid) ? s1[0] : -INFINITY, v11 = (row0 && 9 + 2 * t < nvalid) ? s1[1] : -INFINITY;
+      float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = __shfl_sync(0xffffffffu, mx, 0);
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = __expf(m_run - m_new);
+      const __half2 p0 = __floats2half2_rn(__expf(v00 - m_new), __expf(v01 - m_new)), p1 = __floats2half2_rn(__expf(v10 - m_new), __expf(v11 - m_new));
+      const float2 pf0 = __half22float2(p0), pf1 = __half22float2(p1);
+      l_part = fmaf(l_part, alpha, (pf0.x + pf0.y) + (pf1.x + pf1.y));
+      m_run = m_new;
+      const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(&p0), pa2 = *reinterpret_cast<const uint32_t*>(&p1);
+      // ---- O (+)= P V: B = V via ldmatrix.trans (16 keys x 8 dims per tile) ----
+      const int mi = lane >> 3, r8 = lane & 7;
+      const int vkey = 8 * (mi & 1) + r8;
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ds_ldmatrix_x4_trans(b0, b1, b2, b3, vt + vkey * 64 + (((2 * dp + (mi >> 1)) ^ (vkey & 7)) << 3));
+        oacc[2 * dp][0] *= alpha;
+        oacc[2 * dp][1] *= alpha;
+        oacc[2 * dp + 1][0] *= alpha;
+        oacc[2 * dp + 1][1] *= alpha;
+        ds_mma(oacc[2 * dp], pa0, 0u, pa2, 0u, b0, b1);
+        ds_mma(oacc[2 * dp + 1], pa0, 0u, pa2, 0u, b2, b3);
       }
       __syncwarp();  // the buffer may be refilled by the copies issued in the next iteration
       BS_ATICK(6, 3, tp);
       if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
     }
-    const float inv = 1.f / l_run;
-    *reinterpret_cast<uint32_t*>(a.ao + (long long)r * d + h * 64 + e0) = pack_half2(acc.x * inv, acc.y * inv);
+    float l_run = l_part;
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (g == 0) {
+      const float inv = 1.f / l_run;
+      __half* o = a.ao + (long long)r * d + h * 64 + 2 * t;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(o + 8 * dt) = pack_half2(oacc[dt][0] * inv, oacc[dt][1] * inv);
+    }
   }
 }
 
@@ -1177,7 +1215,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
   u = std::max(u, (size_t)kBsKvBytes + ((kBsXScratch + 127) & ~127));                        // second K/V tile + cross-attention scratch
-  u = std::max(u, (size_t)kBsWarps * (kBsSelfTile + 64 * 4));                                // self-attention: K/V tiles + query per warp
+  u = std::max(u, (size_t)kBsWarps * (kBsSelfTile + 64 * 2));                                // self-attention: K/V tiles + query per warp
   a.u_bytes = (int)((u + 1023) & ~size_t(1023));
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
