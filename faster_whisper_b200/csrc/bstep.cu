@@ -112,16 +112,39 @@ struct BsRange {  // scalars only: arrays indexed at run time would live in loca
   __device__ __forceinline__ int ka0(int sg) const { return sg ? ka01 : ka00; }
   __device__ __forceinline__ int n(int sg) const { return sg ? n1 : n0; }
 };
-// atoms of GEMM s owned by this CTA, cut at n-block boundaries (at most two segments: an even share is shorter than one n-block's K)
+// Atoms of GEMM s owned by this CTA.  The CTAs are dealt out to the n-blocks (as evenly as the counts allow) and the CTAs of an
+// n-block split its K atoms among themselves, so a CTA's run never crosses an n-block: one accumulator, one epilogue, one bulk
+// reduction per phase.  (A plain stream-K cut balances one atom better in FFN1 but gives ~10% of the CTAs a second segment whose
+// epilogue lands on the critical path of every phase.)  With fewer CTAs than n-blocks it falls back to the stream-K cut.
+__host__ __device__ __forceinline__ void bs_split(int NB, int KA, int c, int G, int& a0, int& a1) {
+  const int base = G / NB, extra = G - base * NB;
+  if (base == 0) {
+    const unsigned A = (unsigned)NB * (unsigned)KA;
+    a0 = (int)(A * (unsigned)c / (unsigned)G);
+    a1 = (int)(A * (unsigned)(c + 1) / (unsigned)G);
+    return;
+  }
+  int nb, idx, cnt;
+  if (c < extra * (base + 1)) {
+    nb = c / (base + 1);
+    idx = c - nb * (base + 1);
+    cnt = base + 1;
+  } else {
+    const int c2 = c - extra * (base + 1);
+    nb = extra + c2 / base;
+    idx = c2 - (c2 / base) * base;
+    cnt = base;
+  }
+  a0 = nb * KA + KA * idx / cnt;
+  a1 = nb * KA + KA * (idx + 1) / cnt;
+}
 __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
   const int j = s % 6, d = a.d;
   const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
   const int K = j == 5 ? 4 * d : d;
   BsRange r;
   r.KA = K >> 6;
-  const unsigned A = (unsigned)((N + 127) >> 7) * (unsigned)r.KA;  // <= 800 atoms x 148 CTAs: 32-bit products
-  r.a0 = (int)(A * blockIdx.x / gridDim.x);
-  r.a1 = (int)(A * (blockIdx.x + 1) / gridDim.x);
+  bs_split((N + 127) >> 7, r.KA, (int)blockIdx.x, (int)gridDim.x, r.a0, r.a1);
   r.nseg = 0;
   r.nb0 = r.nb1 = r.ka00 = r.ka01 = r.n0 = r.n1 = 0;
   if (r.a1 > r.a0) {
@@ -341,7 +364,7 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
 //   X == true : source = fp32 residual stream, n-block-major (converted raw; the LayerNorm is applied by the consumer of the GEMM
 //               output); sum(x), sum(x^2) of every K slice are accumulated into `st` by exactly one of the CTAs that stage it
 //   X == false: source = fp16 activations [R][ld]
-// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); two tiles (<= 6 chunks per thread)
+// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); three (fp32) or four (fp16) tiles
 // are in flight together.
 template <bool X>
 __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
@@ -351,12 +374,13 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
   const int natoms = rg.a1 - rg.a0;
   const int c = tid & 7, r_lo = tid >> 3;
   constexpr int PASSES = 3;  // 96 rows >= NP (<= 80)
+  constexpr int GRP = X ? 3 : 4;
 #pragma unroll 1
-  for (int i0 = 0; i0 < natoms; i0 += 2) {
-    uint4 v0[2][PASSES], v1[X ? 2 : 1][X ? PASSES : 1];
-    int duty[2];
+  for (int i0 = 0; i0 < natoms; i0 += GRP) {
+    uint4 v0[GRP][PASSES], v1[X ? GRP : 1][X ? PASSES : 1];
+    int duty[GRP];
 #pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
+    for (int ii = 0; ii < GRP; ++ii) {
       const int i = i0 + ii;
       const bool on = i < natoms;
       const int sg = i < rg.n0 ? 0 : 1;
@@ -380,7 +404,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
       }
     }
 #pragma unroll
-    for (int ii = 0; ii < 2; ++ii) {
+    for (int ii = 0; ii < GRP; ++ii) {
       const int i = i0 + ii;
       if (i >= natoms) break;
       unsigned char* tile = xs + (size_t)i * (NP * 128);
@@ -1206,11 +1230,13 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
   int max_atoms = 1;
   const int Ns[3] = {3 * d, 4 * d, d}, Ks[3] = {d, d, 4 * d};
   for (int i = 0; i < 3; ++i) {
-    const int KA = Ks[i] / 64;
-    const long long A = (long long)((Ns[i] + 127) / 128) * KA;
-    const int share = (int)((A + G - 1) / G);
-    if (share > KA) return false;  // a CTA's range would span more than two n-blocks
-    max_atoms = std::max(max_atoms, share);
+    const int KA = Ks[i] / 64, NB = (Ns[i] + 127) / 128;
+    for (int c = 0; c < G; ++c) {
+      int a0, a1;
+      bs_split(NB, KA, c, G, a0, a1);
+      if (a1 - a0 > KA) return false;  // a CTA's run would span more than two n-blocks
+      max_atoms = std::max(max_atoms, a1 - a0);
+    }
   }
   size_t u = (size_t)max_atoms * a.NP * 128;
   u = std::max(u, (size_t)a.NP * 512);                                                       // fp32 staging tile of the bulk reductions
