@@ -37,7 +37,10 @@ namespace b2w {
 constexpr int kBsThreads = 256;   // compute threads (8 warps)
 constexpr int kBsLaunch = 352;    // + weight producer warp, K/V producer warp, MMA warp
 constexpr int kBsWarps = 8;
-constexpr int kBsSlots = 5;       // weight-atom ring
+constexpr int kBsSlots = 5;       // weight-atom ring (fp16 atoms, 16 KB each)
+constexpr int kBsSlots8 = 6;      // int8 atoms (8 KB each) + two 16 KB fp16 tiles the compute warps widen them into: the same 80 KB
+constexpr int kBsAtomBytes8 = 8192;
+constexpr int kBsMaxSlots = 6;
 constexpr int kBsKvBytes = 2 * kDsXKeysMax * 64 * 2;  // one cross-attention K + V tile (57 344 B)
 constexpr int kBsXQ = 8;          // rows per chunk the cross-attention task handles
 constexpr int kBsQLd = 96;
@@ -86,8 +89,11 @@ struct BsShared {
   unsigned ticks[8 * 8];     // B2W_DSTEP_PROF: cycles of CTA 0 per GEMM kind: [stage, wait acc, epilogue, bulk wait, count]
   int acc_par[2];            // parity of the next acc_full wait (compute side)
   uint32_t tmem_base;
-  uint64_t wfull[kBsSlots];  // weight atom landed (TMA complete_tx)
-  uint64_t wempty[kBsSlots]; // weight atom consumed (tcgen05.commit)
+  uint64_t wfull[kBsMaxSlots];   // weight atom landed (TMA complete_tx)
+  uint64_t wempty[kBsMaxSlots];  // weight atom consumed (tcgen05.commit; with int8 atoms: widened, arrival by compute thread 0)
+  uint64_t ffull[2];             // int8 path: widened fp16 tile ready (compute -> MMA thread)
+  uint64_t fempty[2];            // int8 path: widened tile consumed (tcgen05.commit)
+  int cons8, fcnt;               // int8 path: atoms widened so far (ring index / fp16 tile index), compute side
   uint64_t xs_ready;         // activations of the phase staged (compute -> MMA thread)
   uint64_t acc_full[2];      // accumulator complete (tcgen05.commit -> compute)
   uint64_t acc_empty[2];     // accumulator drained (compute -> MMA thread; logits phase only)
@@ -183,11 +189,14 @@ __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
 // ---- producer threads ------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh, unsigned char* ring) {
   int n = 0;
-  auto push = [&](const unsigned char* src) {
-    const int slot = n % kBsSlots;
-    mbar_wait(&sh.wempty[slot], (uint32_t)(((n / kBsSlots) & 1) ^ 1));
-    mbar_expect_tx(&sh.wfull[slot], kBsAtomBytes);
-    ds_bulk_g2s(ring + (size_t)slot * kBsAtomBytes, src, kBsAtomBytes, &sh.wfull[slot]);
+  const int nslots = a.w8 ? kBsSlots8 : kBsSlots;
+  const uint32_t abytes = a.w8 ? kBsAtomBytes8 : kBsAtomBytes;
+  auto push = [&](const unsigned char* src0, size_t index) {
+    const int slot = n % nslots;
+    mbar_wait(&sh.wempty[slot], (uint32_t)(((n / nslots) & 1) ^ 1));
+    if (a.w8) fence_proxy_async();  // the slot was last read through the generic proxy (widening)
+    mbar_expect_tx(&sh.wfull[slot], abytes);
+    ds_bulk_g2s(ring + (size_t)slot * abytes, src0 + index * abytes, abytes, &sh.wfull[slot]);
     n += 1;
   };
 #pragma unroll 1
@@ -196,7 +205,7 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
     const BsRange r = bs_range(a, s);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(sh.lay[s / 6].wt[s % 6]);
 #pragma unroll 1
-    for (int at = r.a0; at < r.a1; ++at) push(base + (size_t)at * kBsAtomBytes);
+    for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
   int nhalves, Rh, NPh;
@@ -208,7 +217,7 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
 #pragma unroll 1
   for (int nb = grp; nb < NBv; nb += groups)
 #pragma unroll 1
-    for (int ka = 0; ka < KA; ++ka) push(base + ((size_t)nb * KA + ka) * kBsAtomBytes);
+    for (int ka = 0; ka < KA; ++ka) push(base, (size_t)nb * KA + ka);
 }
 
 // cross-attention tiles (group-major: tile = (chunk * H + head) * splits + split) are dealt out as contiguous runs ("stream-K")
@@ -267,15 +276,28 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
   const uint32_t idesc = umma_idesc_f16(128, a.NP, false);
   const uint32_t xs_tile = (uint32_t)a.NP * 128u;
   int consumed = 0, xs_uses = 0;
+  const bool w8 = a.w8 != 0;
+  unsigned char* ftiles = ring + (size_t)kBsSlots8 * kBsAtomBytes8;  // int8 path: the two widened fp16 tiles
   auto atom = [&](uint32_t d_tmem, uint32_t b_addr, uint32_t id, bool first) {
-    const int slot = consumed % kBsSlots;
-    mbar_wait(&sh.wfull[slot], (uint32_t)((consumed / kBsSlots) & 1));
+    uint32_t a_addr;
+    uint64_t* done;
+    if (w8) {  // the compute warps widen int8 atoms into one of two fp16 tiles
+      const int f = consumed & 1;
+      mbar_wait(&sh.ffull[f], (uint32_t)((consumed >> 1) & 1));
+      a_addr = smem_u32(ftiles + (size_t)f * kBsAtomBytes);
+      done = &sh.fempty[f];
+    } else {
+      const int slot = consumed % kBsSlots;
+      mbar_wait(&sh.wfull[slot], (uint32_t)((consumed / kBsSlots) & 1));
+      a_addr = smem_u32(ring + (size_t)slot * kBsAtomBytes);
+      done = &sh.wempty[slot];
+    }
     tc_fence_after();
-    const uint64_t da = umma_smem_desc_sw128(smem_u32(ring + (size_t)slot * kBsAtomBytes));
+    const uint64_t da = umma_smem_desc_sw128(a_addr);
     const uint64_t db = umma_smem_desc_sw128(b_addr);
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_ss(d_tmem, da + 2 * k, db + 2 * k, id, (first && k == 0) ? 0u : 1u);
-    tc_commit(&sh.wempty[slot]);
+    tc_commit(done);
     consumed += 1;
   };
 #pragma unroll 1
@@ -440,6 +462,44 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
 }
 
 // One GEMM phase (compute warps): stage -> signal the MMA thread -> drain the accumulators into L2 with bulk reductions.
+// int8 path: widen `natoms` atoms of the ring ([128 channels][64] bytes holding q + 128) into the two fp16 UMMA tiles (128-byte
+// swizzle), handing each to the MMA thread as soon as it is complete.  Per atom a thread converts two 16-byte pieces
+// (2 instructions per 2 weights: prmt builds 1024 + u in fp16, one hsub2 removes 1152); the per-channel scale multiplies the fp32
+// accumulator in the epilogue ("per-channel dequant fused into the load path" of BASELINE.json configs[3]).
+__device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned char* ring) {
+  const int tid = threadIdx.x;
+  unsigned char* ftiles = ring + (size_t)kBsSlots8 * kBsAtomBytes8;
+  const int n0 = sh.cons8, f0 = sh.fcnt;
+#pragma unroll 1
+  for (int i = 0; i < natoms; ++i) {
+    const int n8 = n0 + i, slot = n8 % kBsSlots8, fc = f0 + i, f = fc & 1;
+    mbar_wait(&sh.wfull[slot], (uint32_t)((n8 / kBsSlots8) & 1));
+    mbar_wait(&sh.fempty[f], (uint32_t)(((fc >> 1) & 1) ^ 1));
+    const unsigned char* src = ring + (size_t)slot * kBsAtomBytes8;
+    unsigned char* dst = ftiles + (size_t)f * kBsAtomBytes;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * kBsThreads, row = idx >> 2, c4 = idx & 3;
+      const uint4 w = *reinterpret_cast<const uint4*>(src + row * 64 + c4 * 16);
+      const uint4 lo = make_uint4(ds_cvt_u8x2(w.x, 0x5140u), ds_cvt_u8x2(w.x, 0x5342u), ds_cvt_u8x2(w.y, 0x5140u), ds_cvt_u8x2(w.y, 0x5342u));
+      const uint4 hi = make_uint4(ds_cvt_u8x2(w.z, 0x5140u), ds_cvt_u8x2(w.z, 0x5342u), ds_cvt_u8x2(w.w, 0x5140u), ds_cvt_u8x2(w.w, 0x5342u));
+      *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c4) ^ (row & 7)) << 4)) = lo;
+      *reinterpret_cast<uint4*>(dst + row * 128 + (((2 * c4 + 1) ^ (row & 7)) << 4)) = hi;
+    }
+    fence_proxy_async();
+    bs_sync();
+    if (tid == 0) {
+      mbar_arrive(&sh.ffull[f]);
+      mbar_arrive(&sh.wempty[slot]);
+    }
+  }
+  if (tid == 0) {
+    sh.cons8 = n0 + natoms;
+    sh.fcnt = f0 + natoms;
+  }
+  bs_sync();
+}
+
 #define BS_ATICK(kind, point, tp)                                        \
   do {                                                                   \
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -458,7 +518,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
     }                                                                    \
   } while (0)
 
-__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U) {
+__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U, unsigned char* ring) {
   const BsRange rg = bs_range(a, s);
   if (rg.a1 <= rg.a0) return;
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -479,6 +539,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   bs_sync();
   if (tid == 0) mbar_arrive(&sh.xs_ready);
   BS_TICK(0);
+  if (a.w8) bs_widen_atoms(sh, rg.a1 - rg.a0, ring);
   // all accumulators of the phase must be complete before the staging tile (which aliases the activation tiles) is written
   for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
   tc_fence_after();
@@ -492,6 +553,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   for (int sg = 0; sg < rg.nseg; ++sg) {
     const int n_glob = rg.nb(sg) * 128 + q * 32 + lane;
     const float bv = (bias && rg.ka0(sg) == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
+    const float wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
 #pragma unroll 1
     for (int c = 0; c < half_cols; c += 8) {
@@ -499,7 +561,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
       bs_tmem_ld8(taddr + c, v);
       tc_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = __uint_as_float(v[i]) + bv;
+      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[i]), wsc, bv);
     }
     fence_proxy_async();
     bs_sync();
@@ -1012,7 +1074,7 @@ __device__ __noinline__ void bs_final_ln_phase(const BStepArgs& a, float* red) {
 }
 
 // logits[r][v] = xn16[r] . E'[v] + b[v]: whole n-blocks (full K) per CTA group, double-buffered accumulators, direct fp32 stores
-__device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, unsigned char* xs_logits) {
+__device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, unsigned char* xs_logits, unsigned char* ring) {
   int nhalves, Rh, NPh;
   bs_logit_plan(a.R, a.d, kBsKvBytes + a.u_bytes, nhalves, Rh, NPh);
   const int groups = gridDim.x / nhalves, grp = blockIdx.x / nhalves, half = blockIdx.x % nhalves;
@@ -1037,11 +1099,13 @@ __device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, u
 #pragma unroll 1
   for (int nb = grp; nb < NBv; nb += groups, ++it) {
     const int acc = it & 1;
+    if (a.w8) bs_widen_atoms(sh, KA, ring);
     mbar_wait(&sh.acc_full[acc], (uint32_t)sh.acc_par[acc]);
     tc_fence_after();
     const int vidx = nb * 128 + q * 32 + lane;
     const bool vok = vidx < a.vpad;
     const float bv = vok ? __ldg(a.logit_bias + vidx) : 0.f;
+    const float wsc = (a.w8 && vok) ? __ldg(a.logit_scale + vidx) : 1.f;
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + acc * 128 + ch * half_cols;
 #pragma unroll 1
     for (int c = 0; c < half_cols; c += 8) {
@@ -1051,7 +1115,7 @@ __device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, u
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = ch * half_cols + c + i;
-        if (vok && rr < r_n) a.logits[(long long)(r_lo + rr) * a.vpad + vidx] = __uint_as_float(v[i]) + bv;
+        if (vok && rr < r_n) a.logits[(long long)(r_lo + rr) * a.vpad + vidx] = fmaf(__uint_as_float(v[i]), wsc, bv);
       }
     }
     tc_fence_before();
@@ -1087,10 +1151,15 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       sh.prof_i = 1;
       sh.acc_par[0] = sh.acc_par[1] = 0;
       for (int i = 0; i < 8 * 8; ++i) sh.ticks[i] = 0;
-      for (int i = 0; i < kBsSlots; ++i) {
+      for (int i = 0; i < kBsMaxSlots; ++i) {
         mbar_init(&sh.wfull[i], 1);
         mbar_init(&sh.wempty[i], 1);
       }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&sh.ffull[i], 1);
+        mbar_init(&sh.fempty[i], 1);
+      }
+      sh.cons8 = sh.fcnt = 0;
       mbar_init(&sh.xs_ready, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&sh.acc_full[i], 1);
@@ -1121,21 +1190,21 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
 #pragma unroll 1
       for (int ph = 0; ph < 9 && run; ++ph) {
         switch (ph) {
-          case 0: bs_gemm_phase(a, sh, 6 * l + 0, U); break;
+          case 0: bs_gemm_phase(a, sh, 6 * l + 0, U, ring); break;
           case 1: bs_self_attn_phase(a, sh, l, U); break;
           case 2:
             bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer
-            bs_gemm_phase(a, sh, 6 * l + 1, U);
+            bs_gemm_phase(a, sh, 6 * l + 1, U, ring);
             break;
-          case 3: bs_gemm_phase(a, sh, 6 * l + 2, U); break;
+          case 3: bs_gemm_phase(a, sh, 6 * l + 2, U, ring); break;
           case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
           case 5:
             bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer
-            bs_gemm_phase(a, sh, 6 * l + 3, U);
+            bs_gemm_phase(a, sh, 6 * l + 3, U, ring);
             break;
-          case 6: bs_gemm_phase(a, sh, 6 * l + 4, U); break;
+          case 6: bs_gemm_phase(a, sh, 6 * l + 4, U, ring); break;
           case 7: bs_gelu_phase(a, sh, l); break;
-          default: bs_gemm_phase(a, sh, 6 * l + 5, U); break;
+          default: bs_gemm_phase(a, sh, 6 * l + 5, U, ring); break;
         }
         run = bs_enabled(a, ++phase);
         bs_grid_barrier(a, sh);
@@ -1146,7 +1215,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       run = bs_enabled(a, ++phase);
       bs_grid_barrier(a, sh);
     }
-    if (run) bs_logits_phase(a, sh, kv0);
+    if (run) bs_logits_phase(a, sh, kv0, ring);
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
       a.prof[sh.prof_i] = ds_globaltimer();
       for (int k = 0; k < 8; ++k)
@@ -1188,6 +1257,42 @@ __global__ void bs_row_sums_kernel(const __half* __restrict__ W, int N, int K, f
   }
   s = warp_sum(s);
   if (lane == 0) out[row] = s;
+}
+
+// int8 atoms: [128 channels][64 K] bytes, row-major (the widening pass applies the swizzle); rows beyond N hold 128 (= zero)
+__global__ void bs_pack_atoms_i8_kernel(const unsigned char* __restrict__ q, int N, int K, uint4* __restrict__ out) {
+  const int KA = K >> 6;
+  const long long total = (long long)((N + 127) >> 7) * KA * 512;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long atom = idx >> 9;
+    const int w = (int)(idx & 511), i = w >> 2, c = w & 3;
+    const int nb = (int)(atom / KA), ka = (int)(atom - (long long)nb * KA);
+    const int n = nb * 128 + i;
+    uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+    if (n < N) v = *reinterpret_cast<const uint4*>(q + (long long)n * K + ka * 64 + c * 16);
+    out[idx] = v;
+  }
+}
+__global__ void bs_row_sums_i8_kernel(const unsigned char* __restrict__ q, const float* __restrict__ scale, int N, int K, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const unsigned char* w = q + (long long)row * K;
+  int s = 0;
+  for (int k = lane; k < K; k += 32) s += (int)w[k] - 128;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = (float)s * scale[row];
+}
+
+size_t bstep_atoms_bytes_i8(int N, int K) { return (size_t)((N + 127) / 128) * (K / 64) * kBsAtomBytes8; }
+void bstep_pack_atoms_i8(const unsigned char* q, int N, int K, unsigned char* out, cudaStream_t s) {
+  B2W_CHECK(K % 64 == 0 && N % 8 == 0, "bstep_pack_atoms_i8: shape");
+  bs_pack_atoms_i8_kernel<<<1024, 256, 0, s>>>(q, N, K, reinterpret_cast<uint4*>(out));
+  B2W_LAUNCHED();
+}
+void bstep_row_sums_i8(const unsigned char* q, const float* scale, int N, int K, float* out, cudaStream_t s) {
+  bs_row_sums_i8_kernel<<<ceil_div(N, 8), 256, 0, s>>>(q, scale, N, K, out);
+  B2W_LAUNCHED();
 }
 
 size_t bstep_atoms_bytes(int N, int K) { return (size_t)((N + 127) / 128) * (K / 64) * kBsAtomBytes; }

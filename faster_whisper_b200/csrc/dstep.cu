@@ -125,14 +125,6 @@ __device__ __forceinline__ int ds_item(int ntiles, int ksplit, int j) {
 __host__ __device__ __forceinline__ uint32_t ds_tile_bytes(int d, int w8) {
   return w8 ? (uint32_t)(16 * (d + 32) + 128) : (uint32_t)(16 * (d + 32) + 32) * 2u;
 }
-// two biased-uint8 weights (bytes selected by `sel`) -> half2 of their signed values: 0x64xx is 1024 + xx in fp16, minus 1152
-__device__ __forceinline__ uint32_t ds_cvt_u8x2(uint32_t word, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x64646464u), "r"(sel));
-  const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&r), __floats2half2_rn(1152.f, 1152.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 // Weight producer (one thread of a dedicated warp): walks this CTA's work items of the whole step in order and keeps the
 // ring full — wait until the buffer's previous tile has been consumed, then one TMA bulk copy per tile.  It never
 // synchronises with the compute warps other than through the mbarriers, so it runs ahead across phase boundaries.

@@ -450,33 +450,74 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
       q_scratch = dalloc<unsigned char>((size_t)m->vpad * dt > (size_t)4 * dt * dt ? (size_t)m->vpad * dt : (size_t)4 * dt * dt);
       scale_scratch = dalloc<float>((size_t)std::max(m->vpad, 4 * dt));
     }
-    auto pack = [&](const __half* W, const float* bias, int N, int K, int ksplit) -> const __half* {
+    // every decoder matrix is laid out twice: as the <= 8-row kernel's tile stream (dstep.cu) and as the many-row kernel's atom
+    // stream (bstep.cu, + row sums for the deferred LayerNorm); with compute_type int8* both streams carry the int8 values
+    const bool want_b = m->use_bstep && dt % 64 == 0 && dt == 64 * cfg.n_text_head;
+    struct BPack {
+      const void* atoms = nullptr;
+      const float* scale = nullptr;
+      const float* wsum = nullptr;
+    };
+    auto pack = [&](const __half* W, const float* bias, int N, int K, int ksplit, BPack* bp, bool want_wsum) -> const __half* {
+      const __half* tiles = nullptr;
       if (m->w8 || m->w8_fake) {
-        // quantise per output channel; W now holds q * scale (what the prefill / many-row paths multiply with)
+        // quantise per output channel; W now holds q * scale (what the prefill / multi-kernel paths multiply with)
         dstep_quantize_rows(const_cast<__half*>(W), N, K, q_scratch, scale_scratch, m->stream);
-        if (m->w8) {
-          unsigned char* out8 = up.alloc<unsigned char>(dstep_packed_bytes_i8(N, K, ksplit));
-          dstep_pack_tiles_i8(q_scratch, scale_scratch, bias, N, K, ksplit, out8, m->stream);
-          B2W_CUDA(cudaStreamSynchronize(m->stream));  // the scratch buffers are reused by the next matrix
-          return reinterpret_cast<const __half*>(out8);
+      }
+      if (m->w8) {
+        unsigned char* out8 = up.alloc<unsigned char>(dstep_packed_bytes_i8(N, K, ksplit));
+        dstep_pack_tiles_i8(q_scratch, scale_scratch, bias, N, K, ksplit, out8, m->stream);
+        tiles = reinterpret_cast<const __half*>(out8);
+        if (want_b && bp) {
+          unsigned char* a8 = up.alloc<unsigned char>(bstep_atoms_bytes_i8(N, K));
+          bstep_pack_atoms_i8(q_scratch, N, K, a8, m->stream);
+          float* sc = up.alloc<float>((size_t)N);
+          B2W_CUDA(cudaMemcpyAsync(sc, scale_scratch, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, m->stream));
+          bp->atoms = a8;
+          bp->scale = sc;
+          if (want_wsum) {
+            float* wsum = up.alloc<float>((size_t)N);
+            bstep_row_sums_i8(q_scratch, scale_scratch, N, K, wsum, m->stream);
+            bp->wsum = wsum;
+          }
+        }
+      } else {
+        __half* out = up.alloc<__half>(dstep_packed_halves(N, K, ksplit));
+        dstep_pack_tiles(W, bias, N, K, ksplit, out, m->stream);
+        tiles = out;
+        if (want_b && bp) {
+          __half* at = reinterpret_cast<__half*>(up.alloc<unsigned char>(bstep_atoms_bytes(N, K)));
+          bstep_pack_atoms(W, N, K, at, m->stream);
+          bp->atoms = at;
+          if (want_wsum) {
+            float* wsum = up.alloc<float>((size_t)N);
+            bstep_row_sums(W, N, K, wsum, m->stream);
+            bp->wsum = wsum;
+          }
         }
       }
-      __half* out = up.alloc<__half>(dstep_packed_halves(N, K, ksplit));
-      dstep_pack_tiles(W, bias, N, K, ksplit, out, m->stream);
-      B2W_CUDA(cudaStreamSynchronize(m->stream));
-      return out;
+      B2W_CUDA(cudaStreamSynchronize(m->stream));  // the scratch buffers are reused by the next matrix
+      return tiles;
     };
     const bool packable = dt % 64 == 0 && m->vpad % 16 == 0;
+    std::vector<BLayer> bl(L);
     for (int i = 0; i < L && packable; ++i) {
       const DecLayerW& D = m->dec[i];
-      hl[i].wt[0] = pack(D.wqkv, D.bqkv, 3 * dt, dt, 1);
-      hl[i].wt[1] = pack(D.wo, D.bo, dt, dt, 1);
-      hl[i].wt[2] = pack(D.wq_x, D.bq_x, dt, dt, 1);
-      hl[i].wt[3] = pack(D.wo_x, D.bo_x, dt, dt, 1);
-      hl[i].wt[4] = pack(D.w1, D.b1, 4 * dt, dt, 1);
-      hl[i].wt[5] = pack(D.w2, D.b2, dt, 4 * dt, 4);
+      const __half* Ws[6] = {D.wqkv, D.wo, D.wq_x, D.wo_x, D.w1, D.w2};
+      const float* Bs[6] = {D.bqkv, D.bo, D.bq_x, D.bo_x, D.b1, D.b2};
+      const int Ns[6] = {3 * dt, dt, dt, dt, 4 * dt, dt}, Ks[6] = {dt, dt, dt, dt, dt, 4 * dt};
+      for (int j = 0; j < 6; ++j) {
+        BPack bp;
+        const bool ln_in = j == 0 || j == 2 || j == 4;
+        hl[i].wt[j] = pack(Ws[j], Bs[j], Ns[j], Ks[j], j == 5 ? 4 : 1, &bp, ln_in);
+        bl[i].wt[j] = bp.atoms;
+        bl[i].bias[j] = Bs[j];
+        bl[i].scale[j] = bp.scale;
+        if (ln_in) bl[i].wsum[j >> 1] = bp.wsum;
+      }
     }
-    if (packable) m->logit_tiles = pack(m->logit_w, m->logit_b, m->vpad, dt, 1);
+    BPack lp;
+    if (packable) m->logit_tiles = pack(m->logit_w, m->logit_b, m->vpad, dt, 1, &lp, false);
     else m->use_dstep = false;
     if (q_scratch) {
       B2W_CUDA(cudaStreamSynchronize(m->stream));
@@ -485,29 +526,9 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
     }
     m->d_layers = dalloc<DLayer>(L);
     B2W_CUDA(cudaMemcpy(m->d_layers, hl.data(), L * sizeof(DLayer), cudaMemcpyHostToDevice));
-    // the same (possibly de-quantised) weights as the many-row step kernel's atom stream (bstep.cu) + row sums for the deferred LayerNorm
-    if (m->use_bstep && dt % 64 == 0 && dt == 64 * cfg.n_text_head) {
-      std::vector<BLayer> bl(L);
-      auto atoms = [&](const __half* W, int N, int K) -> const __half* {
-        __half* out = reinterpret_cast<__half*>(up.alloc<unsigned char>(bstep_atoms_bytes(N, K)));
-        bstep_pack_atoms(W, N, K, out, m->stream);
-        return out;
-      };
-      auto sums = [&](const __half* W, int N, int K) -> const float* {
-        float* out = up.alloc<float>((size_t)N);
-        bstep_row_sums(W, N, K, out, m->stream);
-        return out;
-      };
-      for (int i = 0; i < L; ++i) {
-        const DecLayerW& D = m->dec[i];
-        bl[i].wt[0] = atoms(D.wqkv, 3 * dt, dt); bl[i].bias[0] = D.bqkv; bl[i].wsum[0] = sums(D.wqkv, 3 * dt, dt);
-        bl[i].wt[1] = atoms(D.wo, dt, dt);       bl[i].bias[1] = D.bo;
-        bl[i].wt[2] = atoms(D.wq_x, dt, dt);     bl[i].bias[2] = D.bq_x; bl[i].wsum[1] = sums(D.wq_x, dt, dt);
-        bl[i].wt[3] = atoms(D.wo_x, dt, dt);     bl[i].bias[3] = D.bo_x;
-        bl[i].wt[4] = atoms(D.w1, 4 * dt, dt);   bl[i].bias[4] = D.b1;   bl[i].wsum[2] = sums(D.w1, 4 * dt, dt);
-        bl[i].wt[5] = atoms(D.w2, dt, 4 * dt);   bl[i].bias[5] = D.b2;
-      }
-      m->logit_atoms = atoms(m->logit_w, m->vpad, dt);
+    if (want_b && packable) {
+      m->logit_atoms = lp.atoms;
+      m->logit_scale = lp.scale;
       m->d_blayers = dalloc<BLayer>(L);
       B2W_CUDA(cudaMemcpy(m->d_blayers, bl.data(), L * sizeof(BLayer), cudaMemcpyHostToDevice));
       m->bstep_packed = true;
@@ -1103,7 +1124,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
   bool use_bstep = m->use_bstep && m->bstep_packed && !sp.fake_logits && !m->use_ref_gemv && (m->bstep_all || !use_dstep) && R <= kBsMaxRows;
   if (use_bstep) {
     bs.layers = m->d_blayers; bs.L = c.n_text_layer; bs.tok_emb = m->tok_emb; bs.pos_emb = m->dec_pos;
-    bs.logit_atoms = m->logit_atoms; bs.logit_bias = m->logit_b;
+    bs.logit_atoms = m->logit_atoms; bs.logit_bias = m->logit_b; bs.logit_scale = m->logit_scale; bs.w8 = m->w8 ? 1 : 0;
     bs.R = R; bs.d = c.n_text_state; bs.H = c.n_text_head; bs.n_ctx = c.n_text_ctx; bs.slots = K; bs.T = 1500;
     bs.vpad = m->vpad; bs.n_vocab = c.n_vocab; bs.n_chunks = n; bs.rows_per_chunk = K;
     bs.stop_phase = m->bstep_stop;
@@ -1208,7 +1229,9 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
       }
       ++steps_run;
       // algorithmic bytes of this step: weights + beam-shared cross-KV + self-KV read so far
-      m->decode_alg_bytes += m->dec_weight_bytes + (double)n * c.n_text_layer * 2.0 * 1500 * c.n_text_state * 2.0 +
+      // (the persistent kernels stream int8 weights with compute_type int8*: half the fp16 bytes; per-channel scales are negligible)
+      m->decode_alg_bytes += ((m->w8 && (use_dstep || use_bstep)) ? 0.5 * m->dec_weight_bytes : m->dec_weight_bytes) +
+                             (double)n * c.n_text_layer * 2.0 * 1500 * c.n_text_state * 2.0 +
                              (double)R * (P + step) * c.n_text_layer * 2.0 * c.n_text_state * 2.0;
       if ((step % poll) == poll - 1 && step + 1 < max_steps) {
         B2W_CUDA(cudaMemcpyAsync(m->h_pinned, &sb.state->n_done, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -133,7 +133,8 @@ struct Model {
   int bstep_stop = 0;        // B2W_BSTEP_STOP=n: run only the first n grid phases of every step (debug)
   bool bstep_packed = false;
   BLayer* d_blayers = nullptr;
-  const __half* logit_atoms = nullptr;
+  const void* logit_atoms = nullptr;
+  const float* logit_scale = nullptr;
   float *d_qkv32 = nullptr, *d_cq32 = nullptr, *d_h32 = nullptr, *d_stats = nullptr;
   __half *d_h16 = nullptr, *d_xn16 = nullptr;
   bool use_mma_xattn = true;  // decode cross attention on mma.sync (dstep.cu) instead of the SIMT kernel (B2W_XATTN_IMPL=simt)

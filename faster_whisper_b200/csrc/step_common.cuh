@@ -32,5 +32,13 @@ __device__ __forceinline__ unsigned long long ds_globaltimer() {
   return t;
 }
 
+// two biased-uint8 weights (bytes selected by `sel`) -> half2 of their signed values: 0x64xx is 1024 + xx in fp16, minus 1152
+__device__ __forceinline__ uint32_t ds_cvt_u8x2(uint32_t word, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x64646464u), "r"(sel));
+  const __half2 h = __hsub2(*reinterpret_cast<const __half2*>(&r), __floats2half2_rn(1152.f, 1152.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 
 }  // namespace b2w

@@ -243,7 +243,9 @@ class WhisperOracle:
             h = self._ln(x, p + ".mlp_ln")
             x = x + self._lin(F.gelu(self._lin(h, p + ".mlp.0")), p + ".mlp.2")
         x = self._ln(x, "decoder.ln")
-        logits = self.q["__logits__"](x) if "__logits__" in self.q else x @ w["decoder.token_embedding.weight"].t()
+        # "decoder.output_projection.weight" (tests of quantised engines only): an output embedding that differs from the input one
+        out_w = w.get("decoder.output_projection.weight", w["decoder.token_embedding.weight"])
+        logits = self.q["__logits__"](x) if "__logits__" in self.q else x @ out_w.t()
         return (logits, cross_atts) if want_cross_att else logits
 
     # ---- logits processors (CT2 semantics, CPU ordering: DisableTokens writes immediately) --------

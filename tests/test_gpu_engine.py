@@ -344,26 +344,3 @@ def test_persistent_step_long_context(micro_ml):
             assert w.min_margin < 2 * LOGIT_TOL, (first, w.min_margin)
         else:
             assert abs(got.scores[0] - w.scores[0]) < 0.05
-
-
-# ---- int8 weight stream (compute_type="int8_float16"): per-channel quantised decoder weights streamed as int8 by the step kernel --
-@pytest.mark.parametrize("beam,n_chunks", [(5, 1), (1, 3)])
-def test_int8_weight_stream_matches_dequantised_fp16(micro_ml, beam, n_chunks):
-    """The int8 tile stream (q + 128 bytes, per-channel scale applied to the fp32 sum) against fp16 tiles holding the same
-    de-quantised values (B2W_W8_FAKE=1): same tokens, scores within fp16 rounding of q * scale."""
-    st = micro_ml["tokens"]
-    feats = features_for(micro_ml, n_chunks, seed=97)
-    prompts = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]] * n_chunks
-    kw = dict(beam_size=beam, max_length=30, return_scores=True, return_no_speech_prob=True)
-    i8 = engine.Whisper(dims=micro_ml["dims"], weights=micro_ml["weights"], tokens=st, device="cuda", compute_type="int8_float16")
-    fake = make_engine(micro_ml, B2W_W8_FAKE="1")
-    fp16 = make_engine(micro_ml)
-    a = i8.generate(i8.encode(feats), prompts, **kw)
-    b = fake.generate(fake.encode(feats), prompts, **kw)
-    c = fp16.generate(fp16.encode(feats), prompts, **kw)
-    for x, y, z in zip(a, b, c):
-        assert x.sequences_ids[0] == y.sequences_ids[0], (x.sequences_ids[0][:10], y.sequences_ids[0][:10])
-        assert abs(x.scores[0] - y.scores[0]) < 5e-3
-        assert abs(x.no_speech_prob - y.no_speech_prob) < 1e-3 * max(1.0, y.no_speech_prob) + 1e-6
-        # quantisation noise vs the unquantised model stays small on the first-step statistics
-        assert abs(x.no_speech_prob - z.no_speech_prob) < 0.2 * max(z.no_speech_prob, 1e-6) + 1e-6
