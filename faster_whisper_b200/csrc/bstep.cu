@@ -848,60 +848,89 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
     BS_ATICK(7, 0, tp);
     const int ngroups16 = (nk + 15) >> 4;
-#pragma unroll 1
-    for (int g16 = warp; g16 < ngroups16; g16 += kBsWarps) {
-      const int kb = g16 * 16;
-      if (kb + 16 > nk) {  // the tail rows of V are multiplied by zero probabilities: make them finite (the TMA never writes them)
-        for (int i = lane; i < (kb + 16 - nk) * 8; i += 32) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    {
+      // this warp's keys of the tile: the 16-key groups `warp` and `warp + 8` (14 groups per tile), processed together so that the two
+      // score chains, the softmax update and the two P V steps overlap
+      const int kbA = warp * 16, kbB = (warp + 8) * 16;
+      const bool hasA = warp < ngroups16, hasB = warp + 8 < ngroups16;
+      const int kb_last = (ngroups16 - 1) * 16;
+      if ((hasB ? kbB : kbA) == kb_last && kb_last + 16 > nk) {  // the tail rows of V are multiplied by zero probabilities: make them finite
+        for (int i = lane; i < (kb_last + 16 - nk) * 8; i += 32) *reinterpret_cast<uint4*>(vt + (nk + (i >> 3)) * 64 + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
       }
-      // ---- S = Q K^T for 16 keys: rows = queries (g), columns = keys (two n8 tiles); 16-byte k-permuted fragments ----
-      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        const int key0 = kb + g, key1 = kb + 8 + g;
+      // ---- S = Q K^T: rows = queries (g), columns = keys (two n8 tiles per group); 16-byte k-permuted fragments ----
+      float sA0[4] = {0.f, 0.f, 0.f, 0.f}, sA1[4] = {0.f, 0.f, 0.f, 0.f}, sB0[4] = {0.f, 0.f, 0.f, 0.f}, sB1[4] = {0.f, 0.f, 0.f, 0.f};
+      if (hasA) {
+        const int key0 = kbA + g, key1 = kbA + 8 + g;
         const int sw0 = (k0 + key0) & 7, sw1 = (k0 + key1) & 7;
         const uint4 ka = *reinterpret_cast<const uint4*>(kt + key0 * 64 + ((t ^ sw0) << 3));
         const uint4 kb4 = *reinterpret_cast<const uint4*>(kt + key0 * 64 + (((4 + t) ^ sw0) << 3));
         const uint4 kc4 = *reinterpret_cast<const uint4*>(kt + key1 * 64 + ((t ^ sw1) << 3));
         const uint4 kd = *reinterpret_cast<const uint4*>(kt + key1 * 64 + (((4 + t) ^ sw1) << 3));
-        ds_mma(s0, qf0.x, 0u, qf0.y, 0u, ka.x, ka.y);
-        ds_mma(s0, qf0.z, 0u, qf0.w, 0u, ka.z, ka.w);
-        ds_mma(s0, qf1.x, 0u, qf1.y, 0u, kb4.x, kb4.y);
-        ds_mma(s0, qf1.z, 0u, qf1.w, 0u, kb4.z, kb4.w);
-        ds_mma(s1, qf0.x, 0u, qf0.y, 0u, kc4.x, kc4.y);
-        ds_mma(s1, qf0.z, 0u, qf0.w, 0u, kc4.z, kc4.w);
-        ds_mma(s1, qf1.x, 0u, qf1.y, 0u, kd.x, kd.y);
-        ds_mma(s1, qf1.z, 0u, qf1.w, 0u, kd.z, kd.w);
+        ds_mma(sA0, qf0.x, 0u, qf0.y, 0u, ka.x, ka.y);
+        ds_mma(sA1, qf0.x, 0u, qf0.y, 0u, kc4.x, kc4.y);
+        ds_mma(sA0, qf0.z, 0u, qf0.w, 0u, ka.z, ka.w);
+        ds_mma(sA1, qf0.z, 0u, qf0.w, 0u, kc4.z, kc4.w);
+        ds_mma(sA0, qf1.x, 0u, qf1.y, 0u, kb4.x, kb4.y);
+        ds_mma(sA1, qf1.x, 0u, qf1.y, 0u, kd.x, kd.y);
+        ds_mma(sA0, qf1.z, 0u, qf1.w, 0u, kb4.z, kb4.w);
+        ds_mma(sA1, qf1.z, 0u, qf1.w, 0u, kd.z, kd.w);
       }
-      // thread (g, t): query g, keys kb + 2t, kb + 2t + 1 (s0[0..1]) and kb + 8 + 2t, + 1 (s1[0..1])
-      const float v00 = (kb + 2 * t < nk) ? s0[0] : -INFINITY, v01 = (kb + 2 * t + 1 < nk) ? s0[1] : -INFINITY;
-      const float v10 = (kb + 8 + 2 * t < nk) ? s1[0] : -INFINITY, v11 = (kb + 9 + 2 * t < nk) ? s1[1] : -INFINITY;
-      float mx = fmaxf(fmaxf(v00, v01), fmaxf(v10, v11));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = __expf(m_run - m_new);  // 0 for the first keys of a piece (m_run = -inf, m_new finite: every group holds a real key)
-      const __half2 p0 = __floats2half2_rn(__expf(v00 - m_new), __expf(v01 - m_new)), p1 = __floats2half2_rn(__expf(v10 - m_new), __expf(v11 - m_new));
-      const float2 pf0 = __half22float2(p0), pf1 = __half22float2(p1);
-      float ps = (pf0.x + pf0.y) + (pf1.x + pf1.y);
-      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-      l_run = fmaf(l_run, alpha, ps);
-      m_run = m_new;
-      const uint32_t pa0 = *reinterpret_cast<const uint32_t*>(&p0), pa2 = *reinterpret_cast<const uint32_t*>(&p1);
-      // ---- O (+)= P V: A = P (rows = queries, 16 keys), B = V via ldmatrix.trans (keys x 8 dims per tile) ----
-      const int mi = lane >> 3, r8 = lane & 7;
-      const int vkey = kb + 8 * (mi & 1) + r8, vsw = (k0 + vkey) & 7;
+      if (hasB) {
+        const int key0 = kbB + g, key1 = kbB + 8 + g;
+        const int sw0 = (k0 + key0) & 7, sw1 = (k0 + key1) & 7;
+        const uint4 ka = *reinterpret_cast<const uint4*>(kt + key0 * 64 + ((t ^ sw0) << 3));
+        const uint4 kb4 = *reinterpret_cast<const uint4*>(kt + key0 * 64 + (((4 + t) ^ sw0) << 3));
+        const uint4 kc4 = *reinterpret_cast<const uint4*>(kt + key1 * 64 + ((t ^ sw1) << 3));
+        const uint4 kd = *reinterpret_cast<const uint4*>(kt + key1 * 64 + (((4 + t) ^ sw1) << 3));
+        ds_mma(sB0, qf0.x, 0u, qf0.y, 0u, ka.x, ka.y);
+        ds_mma(sB1, qf0.x, 0u, qf0.y, 0u, kc4.x, kc4.y);
+        ds_mma(sB0, qf0.z, 0u, qf0.w, 0u, ka.z, ka.w);
+        ds_mma(sB1, qf0.z, 0u, qf0.w, 0u, kc4.z, kc4.w);
+        ds_mma(sB0, qf1.x, 0u, qf1.y, 0u, kb4.x, kb4.y);
+        ds_mma(sB1, qf1.x, 0u, qf1.y, 0u, kd.x, kd.y);
+        ds_mma(sB0, qf1.z, 0u, qf1.w, 0u, kb4.z, kb4.w);
+        ds_mma(sB1, qf1.z, 0u, qf1.w, 0u, kd.z, kd.w);
+      }
+      if (hasA) {  // (a warp without keys in this tile keeps its state untouched)
+        // thread (g, t): query g, keys kb + 2t, kb + 2t + 1 (s*0[0..1]) and kb + 8 + 2t, + 1 (s*1[0..1]) of each group
+        const float a00 = (kbA + 2 * t < nk) ? sA0[0] : -INFINITY, a01 = (kbA + 2 * t + 1 < nk) ? sA0[1] : -INFINITY;
+        const float a10 = (kbA + 8 + 2 * t < nk) ? sA1[0] : -INFINITY, a11 = (kbA + 9 + 2 * t < nk) ? sA1[1] : -INFINITY;
+        const float b00 = (hasB && kbB + 2 * t < nk) ? sB0[0] : -INFINITY, b01 = (hasB && kbB + 2 * t + 1 < nk) ? sB0[1] : -INFINITY;
+        const float b10 = (hasB && kbB + 8 + 2 * t < nk) ? sB1[0] : -INFINITY, b11 = (hasB && kbB + 9 + 2 * t < nk) ? sB1[1] : -INFINITY;
+        float mx = fmaxf(fmaxf(fmaxf(a00, a01), fmaxf(a10, a11)), fmaxf(fmaxf(b00, b01), fmaxf(b10, b11)));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = __expf(m_run - m_new);  // 0 for the first keys of a piece (m_run = -inf, m_new finite: group A always holds a real key)
+        const __half2 pA0 = __floats2half2_rn(__expf(a00 - m_new), __expf(a01 - m_new)), pA1 = __floats2half2_rn(__expf(a10 - m_new), __expf(a11 - m_new));
+        const __half2 pB0 = __floats2half2_rn(__expf(b00 - m_new), __expf(b01 - m_new)), pB1 = __floats2half2_rn(__expf(b10 - m_new), __expf(b11 - m_new));
+        const float2 fA0 = __half22float2(pA0), fA1 = __half22float2(pA1), fB0 = __half22float2(pB0), fB1 = __half22float2(pB1);
+        // l_run is this thread's share of the row sum (its own keys); the four t-lanes are added when the piece is written out
+        l_run = fmaf(l_run, alpha, ((fA0.x + fA0.y) + (fA1.x + fA1.y)) + ((fB0.x + fB0.y) + (fB1.x + fB1.y)));
+        m_run = m_new;
+        const uint32_t paA0 = *reinterpret_cast<const uint32_t*>(&pA0), paA2 = *reinterpret_cast<const uint32_t*>(&pA1);
+        const uint32_t paB0 = *reinterpret_cast<const uint32_t*>(&pB0), paB2 = *reinterpret_cast<const uint32_t*>(&pB1);
+        // ---- O (+)= P V: A = P (rows = queries, 16 keys per group), B = V via ldmatrix.trans (keys x 8 dims per tile) ----
+        const int mi = lane >> 3, r8 = lane & 7;
+        const int vkA = kbA + 8 * (mi & 1) + r8, vswA = (k0 + vkA) & 7;
+        const int vkB = kbB + 8 * (mi & 1) + r8, vswB = (k0 + vkB) & 7;
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t b0, b1, b2, b3;
-        ds_ldmatrix_x4_trans(b0, b1, b2, b3, vt + vkey * 64 + (((2 * dp + (mi >> 1)) ^ vsw) << 3));
-        oacc[2 * dp][0] *= alpha;
-        oacc[2 * dp][1] *= alpha;
-        oacc[2 * dp + 1][0] *= alpha;
-        oacc[2 * dp + 1][1] *= alpha;
-        ds_mma(oacc[2 * dp], pa0, 0u, pa2, 0u, b0, b1);
-        ds_mma(oacc[2 * dp + 1], pa0, 0u, pa2, 0u, b2, b3);
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t b0, b1, b2, b3;
+          ds_ldmatrix_x4_trans(b0, b1, b2, b3, vt + vkA * 64 + (((2 * dp + (mi >> 1)) ^ vswA) << 3));
+          oacc[2 * dp][0] *= alpha;
+          oacc[2 * dp][1] *= alpha;
+          oacc[2 * dp + 1][0] *= alpha;
+          oacc[2 * dp + 1][1] *= alpha;
+          ds_mma(oacc[2 * dp], paA0, 0u, paA2, 0u, b0, b1);
+          ds_mma(oacc[2 * dp + 1], paA0, 0u, paA2, 0u, b2, b3);
+          if (hasB) {
+            ds_ldmatrix_x4_trans(b0, b1, b2, b3, vt + vkB * 64 + (((2 * dp + (mi >> 1)) ^ vswB) << 3));
+            ds_mma(oacc[2 * dp], paB0, 0u, paB2, 0u, b0, b1);
+            ds_mma(oacc[2 * dp + 1], paB0, 0u, paB2, 0u, b2, b3);
+          }
+        }
       }
     }
     const bool piece_ends = (k == nt - 1 || split == S - 1);
@@ -909,9 +938,12 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       float* w = mb + (warp * kBsXQ + g) * 66;
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<float2*>(w + 8 * dt + 2 * t) = make_float2(oacc[dt][0], oacc[dt][1]);
+      float lr = l_run;  // the four t-lanes of a query row hold disjoint shares of the row sum
+      lr += __shfl_xor_sync(0xffffffffu, lr, 1);
+      lr += __shfl_xor_sync(0xffffffffu, lr, 2);
       if (t == 0) {
         w[64] = m_run;
-        w[65] = l_run;
+        w[65] = lr;
       }
     }
     // release the tile (one arrival per warp): buffer 0 always, buffer 1 only when another tile of this phase will use it
