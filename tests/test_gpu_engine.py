@@ -344,3 +344,34 @@ def test_persistent_step_long_context(micro_ml):
             assert w.min_margin < 2 * LOGIT_TOL, (first, w.min_margin)
         else:
             assert abs(got.scores[0] - w.scores[0]) < 0.05
+
+
+# ---- a transformers checkpoint directory (config.json + model.safetensors) loaded by the engine itself ---------------------------------
+def test_engine_loads_hf_safetensors_directory(tmp_path):
+    """`WhisperForConditionalGeneration.save_pretrained` writes the directory (an independent writer), the engine loads it
+    through `faster_whisper_b200.hf_format` and its teacher-forced logits match the oracle built from the original weights."""
+    transformers = pytest.importorskip("transformers")
+    import torch
+
+    from faster_whisper_b200.config import special_tokens
+    from faster_whisper_b200.synthetic import custom_dims, make_weights
+    from oracle.check_against_transformers import to_hf_state
+
+    dims = custom_dims(d=128, heads=2, enc_layers=2, dec_layers=2, n_vocab=51864)
+    w = make_weights(dims, seed=31)
+    cfg = transformers.WhisperConfig(vocab_size=dims.n_vocab, num_mel_bins=dims.n_mels, d_model=dims.n_text_state, encoder_layers=dims.n_audio_layer,
+                                     decoder_layers=dims.n_text_layer, encoder_attention_heads=dims.n_audio_head, decoder_attention_heads=dims.n_text_head,
+                                     encoder_ffn_dim=4 * dims.n_audio_state, decoder_ffn_dim=4 * dims.n_text_state, max_source_positions=1500,
+                                     max_target_positions=448, activation_function="gelu")
+    hf = transformers.WhisperForConditionalGeneration(cfg)
+    hf.load_state_dict(to_hf_state(w, dims), strict=False)
+    hf.save_pretrained(str(tmp_path), safe_serialization=True)
+    e = engine.Whisper(str(tmp_path), device="cuda")
+    assert (e.dims.n_text_state, e.dims.n_text_layer, e.dims.n_vocab) == (dims.n_text_state, dims.n_text_layer, dims.n_vocab)
+    st = special_tokens(dims.n_vocab)
+    o = orc.WhisperOracle(dims.to_dict(), w, st.to_dict())
+    feats = np.stack([orc.pad_or_trim(orc.log_mel(synthetic_audio(77, 30.0), dims.n_mels)[:, :-1])])
+    toks = np.array([[st.sot, st.no_timestamps, 11, 22, 33, 44]], dtype=np.int32)
+    want = o.decoder_forward(torch.from_numpy(toks).long(), 0, [None] * dims.n_text_layer, o.cross_kv(o.encode(feats)), torch.arange(1)).numpy()
+    got = e.debug_logits(e.encode(feats), toks)
+    assert np.abs(got - want).max() < LOGIT_TOL, np.abs(got - want).max()
