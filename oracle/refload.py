@@ -7,6 +7,7 @@ empty modules of those names exist.  ``ctranslate2`` can instead be bound to a s
 Nothing here may be used on the GPU box: /root/reference does not exist there.
 """
 import importlib
+import importlib.machinery
 import os
 import sys
 import types
@@ -26,7 +27,11 @@ def load_reference(ct2_module=None):
         if name == "faster_whisper" or name.startswith("faster_whisper."):
             del sys.modules[name]
     for name in ("av", "av.audio", "av.audio.fifo", "av.audio.resampler", "onnxruntime"):
-        sys.modules.setdefault(name, types.ModuleType(name))
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            # a real spec: importlib.util.find_spec (used by transformers' availability probes) raises on modules whose __spec__ is None
+            stub.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            sys.modules[name] = stub
     if ct2_module is None:
         ct2_module = types.ModuleType("ctranslate2")
         ct2_module.models = types.ModuleType("ctranslate2.models")
