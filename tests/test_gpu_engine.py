@@ -1,7 +1,8 @@
 """-m gpu: the engine (encoder, decoder, on-device search) against the CPU oracle, through the C ABI.
 
-Stated tolerances: encoder activations |err| <= 1e-2 absolute on O(1)-magnitude LayerNorm outputs with
-relative Frobenius error <= 3e-3 (fp16 tensor-core inputs, fp32 accumulate and residual stream); teacher-forced
+Stated tolerances: encoder activations relative Frobenius error < 1e-3 (BASELINE.json's "within 1e-3 on encoder activations", read as a
+relative error: fp16 tensor-core inputs with fp32 accumulation and an fp32 residual stream give 6.8e-4 at large-v3) with the worst single
+element below 1e-2 absolute on O(1)-magnitude LayerNorm outputs (measured 3.7e-3 at large-v3); teacher-forced
 logits <= 0.05 absolute on logits of standard deviation ~4; tokens exact on greedy/beam unless the oracle
 itself reports a near-tie (margin below the logit tolerance) at the first point of divergence.
 """
@@ -60,14 +61,14 @@ def test_encoder_matches_oracle(micro, impl):
     got = e.encode(feats).numpy()
     assert got.shape == want.shape == (2, 1500, micro["dims"].n_audio_state)
     assert np.abs(got - want).max() < 1e-2, np.abs(got - want).max()
-    assert rel_fro(got, want) < 3e-3
+    assert rel_fro(got, want) < 1e-3, rel_fro(got, want)
 
 
 def test_encoder_multilingual_geometry(micro_ml, eng_ml):
     feats = features_for(micro_ml, 3, seed=4)
     want = micro_ml["oracle"].encode(feats).numpy()
     got = eng_ml.encode(feats).numpy()
-    assert np.abs(got - want).max() < 1e-2 and rel_fro(got, want) < 3e-3
+    assert np.abs(got - want).max() < 1e-2 and rel_fro(got, want) < 1e-3, (np.abs(got - want).max(), rel_fro(got, want))
 
 
 def test_encode_audio_fused_path(micro, eng):
@@ -77,7 +78,7 @@ def test_encode_audio_fused_path(micro, eng):
     assert np.abs(feats - want_feats).max() < 2e-3
     want = micro["oracle"].encode(want_feats).numpy()
     got = sv.numpy()
-    assert np.abs(got - want).max() < 1.5e-2 and rel_fro(got, want) < 4e-3
+    assert np.abs(got - want).max() < 1.5e-2 and rel_fro(got, want) < 1.5e-3, (np.abs(got - want).max(), rel_fro(got, want))
 
 
 def test_encode_rejects_bad_shapes(eng, micro):
@@ -309,10 +310,11 @@ def test_large_v3_geometry_matches_oracle():
     err = np.abs(got_enc - want_enc.numpy())
     print("large-v3 encoder: max abs err %.4g, rel Frobenius %.4g" % (err.max(), rel_fro(got_enc, want_enc.numpy())))
     # measured on B200: max abs 3.7e-3 on O(1) activations, relative Frobenius 6.8e-4
-    assert err.max() < 1e-2 and rel_fro(got_enc, want_enc.numpy()) < 1.5e-3
+    assert err.max() < 1e-2 and rel_fro(got_enc, want_enc.numpy()) < 1e-3
     prompt = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]]
     sup = [st.eot, st.sot, st.transcribe, st.translate, st.sot_prev, st.sot_lm, st.no_speech]
-    for beam, n_new, extra in ((1, 10, {}), (1, 10, dict(repetition_penalty=1.4, no_repeat_ngram_size=2)), (5, 8, {})):
+    # the second case free-runs 64 tokens with repetition penalty + n-gram blocking, so every step picks a different token
+    for beam, n_new, extra in ((1, 10, {}), (1, 64, dict(repetition_penalty=1.4, no_repeat_ngram_size=2)), (5, 8, {})):
         kw = dict(beam_size=beam, max_length=len(prompt[0]) + n_new, suppress_tokens=sup, return_scores=True, return_no_speech_prob=True, **extra)
         want = o.generate(want_enc, prompt, **kw)[0]
         got = e.generate(enc, prompt, **kw)[0]
@@ -323,6 +325,50 @@ def test_large_v3_geometry_matches_oracle():
             assert want.min_margin < 2 * LOGIT_TOL, (want.min_margin, got.sequences_ids[0], want.sequences_ids[0])
         else:
             assert abs(got.scores[0] - want.scores[0]) < 0.05
+        if n_new >= 64:
+            assert len(set(got.sequences_ids[0])) > 32  # not a degenerate repetition
+    # two chunks x beam 5 = 10 rows: the many-row persistent kernel (bstep.cu) at the production geometry (UMMA N = 16, 1280-wide atoms)
+    feats2 = np.stack([orc.pad_or_trim(orc.log_mel(synthetic_audio(i, 30.0), dims.n_mels)[:, :-1]) for i in range(2)])
+    want_enc2, enc2 = o.encode(feats2), e.encode(feats2)
+    kw = dict(beam_size=5, max_length=len(prompt[0]) + 10, suppress_tokens=sup, return_scores=True, return_no_speech_prob=True, repetition_penalty=1.3,
+              no_repeat_ngram_size=2)
+    want2, got2 = o.generate(want_enc2, prompt * 2, **kw), e.generate(enc2, prompt * 2, **kw)
+    for w2, g2 in zip(want2, got2):
+        print("large-v3 2 x beam 5 (bstep): tokens %s score %.4f (oracle %.4f, min margin %.3f)" % (g2.sequences_ids[0], g2.scores[0], w2.scores[0], w2.min_margin))
+        if g2.sequences_ids[0] != w2.sequences_ids[0]:
+            assert w2.min_margin < 2 * LOGIT_TOL, (w2.min_margin, g2.sequences_ids[0], w2.sequences_ids[0])
+        else:
+            assert abs(g2.scores[0] - w2.scores[0]) < 0.05
+
+
+def test_in_process_replicas_on_two_gpus(micro_ml):
+    """`device_index=[0, 1]` (reference transcribe.py:646-657: one model replica per GPU behind one object): encoder outputs stay on the GPU
+    that made them and every replica decodes its own chunks; results equal a single-GPU run.  Needs two visible GPUs (skipped otherwise)."""
+    if engine.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import threading
+
+    st = micro_ml["tokens"]
+    both = engine.Whisper(dims=micro_ml["dims"], weights=micro_ml["weights"], tokens=st, device="cuda", device_index=[0, 1])
+    one = make_engine(micro_ml)
+    assert both.device_index == [0, 1]
+    feats = [features_for(micro_ml, 3, seed=500 + 10 * i) for i in range(4)]
+    prompts = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]] * 3
+    kw = dict(beam_size=5, max_length=24, return_scores=True)
+    out = [None] * 4
+
+    def work(i):
+        enc = both.encode(feats[i])  # replicas are handed out round-robin
+        out[i] = both.generate(enc, prompts, **kw)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(4):
+        ref = one.generate(one.encode(feats[i]), prompts, **kw)
+        assert [r.sequences_ids for r in out[i]] == [r.sequences_ids for r in ref]
 
 
 def test_persistent_step_long_context(micro_ml):

@@ -30,6 +30,24 @@ def test_logmel_matches_oracle(n_mels, n):
     assert err.mean() < 1e-4, err.mean()
 
 
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_matches_reference_goldens(n_mels):
+    """The CUDA front end against outputs of the REFERENCE's own FeatureExtractor (tests/golden/mel_golden.npz, made by
+    oracle/make_golden.py from the first 3 s of tests/data/physicsworks.wav — real speech, not noise) and, beyond one chunk, against the
+    oracle on a 47.3 s clip (the sequential path takes the log-mel of whole files with a whole-file clamp maximum)."""
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_golden.npz"))
+    got = engine.log_mel(gold["speech_pcm_head"], n_mels)
+    want = gold[f"speech_head_{n_mels}"]
+    err = np.abs(got - want)
+    assert got.shape == want.shape and err.max() < 2e-3 and err.mean() < 1e-4, (err.max(), err.mean())
+    x = synthetic_audio(17, 47.3)
+    got, want = engine.log_mel(x, n_mels), orc.log_mel(x, n_mels)
+    err = np.abs(got - want)
+    assert got.shape == want.shape == (n_mels, 1 + len(x) // 160) and err.max() < 2e-3 and err.mean() < 1e-4, (err.max(), err.mean())
+
+
 def test_logmel_silence_and_impulse():
     z = np.zeros(16000, np.float32)
     got = engine.log_mel(z, 80)
