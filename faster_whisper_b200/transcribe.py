@@ -356,7 +356,14 @@ class BatchedInferencePipeline:
             if not model.model.is_multilingual:
                 language, language_probability = "en", 1
             else:
-                feats = [model.feature_extractor(c)[..., :-1] for c in audio_chunks[: max(1, language_detection_segments)]]
+                # the reference concatenates the features of ALL chunks and detect_language reads the first
+                # `language_detection_segments` windows of 3000 frames (transcribe.py:478-489): short leading chunks are followed by the
+                # next chunks' frames inside a window.  Only the chunks that reach into those windows are computed here.
+                feats, need = [], max(1, language_detection_segments) * model.feature_extractor.nb_max_frames
+                for c in audio_chunks:
+                    if sum(f.shape[-1] for f in feats) >= need:
+                        break
+                    feats.append(model.feature_extractor(c)[..., :-1])
                 feats.append(np.full((model.model.n_mels, 1), -1.5, dtype="float32"))  # keeps empty audio well-formed
                 language, language_probability, all_language_probs = model.detect_language(
                     features=np.concatenate(feats, axis=1), language_detection_segments=language_detection_segments,

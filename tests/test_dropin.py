@@ -263,3 +263,19 @@ def test_transcribe_with_vad_filter_matches_reference(both):
     finally:
         mp.undo()
         our_vad.set_vad_model(None)
+
+
+def test_batched_language_detection_window_spans_chunks(both):
+    """A short first chunk: the reference's detection window continues into the NEXT chunk's frames (it concatenates all chunk features,
+    transcribe.py:478-489); ours must pick the same language with the same probability and emit the same segments."""
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(80, 8.0), synthetic_audio(81, 30.0), synthetic_audio(82, 5.0)])
+    clips = [{"start": 0.0, "end": 8.0}, {"start": 8.0, "end": 38.0}, {"start": 38.0, "end": 43.0}]
+    kw = dict(beam_size=1, batch_size=2, max_new_tokens=5, vad_filter=False, clip_timestamps=clips, language_detection_segments=2)
+    ref_segs, ref_info = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), **kw)
+    ref_segs = [seg_tuple(s) for s in ref_segs]
+    our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), **kw)
+    our_segs = [seg_tuple(s) for s in our_segs]
+    assert our_info.language == ref_info.language and our_info.language_probability == pytest.approx(ref_info.language_probability)
+    assert [x[0] for x in our_info.all_language_probs[:5]] == [x[0] for x in ref_info.all_language_probs[:5]]
+    assert our_segs == ref_segs and len(ref_segs) >= 3
