@@ -40,6 +40,7 @@ def compare(eng, m, feats, prompts, **kw):
     want = o.generate(o.encode(feats), prompts, return_scores=True, return_no_speech_prob=True, **kw)
     got = eng.generate(eng.encode(feats), prompts, return_scores=True, return_no_speech_prob=True, **kw)
     exact = 0
+    compare.first_divergence = []
     for i, (w, g) in enumerate(zip(want, got)):
         assert abs(g.no_speech_prob - w.no_speech_prob) < 5e-3 * max(1.0, w.no_speech_prob) + 1e-6
         if g.sequences_ids[0] == w.sequences_ids[0]:
@@ -48,6 +49,7 @@ def compare(eng, m, feats, prompts, **kw):
         else:
             first = next((j for j, (x, y) in enumerate(zip(g.sequences_ids[0], w.sequences_ids[0])) if x != y), -1)
             print("chunk %d diverges at token %d, oracle min margin %.4f" % (i, first, w.min_margin))
+            compare.first_divergence.append(first)
             assert w.min_margin < 2 * LOGIT_TOL, (i, first, w.min_margin, g.sequences_ids[0][:12], w.sequences_ids[0][:12])
     return exact, len(want)
 
@@ -101,3 +103,26 @@ def test_many_row_kernel_matches_multikernel_path(micro):
     for x, y in zip(ra, rb):
         if x.sequences_ids[0] == y.sequences_ids[0]:
             assert abs(x.scores[0] - y.scores[0]) < 5e-3
+
+
+def test_many_row_kernel_long_context(micro_ml):
+    """2 chunks x beam 5 for 236 steps: up to 15 sixteen-key blocks per self-attention task, double-buffer wrap-around, slot bytes of all
+    eight 32-key groups; tokens vs the oracle (exact unless the oracle reports a near-tie at the first divergence)."""
+    st = micro_ml["tokens"]
+    eng = make_engine(micro_ml)
+    feats = features_for(micro_ml, 2, seed=330)
+    prompts = [[st.sot, st.lang_begin, st.transcribe, st.no_timestamps]] * 2
+    exact, n = compare(eng, micro_ml, feats, prompts, beam_size=5, max_length=240, suppress_tokens=[st.eot], repetition_penalty=1.3, no_repeat_ngram_size=3)
+    # a divergence (only ever at a near-tie of the oracle, checked in compare) must come late: well past the 192 cached positions
+    assert all(f >= 150 for f in compare.first_divergence), compare.first_divergence
+
+
+@pytest.mark.parametrize("n_chunks,beam,extra", [(2, 8, {}), (7, 5, dict(patience=2.0, length_penalty=0.6)), (5, 3, dict(num_hypotheses=2))])
+def test_many_row_kernel_other_beam_shapes(micro, n_chunks, beam, extra):
+    """8 rows per chunk (the cross-attention task's maximum), an odd number of chunks with patience / length penalty, several hypotheses."""
+    st = micro["tokens"]
+    eng = make_engine(micro)
+    feats = features_for(micro, n_chunks, seed=340)
+    prompts = [[st.sot_prev, 900, 901, st.sot]] * n_chunks  # timestamps on
+    exact, n = compare(eng, micro, feats, prompts, beam_size=beam, max_length=40, repetition_penalty=1.2, no_repeat_ngram_size=3, **extra)
+    assert 2 * exact >= n, (exact, n)
