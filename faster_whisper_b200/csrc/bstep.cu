@@ -602,13 +602,24 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const int ntasks = H * a.R, e0 = 2 * lane;
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
+  // The coherent loads a task starts with (raw q/k/v, statistics: a post-barrier L2 round trip, ~2 500 cycles) are requested one task
+  // ahead, so a warp's second task finds them in registers.
+  float2 nrq = make_float2(0.f, 0.f), nrk = nrq, nrv = nrq, nst = nrq;
+  auto prefetch = [&](int tsk) {
+    const int r = tsk / H, h = tsk - r * H;
+    nst = __ldcg(reinterpret_cast<const float2*>(st) + r);
+    nrq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0)));
+    nrk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0)));
+    nrv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
+  };
+  const int task0 = blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
+  if (task0 < ntasks) prefetch(task0);
 #pragma unroll 1
-  for (int task = blockIdx.x * kBsWarps + warp; task < ntasks; task += gridDim.x * kBsWarps) {
+  for (int task = task0; task < ntasks; task += tstride) {
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
     long long tp = clock64();
-    // ---- everything that does not depend on anything else is requested first: ancestry slots, raw q/k/v, statistics ----
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
     uint32_t slots[4] = {0u, 0u, 0u, 0u};  // lane holds the slot byte of key 32 i + lane for i < 14 (n_ctx <= 448)
 #pragma unroll
@@ -617,11 +628,10 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       const uint32_t sv = (jj < pos) ? (uint32_t)__ldg(anc + jj) : 0u;
       slots[i >> 2] |= sv << (8 * (i & 3));
     }
-    float mean, rstd;
-    bs_row_stats(st, r, d, mean, rstd);
-    const float2 rq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0))),
-                 rk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0))),
-                 rv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
+    const float2 rq = nrq, rk = nrk, rv = nrv;
+    const float mean = nst.x / d;
+    const float rstd = rsqrtf(fmaxf(nst.y / d - mean * mean, 0.f) + 1e-5f);
+    if (task + tstride < ntasks) prefetch(task + tstride);
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
     const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),
