@@ -80,6 +80,12 @@ __device__ __forceinline__ void bs_tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
+// A wave = a contiguous group of chunks (and their rows) that walks the layer phases on its own barrier counter.
+struct BsWave {
+  int r0, Rw, NPw;  // first row, rows, rows padded to the UMMA N
+  int c0, nc;       // first chunk, chunks
+};
+
 struct BsShared {
   BLayer lay[32];
   RowInfo rows[kBsMaxRows];
@@ -99,6 +105,14 @@ struct BsShared {
   uint64_t acc_empty[2];     // accumulator drained (compute -> MMA thread; logits phase only)
   uint64_t kvfull[2];        // cross-attention K/V tile landed
   uint64_t kvfree[2];        // K/V buffer may be overwritten
+  // waves (thread 0 of the compute warps owns the barrier bookkeeping)
+  BsWave wv[kBsMaxWaves];
+  unsigned arrived[kBsMaxWaves];   // this CTA's arrivals on the wave's counter so far
+  unsigned pend_seq[kBsMaxWaves];  // bulk groups committed when the wave's last run ended (its arrival waits for those)
+  unsigned gseq;                   // bulk groups committed so far (thread 0)
+  int pending;                     // bit w: wave w's last run has not been announced yet
+  int kvu[2];                      // uses of the two K/V buffers so far (consumer side; the producer thread keeps its own count)
+  long long t_start;               // B2W_DSTEP_PROF: clock at the start of the current GEMM run (CTA 0, thread 0)
 };
 
 // ---- phase numbering -------------------------------------------------------------------------------------------------------
@@ -168,18 +182,72 @@ __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
   return r;
 }
 
-// Grid barrier (compute warps only): arrive = red.release (cumulative through bar.sync), wait = relaxed polling.
+// ---- barriers (compute warps only) -------------------------------------------------------------------------------------------
+// arrive = red.release (cumulative through bar.sync), wait = relaxed polling.  Counter 0 synchronises the whole grid (embed, final
+// LayerNorm); counter 1 + w belongs to wave w.  A wave's run is announced LAZILY: when it ends the wave is only marked pending;
+// thread 0 makes the arrival (after the run's bulk reductions have completed) at a hook inside the NEXT run — which belongs to
+// another wave and does not depend on it — or at the latest before this CTA waits on the same wave again.  So neither the
+// completion latency of the bulk reductions nor the barrier round trip nor the skew between CTAs is on the critical path as long
+// as another wave has work.
+__device__ __forceinline__ unsigned* bs_bar_ptr(const BStepArgs& a, int i) { return a.bar + kBsBarStride * i; }
+__device__ __forceinline__ void bs_bar_arrive(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+__device__ __forceinline__ void bs_bar_poll(const unsigned* p, unsigned target) {
+  unsigned v;
+  do {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  } while (v < target);
+}
+// thread 0: wait until at most `allowed` of the most recently committed bulk groups are still in flight
+__device__ __forceinline__ void bs_bulk_wait_allow(unsigned allowed) {
+  if (allowed == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  else if (allowed == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+  else if (allowed == 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+}
+// thread 0: announce wave w's last run if that is still pending
+__device__ __forceinline__ void bs_flush_wave(const BStepArgs& a, BsShared& sh, int w) {
+  if (!((sh.pending >> w) & 1)) return;
+  bs_bulk_wait_allow(sh.gseq - sh.pend_seq[w]);
+  bs_fence_async_all();
+  bs_bar_arrive(bs_bar_ptr(a, 1 + w));
+  sh.arrived[w] += 1;
+  sh.pending &= ~(1 << w);
+}
+// thread 0, the hook inside a run: announce every pending wave (their reductions were issued at least one run ago)
+__device__ __forceinline__ void bs_flush_all(const BStepArgs& a, BsShared& sh) {
+  if (sh.pending == 0) return;
+#pragma unroll 1
+  for (int w = 0; w < a.nw; ++w) bs_flush_wave(a, sh, w);
+}
+__device__ __noinline__ void bs_flush_all_ol(const BStepArgs& a, BsShared& sh) { bs_flush_all(a, sh); }  // for the register-starved attention runs
+// all compute threads, after a run of wave w: every global write of the run precedes the bar.sync, so thread 0 may announce it later
+__device__ __forceinline__ void bs_run_end(BsShared& sh, int w) {
+  bs_sync();
+  if (threadIdx.x == 0) {
+    sh.pend_seq[w] = sh.gseq;
+    sh.pending |= 1 << w;
+  }
+}
+// all compute threads, before a run of wave w: every CTA has announced the wave's previous run
+__device__ __noinline__ void bs_wave_wait(const BStepArgs& a, BsShared& sh, int w) {
+  if (threadIdx.x == 0) {
+    bs_flush_wave(a, sh, w);
+    bs_bulk_wait_read();  // the staging tile of the last reduction lives in the multi-purpose region the coming run rewrites
+    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+    bs_bar_poll(bs_bar_ptr(a, 1 + w), sh.arrived[w] * gridDim.x);
+    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();
+    sh.prof_i += 2;
+  }
+  bs_sync();
+}
+// whole-grid barrier (nothing may be pending)
 __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
   bs_sync();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
-    const unsigned target = sh.epoch;
-    unsigned v;
-    do {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
-    } while (v < target);
+    bs_bar_arrive(bs_bar_ptr(a, 0));
+    bs_bar_poll(bs_bar_ptr(a, 0), sh.epoch);
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();
     sh.prof_i += 2;
   }
@@ -205,7 +273,9 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
     const BsRange r = bs_range(a, s);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(sh.lay[s / 6].wt[s % 6]);
 #pragma unroll 1
-    for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
+    for (int w = 0; w < a.nw; ++w)  // every wave streams the CTA's atoms again (the later readers hit L2)
+#pragma unroll 1
+      for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
   int nhalves, Rh, NPh;
@@ -221,10 +291,12 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
 }
 
 // cross-attention tiles (group-major: tile = (chunk * H + head) * splits + split) are dealt out as contiguous runs ("stream-K")
-__device__ __forceinline__ void bs_xrange(const BStepArgs& a, int& t0, int& t1) {
-  const unsigned NT = (unsigned)(kDsXSplits * a.H * a.n_chunks);
-  t0 = (int)(NT * blockIdx.x / gridDim.x);
-  t1 = (int)(NT * (blockIdx.x + 1) / gridDim.x);
+// — per wave: the wave's tiles [base, base + NT) are cut over the whole grid
+__device__ __forceinline__ void bs_xrange(const BStepArgs& a, const BsWave& wv, int& t0, int& t1) {
+  const unsigned NT = (unsigned)(kDsXSplits * a.H * wv.nc);
+  const int base = kDsXSplits * a.H * wv.c0;
+  t0 = base + (int)(NT * blockIdx.x / gridDim.x);
+  t1 = base + (int)(NT * (blockIdx.x + 1) / gridDim.x);
 }
 
 // TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf (one thread).
@@ -243,29 +315,31 @@ __device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer,
   ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, bar);
 }
 
-// K/V producer: the k-th tile of this CTA's run goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile
-// of a layer is fetched as soon as the previous layer released it; buffer 1 lives in the multi-purpose region and is opened
-// by the compute warps when the cross-attention phase starts.
+// K/V producer: the k-th tile of a run goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile of the next run (next wave
+// or next layer) is fetched as soon as the previous run released it; buffer 1 lives in the multi-purpose region and is opened by
+// the compute warps when a cross-attention run starts.  Both sides count the uses of each buffer (mbarrier parities).
 __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, unsigned char* kv0, unsigned char* kv1) {
-  int t0, t1;
-  bs_xrange(a, t0, t1);
-  const int nt = t1 - t0;
-  if (nt == 0) return;
-  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
+  int u0 = 0, u1 = 0;
 #pragma unroll 1
   for (int l = 0; l < a.L; ++l) {
     if (!bs_enabled(a, 1 + 9 * l + 4)) return;
 #pragma unroll 1
-    for (int k = 0; k < nt; ++k) {
-      const int buf = k & 1;
-      if (buf == 0) {
-        const int u = l * n_even + (k >> 1);
-        mbar_wait(&sh.kvfree[0], (uint32_t)((u & 1) ^ 1));
-      } else {
-        const int u = l * n_odd + (k >> 1);
-        mbar_wait(&sh.kvfree[1], (uint32_t)(u & 1));
+    for (int w = 0; w < a.nw; ++w) {
+      int t0, t1;
+      bs_xrange(a, sh.wv[w], t0, t1);
+      const int nt = t1 - t0;
+#pragma unroll 1
+      for (int k = 0; k < nt; ++k) {
+        const int buf = k & 1;
+        if (buf == 0) {
+          mbar_wait(&sh.kvfree[0], (uint32_t)((u0 & 1) ^ 1));
+          u0 += 1;
+        } else {
+          mbar_wait(&sh.kvfree[1], (uint32_t)(u1 & 1));
+          u1 += 1;
+        }
+        bs_issue_cross_kv(a, l, t0 + k, buf ? kv1 : kv0, &sh.kvfull[buf]);
       }
-      bs_issue_cross_kv(a, l, t0 + k, buf ? kv1 : kv0, &sh.kvfull[buf]);
     }
   }
 }
@@ -273,8 +347,6 @@ __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, un
 // MMA thread: per GEMM phase wait for the staged activations, then per atom wait for the weights and issue four K=16 UMMAs.
 __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, unsigned char* ring, unsigned char* xs, unsigned char* xs_logits) {
   const uint32_t tmem = sh.tmem_base;
-  const uint32_t idesc = umma_idesc_f16(128, a.NP, false);
-  const uint32_t xs_tile = (uint32_t)a.NP * 128u;
   int consumed = 0, xs_uses = 0;
   const bool w8 = a.w8 != 0;
   unsigned char* ftiles = ring + (size_t)kBsSlots8 * kBsAtomBytes8;  // int8 path: the two widened fp16 tiles
@@ -305,18 +377,24 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
     if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
     const BsRange r = bs_range(a, s);
     if (r.a1 <= r.a0) continue;
-    mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
-    xs_uses += 1;
-    tc_fence_after();
-    int local = 0;
 #pragma unroll 1
-    for (int sg = 0; sg < r.nseg; ++sg) {
+    for (int w = 0; w < a.nw; ++w) {  // one run per wave: the wave's rows are the N of the UMMAs
+      const int NPw = sh.wv[w].NPw;
+      const uint32_t idesc = umma_idesc_f16(128, NPw, false);
+      const uint32_t xs_tile = (uint32_t)NPw * 128u;
+      mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
+      xs_uses += 1;
+      tc_fence_after();
+      int local = 0;
 #pragma unroll 1
-      for (int i = 0; i < r.n(sg); ++i) {
-        atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
-        local += 1;
+      for (int sg = 0; sg < r.nseg; ++sg) {
+#pragma unroll 1
+        for (int i = 0; i < r.n(sg); ++i) {
+          atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
+          local += 1;
+        }
+        tc_commit(&sh.acc_full[sg]);
       }
-      tc_commit(&sh.acc_full[sg]);
     }
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
@@ -350,6 +428,16 @@ __device__ __noinline__ void bs_zero_f32(float* p, long long n) {  // all comput
     __stcg(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
+// zero the rows [r0, r0 + Rw) of an n-block-major [R x N] buffer (all compute threads of all CTAs)
+__device__ __noinline__ void bs_zero_rows(float* p, int N, int R, int r0, int Rw) {
+  const int per_nb = Rw * 32;  // float4 units of the wave's rows inside one n-block
+  const int total = ((N + 127) >> 7) * per_nb;
+  for (int i = blockIdx.x * kBsThreads + threadIdx.x; i < total; i += gridDim.x * kBsThreads) {
+    const int nb = i / per_nb, rem = i - nb * per_nb;
+    __stcg(reinterpret_cast<float4*>(p + ((long long)nb * R + r0) * 128) + rem, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
+}
+
 // The fp32 split-K accumulation buffers (x, qkv32, cq32, h32) are stored n-block-major: element (row r, channel n) lives at
 // ((n >> 7) * R + r) * 128 + (n & 127), so that the [R x 128] output tile of a GEMM segment is ONE contiguous block and its
 // reduction into L2 is a single cp.reduce.async.bulk (bulk instructions are warp-uniform: one per row would serialise 80 issues).
@@ -378,25 +466,21 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
   rstd = rsqrtf(fmaxf(s.y / d - mean * mean, 0.f) + 1e-5f);
 }
 
-// Stage this CTA's activation slices as UMMA B tiles: tile i = [NP rows][64 K values] fp16, 128-byte swizzle, rows >= R zero.
-//   X == true : source = fp32 residual stream (converted raw; the LayerNorm is applied by the consumer of the GEMM output);
-//               segments of n-block 0 also accumulate sum(x), sum(x^2) of their K slice into `st`
-//   X == false: source = fp16 activations [R][ld]
-// Stage this CTA's activation slices as UMMA B tiles: tile i = [NP rows][64 K values] fp16, 128-byte swizzle, rows >= R zero.
+// Stage this CTA's activation slices of one wave as UMMA B tiles: tile i = [NPw rows][64 K values] fp16, 128-byte swizzle, rows
+// beyond the wave's zero.
 //   X == true : source = fp32 residual stream, n-block-major (converted raw; the LayerNorm is applied by the consumer of the GEMM
 //               output); sum(x), sum(x^2) of every K slice are accumulated into `st` by exactly one of the CTAs that stage it
 //   X == false: source = fp16 activations [R][ld]
-// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); three (fp32) or four (fp16) tiles
-// are in flight together.
-template <bool X>
-__device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src, int ld, float* st, unsigned char* xs) {
+// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); PASSES = 32-row passes that
+// cover the wave's rows; as many tiles as the registers allow are in flight together (one memory round trip per group).
+template <bool X, int PASSES>
+__device__ __noinline__ void bs_stage(const BStepArgs& a, int s, int r0, int Rw, int NPw, const void* src, int ld, float* st, unsigned char* xs) {
   const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
-  const int tid = threadIdx.x, NP = a.NP, R = a.R;
+  const int tid = threadIdx.x, R = a.R;
   const int nblocks = (((s % 6) == 0 ? 3 * a.d : ((s % 6) == 4 ? 4 * a.d : a.d)) + 127) >> 7;
   const int natoms = rg.a1 - rg.a0;
   const int c = tid & 7, r_lo = tid >> 3;
-  constexpr int PASSES = 3;  // 96 rows >= NP (<= 80)
-  constexpr int GRP = X ? 3 : 4;
+  constexpr int GRP = X ? (PASSES == 3 ? 3 : (PASSES == 2 ? 4 : 6)) : (PASSES == 3 ? 4 : 6);
 #pragma unroll 1
   for (int i0 = 0; i0 < natoms; i0 += GRP) {
     uint4 v0[GRP][PASSES], v1[X ? GRP : 1][X ? PASSES : 1];
@@ -413,14 +497,14 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
         const int r = r_lo + 32 * p;
         v0[ii][p] = make_uint4(0u, 0u, 0u, 0u);
         if constexpr (X) v1[ii][p] = make_uint4(0u, 0u, 0u, 0u);
-        if (on && r < R) {
+        if (on && r < Rw) {
           if constexpr (X) {
-            const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r, ka * 64 + c * 8));
+            const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r0 + r, ka * 64 + c * 8));
             const float4 f0 = __ldcg(ptr), f1 = __ldcg(ptr + 1);
             v0[ii][p] = *reinterpret_cast<const uint4*>(&f0);
             v1[ii][p] = *reinterpret_cast<const uint4*>(&f1);
           } else {
-            v0[ii][p] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)r * ld + ka * 64 + c * 8));
+            v0[ii][p] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)(r0 + r) * ld + ka * 64 + c * 8));
           }
         }
       }
@@ -429,7 +513,7 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
     for (int ii = 0; ii < GRP; ++ii) {
       const int i = i0 + ii;
       if (i >= natoms) break;
-      unsigned char* tile = xs + (size_t)i * (NP * 128);
+      unsigned char* tile = xs + (size_t)i * (NPw * 128);
 #pragma unroll
       for (int p = 0; p < PASSES; ++p) {
         const int r = r_lo + 32 * p;
@@ -445,19 +529,38 @@ __device__ __noinline__ void bs_stage(const BStepArgs& a, int s, const void* src
             s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
             s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
             s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-            if (c == 0 && r < R) {
-              atomicAdd(st + 2 * r, s1);
-              atomicAdd(st + 2 * r + 1, s2);
+            if (c == 0 && r < Rw) {
+              atomicAdd(st + 2 * (r0 + r), s1);
+              atomicAdd(st + 2 * (r0 + r) + 1, s2);
             }
           }
-          if (r < NP)
+          if (r < NPw)
             *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) =
                 make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
         } else {
-          if (r < NP) *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v0[ii][p];
+          if (r < NPw) *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v0[ii][p];
         }
       }
     }
+  }
+}
+// Staging of GEMM s for wave w, out of line and called first thing in a run: only a handful of values are live across the
+// call (every value that is costs a local-memory round trip, and with 220 KB of shared memory the L1 is tiny).
+__device__ __noinline__ void bs_stage_run(const BStepArgs& a, const BsShared& sh, int s, int w, unsigned char* xs) {
+  const int l = s / 6, j = s - 6 * l, d = a.d;
+  const int r0 = sh.wv[w].r0, Rw = sh.wv[w].Rw, NPw = sh.wv[w].NPw;
+  const int passes = NPw <= 32 ? 1 : (NPw <= 64 ? 2 : 3);
+  if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream + LayerNorm statistics
+    float* st = a.stats + (long long)(3 * l + (j >> 1)) * a.R * 2;
+    if (passes == 1) bs_stage<true, 1>(a, s, r0, Rw, NPw, a.x, d, st, xs);
+    else if (passes == 2) bs_stage<true, 2>(a, s, r0, Rw, NPw, a.x, d, st, xs);
+    else bs_stage<true, 3>(a, s, r0, Rw, NPw, a.x, d, st, xs);
+  } else {
+    const __half* src = j == 5 ? a.h16 : a.ao;
+    const int ld = j == 5 ? 4 * d : d;
+    if (passes == 1) bs_stage<false, 1>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
+    else if (passes == 2) bs_stage<false, 2>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
+    else bs_stage<false, 3>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
   }
 }
 
@@ -500,6 +603,15 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
   bs_sync();
 }
 
+// cycle counters inside the attention loops: compiled in only with -DB2W_BSTEP_TICKS (they hold two registers across loops that
+// have none to spare)
+#ifndef B2W_BSTEP_TICKS
+#define BS_ATICK(kind, point, tp) do { } while (0)
+#define BS_ATICK_DECL(tp)
+#define BS_ATICK_COUNT(kind) do { } while (0)
+#else
+#define BS_ATICK_DECL(tp) long long tp = clock64()
+#define BS_ATICK_COUNT(kind) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) sh.ticks[(kind) * 8 + 7] += 1; } while (0)
 #define BS_ATICK(kind, point, tp)                                        \
   do {                                                                   \
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -508,6 +620,7 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
       (tp) = _now;                                                       \
     }                                                                    \
   } while (0)
+#endif
 
 #define BS_TICK(point)                                                   \
   do {                                                                   \
@@ -518,67 +631,70 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
     }                                                                    \
   } while (0)
 
-__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U, unsigned char* ring) {
-  const BsRange rg = bs_range(a, s);
-  if (rg.a1 <= rg.a0) return;
-  const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long tp = clock64();
-  const BLayer& lay = sh.lay[l];
-  float* out;
-  int N;
-  const float* bias = nullptr;
-  switch (j) {
-    case 0: out = a.qkv32; N = 3 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l) * a.R * 2, U); break;
-    case 1: out = a.x; N = d; bias = lay.bias[1]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
-    case 2: out = a.cq32; N = d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 1) * a.R * 2, U); break;
-    case 3: out = a.x; N = d; bias = lay.bias[3]; bs_stage<false>(a, s, a.ao, d, nullptr, U); break;
-    case 4: out = a.h32; N = 4 * d; bs_stage<true>(a, s, a.x, d, a.stats + (long long)(3 * l + 2) * a.R * 2, U); break;
-    default: out = a.x; N = d; bias = lay.bias[5]; bs_stage<false>(a, s, a.h16, 4 * d, nullptr, U); break;
+__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, int w, unsigned char* U, unsigned char* ring) {
+  {
+    const BsRange r0 = bs_range(a, s);
+    if (r0.a1 <= r0.a0) {  // no atoms of this matrix here: only the lazy arrivals of the other waves
+      if (threadIdx.x == 0) bs_flush_all(a, sh);
+      return;
+    }
   }
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) sh.t_start = clock64();
+  bs_stage_run(a, sh, s, w, U);
+  const BsRange rg = bs_range(a, s);
+  const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long tp = (a.prof && blockIdx.x == 0 && tid == 0) ? sh.t_start : 0;
+  const BLayer& lay = sh.lay[l];
+  const BsWave wv = sh.wv[w];
+  float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
+  const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
+  const float* bias = (j == 1 || j == 3 || j == 5) ? lay.bias[j] : nullptr;
   fence_proxy_async();
   bs_sync();
-  if (tid == 0) mbar_arrive(&sh.xs_ready);
+  if (tid == 0) {
+    mbar_arrive(&sh.xs_ready);
+    bs_flush_all(a, sh);  // the hook: the other waves' reductions were issued a whole run ago
+  }
   BS_TICK(0);
   if (a.w8) bs_widen_atoms(sh, rg.a1 - rg.a0, ring);
-  // all accumulators of the phase must be complete before the staging tile (which aliases the activation tiles) is written
+  // all accumulators of the run must be complete before the staging tile (which aliases the activation tiles) is written
   for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
   tc_fence_after();
   bs_sync();
   BS_TICK(1);
   if (tid == 0)
     for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
-  float* stg = reinterpret_cast<float*>(U);  // [NP][128] fp32
-  const int q = warp & 3, ch = warp >> 2, half_cols = a.NP >> 1;
+  float* stg = reinterpret_cast<float*>(U);  // [NPw][128] fp32
+  const int q = warp & 3, ch = warp >> 2, half_cols = wv.NPw >> 1, nch8 = half_cols >> 3;  // half_cols is a multiple of 8, <= 40
 #pragma unroll 1
   for (int sg = 0; sg < rg.nseg; ++sg) {
     const int n_glob = rg.nb(sg) * 128 + q * 32 + lane;
     const float bv = (bias && rg.ka0(sg) == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
     const float wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
-#pragma unroll 1
-    for (int c = 0; c < half_cols; c += 8) {
-      uint32_t v[8];
-      bs_tmem_ld8(taddr + c, v);
-      tc_wait_ld();
+    uint32_t v[5][8];  // all of the warp's columns are requested before the one wait
 #pragma unroll
-      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[i]), wsc, bv);
-    }
+    for (int c8 = 0; c8 < 5; ++c8)
+      if (c8 < nch8) bs_tmem_ld8(taddr + 8 * c8, v[c8]);
+    tc_wait_ld();
+#pragma unroll
+    for (int c8 = 0; c8 < 5; ++c8)
+      if (c8 < nch8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) stg[(ch * half_cols + 8 * c8 + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[c8][i]), wsc, bv);
+      }
     fence_proxy_async();
     bs_sync();
-    if (tid == 0) {  // rows 0 .. R-1 of the staging tile = the segment's contiguous [R x 128] block of the n-block-major output
-      bs_bulk_reduce_f32(out + (long long)rg.nb(sg) * a.R * 128, stg, (uint32_t)a.R * 512u);
+    if (tid == 0) {  // rows 0 .. Rw-1 of the staging tile = the wave's contiguous [Rw x 128] block of the n-block-major output
+      bs_bulk_reduce_f32(out + ((long long)rg.nb(sg) * a.R + wv.r0) * 128, stg, (uint32_t)wv.Rw * 512u);
       bs_bulk_commit();
+      sh.gseq += 1;
       if (sg + 1 < rg.nseg) bs_bulk_wait_read();
     }
     if (sg + 1 < rg.nseg) bs_sync();
   }
   tc_fence_before();
   BS_TICK(2);
-  if (tid == 0) {
-    bs_bulk_wait_all();
-    bs_fence_async_all();
-  }
-  BS_TICK(3);
   if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[j * 8 + 7] += 1;
 }
 
@@ -589,7 +705,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
 // touches 4 cache lines, not 32 — and double buffered: the copies of block b + 1 are in flight while block b is scored.  With only
 // eight compute warps per SM this is what keeps enough bytes in flight (registers cannot: 64 data registers per block spill).
 constexpr int kBsSelfTile = 2 * 2 * 16 * 64 * 2;  // per warp: two buffers x (K + V) x 16 keys x 64 halves = 8 KB
-__device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
+__device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, int w, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
   __half* tiles = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [buf][K|V][16 keys][64]; 16-byte chunks at chunk ^ (key & 7)
@@ -599,7 +715,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
   __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
-  const int ntasks = H * a.R, e0 = 2 * lane;
+  const int ntasks = H * (sh.wv[w].r0 + sh.wv[w].Rw), e0 = 2 * lane;  // the wave's (row, head) tasks are [H r0, ntasks)
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
   // The coherent loads a task starts with (raw q/k/v, statistics: a post-barrier L2 round trip, ~2 500 cycles) are requested one task
@@ -612,14 +728,14 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
     nrk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0)));
     nrv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
   };
-  const int task0 = blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
+  const int task0 = H * sh.wv[w].r0 + blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
   if (task0 < ntasks) prefetch(task0);
 #pragma unroll 1
   for (int task = task0; task < ntasks; task += tstride) {
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
-    long long tp = clock64();
+    BS_ATICK_DECL(tp);
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
     uint32_t slots[4] = {0u, 0u, 0u, 0u};  // lane holds the slot byte of key 32 i + lane for i < 14 (n_ctx <= 448)
 #pragma unroll
@@ -759,7 +875,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       }
       __syncwarp();  // the buffer may be refilled by the copies issued in the next iteration
       BS_ATICK(6, 3, tp);
-      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
+      BS_ATICK_COUNT(6);
     }
     float l_run = l_part;
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
@@ -771,6 +887,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(o + 8 * dt) = pack_half2(oacc[dt][0] * inv, oacc[dt][1] * inv);
     }
   }
+  if (tid == 0) bs_flush_all_ol(a, sh);  // the hook: after this thread's tasks (one or two of them)
 }
 
 // Beam-shared cross attention, stream-K over key tiles.  The 1500 keys of a (chunk, head) group are 7 tiles of ~214 keys; all
@@ -779,22 +896,26 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
 // sum per query in shared memory, output accumulators in registers across the tiles of a group.  A group that lies entirely inside
 // one run is written straight to `ao`; a group cut by a run boundary leaves one partial record per piece and the piece that
 // completes the group (ticket = tiles done) merges them.  With 16 chunks a run is ~15 tiles: two groups whole, two cut.
-__device__ __forceinline__ bool bs_piece_starts_at(int t, unsigned NT) {  // is tile t the first tile of some CTA's run?
+__device__ __forceinline__ bool bs_piece_starts_at(int t, unsigned NT) {  // is tile t (wave-relative) the first tile of some CTA's run?
   const unsigned G = gridDim.x;
   const unsigned c = ((unsigned)(t + 1) * G + NT - 1) / NT - 1;
   return (int)(NT * c / G) == t;
 }
 
-__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* kv0, unsigned char* U) {
+__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, int w, unsigned char* kv0, unsigned char* U) {
   int t0, t1;
-  bs_xrange(a, t0, t1);
+  bs_xrange(a, sh.wv[w], t0, t1);
   const int nt = t1 - t0;
-  if (nt == 0) return;
-  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
+  if (nt == 0) {
+    if (threadIdx.x == 0) bs_flush_all_ol(a, sh);
+    return;
+  }
+  const int ku0 = sh.kvu[0], ku1 = sh.kvu[1];  // uses of the two K/V buffers before this run
   const int T = a.T, S = kDsXSplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nq = a.rows_per_chunk, d = a.d;
-  const unsigned NT = (unsigned)(S * a.H * a.n_chunks);
+  const unsigned NT = (unsigned)(S * a.H * sh.wv[w].nc);  // tiles of the wave
+  const int tbase = S * a.H * sh.wv[w].c0;
   unsigned char* kv1 = U;
   unsigned char* scratch = U + kBsKvBytes;
   __half* qs_all = reinterpret_cast<__half*>(scratch);                          // [kBsXGroups][8][96], pre-scaled by 1/8
@@ -840,7 +961,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     const int tile = t0 + k, grp = tile / S, split = tile - grp * S, gi = grp - g_first;
     const int buf = k & 1;
     unsigned char* kvbuf = buf ? kv1 : kv0;
-    const int u = l * (buf ? n_odd : n_even) + (k >> 1);
+    const int u = (buf ? ku1 : ku0) + (k >> 1);
     const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
     const __half* kt = reinterpret_cast<const __half*>(kvbuf);  // [224][64], 16-byte chunks at chunk ^ (encoder position & 7)
     __half* vt = reinterpret_cast<__half*>(kvbuf) + kDsXKeysMax * 64;
@@ -854,7 +975,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       qf0 = *reinterpret_cast<const uint4*>(qs + 8 * t);
       qf1 = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
     }
-    long long tp = clock64();
+    BS_ATICK_DECL(tp);
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
     BS_ATICK(7, 0, tp);
     const int ngroups16 = (nk + 15) >> 4;
@@ -959,8 +1080,9 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     // release the tile (one arrival per warp): buffer 0 always, buffer 1 only when another tile of this phase will use it
     __syncwarp();
     if (lane == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
+    if (k == 0 && tid == 0) bs_flush_all_ol(a, sh);  // the hook: after the first tile
     BS_ATICK(7, 1, tp);
-    if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[7 * 8 + 7] += 1;
+    BS_ATICK_COUNT(7);
     if (!piece_ends) continue;
     bs_sync();
     const int h = grp % a.H, b = grp / a.H, row0 = b * nq;
@@ -998,7 +1120,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       if (sh.flag) {  // this piece completed the group: merge the pieces (their first splits are where some CTA's run starts, or 0)
         const float* pg = a.xpart + (long long)grp * S * (kBsXQ * 66);
         unsigned present = 1u;
-        for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2, NT) ? (1u << s2) : 0u;
+        for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2 - tbase, NT) ? (1u << s2) : 0u;
 #pragma unroll 1
         for (int i = tid; i < nq * 64; i += kBsThreads) {
           const int q = i >> 6, e = i & 63;
@@ -1028,16 +1150,20 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     bs_sync();  // the per-warp partials are reused by the next piece
     BS_ATICK(7, 2, tp);
   }
+  if (tid == 0) {  // (the last tile of a run always ends a piece: every thread passed its bar.sync after reading the counts)
+    sh.kvu[0] = ku0 + ((nt + 1) >> 1);
+    sh.kvu[1] = ku1 + (nt >> 1);
+  }
 }
 
 // h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums.
 // Three float4 per thread are in flight together (one memory round trip for a CTA's whole slice at 80 rows).
-__device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l) {
-  const int d = a.d, R = a.R;
+__device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l, int w) {
+  const int d = a.d, R = a.R, wr0 = sh.wv[w].r0;
   const BLayer& lay = sh.lay[l];
   const float* st = a.stats + (long long)(3 * l + 2) * R * 2;
   const int per_row = d;  // float4 units per row of 4d
-  const int total = R * per_row, stride = gridDim.x * kBsThreads;
+  const int total = sh.wv[w].Rw * per_row, stride = gridDim.x * kBsThreads;
   constexpr int UNR = 3;
 #pragma unroll 1
   for (int i0 = blockIdx.x * kBsThreads + threadIdx.x; i0 < total; i0 += UNR * stride) {
@@ -1046,7 +1172,7 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const int i = min(i0 + u * stride, total - 1);  // clamped: the loads are unconditional, only the stores are predicated
-      const int r = i / per_row, n = (i - r * per_row) * 4;
+      const int rl = i / per_row, n = (i - rl * per_row) * 4, r = wr0 + rl;
       hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + bs_bidx(R, r, n)));
       w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
       bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
@@ -1056,7 +1182,7 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
     for (int u = 0; u < UNR; ++u) {
       const int i = i0 + u * stride;
       if (i < total) {
-        const int r = i / per_row, n = (i - r * per_row) * 4;
+        const int rl = i / per_row, n = (i - rl * per_row) * 4, r = wr0 + rl;
         const float mean = sv[u].x / d;
         const float rstd = rsqrtf(fmaxf(sv[u].y / d - mean * mean, 0.f) + 1e-5f);
         const float mr = mean * rstd;
@@ -1067,6 +1193,7 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
       }
     }
   }
+  if (threadIdx.x == 0) bs_flush_all(a, sh);  // the hook (a short run: at its end)
 }
 
 // xn16[r] = (x[r] - mean) * rstd  (CTA r; the final LayerNorm's affine part is folded into the output embedding)
@@ -1170,6 +1297,33 @@ __device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, u
   }
 }
 
+// One run = phase ph of layer l for wave w (compute warps).  Out of line, with the shared-memory carve-up recomputed inside, so
+// that the phase loop of the kernel keeps next to nothing live across the calls.
+__device__ __noinline__ void bs_layer_run(const BStepArgs& a, BsShared& sh, int l, int ph, int w, unsigned char* smem) {
+  unsigned char* ring = smem;
+  unsigned char* kv0 = ring + (size_t)kBsSlots * kBsAtomBytes;
+  unsigned char* U = kv0 + kBsKvBytes;
+  bs_wave_wait(a, sh, w);
+  switch (ph) {
+    case 0: bs_gemm_phase(a, sh, 6 * l + 0, w, U, ring); break;
+    case 1: bs_self_attn_phase(a, sh, l, w, U); break;
+    case 2:
+      bs_zero_rows(a.qkv32, 3 * a.d, a.R, sh.wv[w].r0, sh.wv[w].Rw);  // consumed by the self-attention of this layer
+      bs_gemm_phase(a, sh, 6 * l + 1, w, U, ring);
+      break;
+    case 3: bs_gemm_phase(a, sh, 6 * l + 2, w, U, ring); break;
+    case 4: bs_cross_attn_phase(a, sh, l, w, kv0, U); break;
+    case 5:
+      bs_zero_rows(a.cq32, a.d, a.R, sh.wv[w].r0, sh.wv[w].Rw);  // consumed by the cross attention of this layer
+      bs_gemm_phase(a, sh, 6 * l + 3, w, U, ring);
+      break;
+    case 6: bs_gemm_phase(a, sh, 6 * l + 4, w, U, ring); break;
+    case 7: bs_gelu_phase(a, sh, l, w); break;
+    default: bs_gemm_phase(a, sh, 6 * l + 5, w, U, ring); break;
+  }
+  bs_run_end(sh, w);
+}
+
 __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_param) {
   extern __shared__ unsigned char bs_smem_raw[];
   __shared__ BStepArgs a_sh;
@@ -1202,6 +1356,20 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
         mbar_init(&sh.fempty[i], 1);
       }
       sh.cons8 = sh.fcnt = 0;
+      sh.gseq = 0;
+      sh.pending = 0;
+      sh.kvu[0] = sh.kvu[1] = 0;
+      for (int w = 0; w < kBsMaxWaves; ++w) {
+        sh.arrived[w] = 0;
+        sh.pend_seq[w] = 0;
+        BsWave v;
+        v.c0 = w < a.nw ? a.n_chunks * w / a.nw : a.n_chunks;
+        v.nc = w < a.nw ? a.n_chunks * (w + 1) / a.nw - v.c0 : 0;
+        v.r0 = v.c0 * a.rows_per_chunk;
+        v.Rw = v.nc * a.rows_per_chunk;
+        v.NPw = bs_ceil16(v.Rw);
+        sh.wv[w] = v;
+      }
       mbar_init(&sh.xs_ready, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&sh.acc_full[i], 1);
@@ -1224,33 +1392,24 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
     if (threadIdx.x == kBsThreads + 64) bs_mma_thread(a, sh, ring, U, kv0);
   } else {
     int phase = 0;  // grid phases executed so far
+    const int nw = a.nw;
     bs_embed_phase(a, sh);
     bool run = bs_enabled(a, ++phase);  // phase 0 done after the barrier; `phase` is the index of the next one
     bs_grid_barrier(a, sh);
+    // The waves walk the nine phases of every layer one behind the other.  A run of wave w starts when every CTA has announced
+    // the wave's previous run; it never waits for another wave, whose runs fill the time a dependency needs to resolve.
 #pragma unroll 1
     for (int l = 0; l < L && run; ++l) {
 #pragma unroll 1
       for (int ph = 0; ph < 9 && run; ++ph) {
-        switch (ph) {
-          case 0: bs_gemm_phase(a, sh, 6 * l + 0, U, ring); break;
-          case 1: bs_self_attn_phase(a, sh, l, U); break;
-          case 2:
-            bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer
-            bs_gemm_phase(a, sh, 6 * l + 1, U, ring);
-            break;
-          case 3: bs_gemm_phase(a, sh, 6 * l + 2, U, ring); break;
-          case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
-          case 5:
-            bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer
-            bs_gemm_phase(a, sh, 6 * l + 3, U, ring);
-            break;
-          case 6: bs_gemm_phase(a, sh, 6 * l + 4, U, ring); break;
-          case 7: bs_gelu_phase(a, sh, l); break;
-          default: bs_gemm_phase(a, sh, 6 * l + 5, U, ring); break;
-        }
+#pragma unroll 1
+        for (int w = 0; w < nw; ++w) bs_layer_run(a, sh, l, ph, w, smem);
         run = bs_enabled(a, ++phase);
-        bs_grid_barrier(a, sh);
       }
+    }
+    if (run || a.stop_phase > 0) {  // every wave's last run has to be complete (and announced) before anything reads across waves
+#pragma unroll 1
+      for (int w = 0; w < nw; ++w) bs_wave_wait(a, sh, w);
     }
     if (run) {
       bs_final_ln_phase(a, red);
@@ -1361,6 +1520,7 @@ static int bstep_max_dynamic_smem() {
 void bstep_configure() { B2W_CUDA(cudaFuncSetAttribute(bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bstep_max_dynamic_smem())); }
 
 int bstep_phase_count(int L) { return 3 + 9 * L; }
+int bstep_sync_points(int L, int nw) { return 2 + 9 * L * nw + nw; }  // barrier waits of one launch, in order (profile stamps)
 
 size_t bstep_xpart_floats(const BStepArgs& a) { return (size_t)a.n_chunks * a.H * kDsXSplits * kBsXQ * 66; }
 
@@ -1371,6 +1531,8 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
     const int NT = kDsXSplits * a.H * a.n_chunks, run = (NT + num_sms - 1) / num_sms;
     if ((run + kDsXSplits - 1) / kDsXSplits + 1 > kBsXGroups) return false;
   }
+  if (a.R != a.n_chunks * a.rows_per_chunk) return false;  // rows are chunk-major: a wave is a contiguous range of both
+  a.nw = std::max(1, std::min(std::min(a.nw, kBsMaxWaves), a.n_chunks));
   a.NP = bs_ceil16(a.R);
   const int d = a.d, G = num_sms;
   // activation tiles of the busiest GEMM phase (an even share of the atoms, rounded up) and the condition for two segments
@@ -1402,7 +1564,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
 
 void bstep_launch(const BStepArgs& a, int grid, cudaStream_t s) {
   const size_t smem = bstep_smem_bytes(a);
-  B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
+  B2W_CUDA(cudaMemsetAsync(a.bar, 0, (size_t)(1 + kBsMaxWaves) * kBsBarStride * sizeof(unsigned), s));
   BStepArgs copy = a;
   void* args[] = {&copy};
   B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bstep_kernel), dim3(grid), dim3(kBsLaunch), args, smem, s));
