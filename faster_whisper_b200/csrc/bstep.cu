@@ -231,11 +231,21 @@ __device__ __forceinline__ void bs_run_end(BsShared& sh, int w) {
 // all compute threads, before a run of wave w: every CTA has announced the wave's previous run
 __device__ __noinline__ void bs_wave_wait(const BStepArgs& a, BsShared& sh, int w) {
   if (threadIdx.x == 0) {
+    const bool prof = a.prof && blockIdx.x == 0;
+    long long t0 = prof ? clock64() : 0;
     bs_flush_wave(a, sh, w);
+    long long t1 = prof ? clock64() : 0;
     bs_bulk_wait_read();  // the staging tile of the last reduction lives in the multi-purpose region the coming run rewrites
-    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
+    long long t2 = prof ? clock64() : 0;
+    if (prof) a.prof[sh.prof_i] = ds_globaltimer();
     bs_bar_poll(bs_bar_ptr(a, 1 + w), sh.arrived[w] * gridDim.x);
-    if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();
+    if (prof) {
+      a.prof[sh.prof_i + 1] = ds_globaltimer();
+      sh.ticks[6 * 8 + 0] += (unsigned)(t1 - t0);             // own-wave flush (bulk completion + arrival)
+      sh.ticks[6 * 8 + 1] += (unsigned)(t2 - t1);             // staging-tile read completion
+      sh.ticks[6 * 8 + 2] += (unsigned)(clock64() - t2);      // poll
+      sh.ticks[6 * 8 + 7] += 1;
+    }
     sh.prof_i += 2;
   }
   bs_sync();
@@ -649,13 +659,18 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
   const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
   const float* bias = (j == 1 || j == 3 || j == 5) ? lay.bias[j] : nullptr;
+  BS_TICK(0);
   fence_proxy_async();
   bs_sync();
-  if (tid == 0) {
-    mbar_arrive(&sh.xs_ready);
-    bs_flush_all(a, sh);  // the hook: the other waves' reductions were issued a whole run ago
-  }
-  BS_TICK(0);
+  if (tid == 0) mbar_arrive(&sh.xs_ready);
+  BS_TICK(3);
+  if (tid == 0) bs_flush_all(a, sh);  // the hook: the other waves' reductions were issued a whole run ago
+  BS_TICK(4);
+  // bias / scale of the first segment's channel: requested now, a global-memory round trip before the epilogue needs them
+  const int q = warp & 3, ch = warp >> 2;
+  const int n_glob0 = rg.nb0 * 128 + q * 32 + lane;
+  const float bv0 = (bias && rg.ka00 == 0 && n_glob0 < N) ? __ldg(bias + n_glob0) : 0.f;
+  const float wsc0 = (a.w8 && n_glob0 < N) ? __ldg(lay.scale[j] + n_glob0) : 1.f;
   if (a.w8) bs_widen_atoms(sh, rg.a1 - rg.a0, ring);
   // all accumulators of the run must be complete before the staging tile (which aliases the activation tiles) is written
   for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
@@ -665,12 +680,15 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   if (tid == 0)
     for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
   float* stg = reinterpret_cast<float*>(U);  // [NPw][128] fp32
-  const int q = warp & 3, ch = warp >> 2, half_cols = wv.NPw >> 1, nch8 = half_cols >> 3;  // half_cols is a multiple of 8, <= 40
+  const int half_cols = wv.NPw >> 1, nch8 = half_cols >> 3;  // half_cols is a multiple of 8, <= 40
 #pragma unroll 1
   for (int sg = 0; sg < rg.nseg; ++sg) {
-    const int n_glob = rg.nb(sg) * 128 + q * 32 + lane;
-    const float bv = (bias && rg.ka0(sg) == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
-    const float wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
+    float bv = bv0, wsc = wsc0;
+    if (sg) {  // (a second segment only exists when there are fewer CTAs than n-blocks)
+      const int n_glob = rg.nb1 * 128 + q * 32 + lane;
+      bv = (bias && rg.ka01 == 0 && n_glob < N) ? __ldg(bias + n_glob) : 0.f;
+      wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
+    }
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
     uint32_t v[5][8];  // all of the warp's columns are requested before the one wait
 #pragma unroll
@@ -718,18 +736,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const int ntasks = H * (sh.wv[w].r0 + sh.wv[w].Rw), e0 = 2 * lane;  // the wave's (row, head) tasks are [H r0, ntasks)
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
-  // The coherent loads a task starts with (raw q/k/v, statistics: a post-barrier L2 round trip, ~2 500 cycles) are requested one task
-  // ahead, so a warp's second task finds them in registers.
-  float2 nrq = make_float2(0.f, 0.f), nrk = nrq, nrv = nrq, nst = nrq;
-  auto prefetch = [&](int tsk) {
-    const int r = tsk / H, h = tsk - r * H;
-    nst = __ldcg(reinterpret_cast<const float2*>(st) + r);
-    nrq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0)));
-    nrk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0)));
-    nrv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
-  };
   const int task0 = H * sh.wv[w].r0 + blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
-  if (task0 < ntasks) prefetch(task0);
 #pragma unroll 1
   for (int task = task0; task < ntasks; task += tstride) {
     const int r = task / H, h = task - r * H;
@@ -744,10 +751,12 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       const uint32_t sv = (jj < pos) ? (uint32_t)__ldg(anc + jj) : 0u;
       slots[i >> 2] |= sv << (8 * (i & 3));
     }
-    const float2 rq = nrq, rk = nrk, rv = nrv;
-    const float mean = nst.x / d;
-    const float rstd = rsqrtf(fmaxf(nst.y / d - mean * mean, 0.f) + 1e-5f);
-    if (task + tstride < ntasks) prefetch(task + tstride);
+    // (with two or more waves a warp has at most one task per run: nothing to prefetch for a second one)
+    float mean, rstd;
+    bs_row_stats(st, r, d, mean, rstd);
+    const float2 rq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0))),
+                 rk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0))),
+                 rv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
     const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),

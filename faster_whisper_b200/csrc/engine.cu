@@ -1269,7 +1269,10 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         std::vector<unsigned long long> f(8 * 16);
         B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
-        if (f[6 * 16 + 15] > 0)
+        if (f[6 * 16 + 15] > 0 && f[6 * 16 + 3] == 0)
+          fprintf(stderr, "[bstep prof]   wave wait, cycles per wait (CTA 0): own arrival (bulk completion) %.0f  staging-tile read %.0f  poll %.0f  (%llu waits)\n",
+                  (double)f[6 * 16] / f[6 * 16 + 15], (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], f[6 * 16 + 15]);
+        else if (f[6 * 16 + 15] > 0)
           fprintf(stderr, "[bstep prof]   self-attn cycles per 16-key block (CTA 0 warp 0): (unused) %.0f  issue+copy-wait %.0f  compute %.0f; prologue per task total %.0f over %llu blocks\n",
                   (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], (double)f[6 * 16 + 3] / f[6 * 16 + 15], (double)f[6 * 16],
                   f[6 * 16 + 15]);
@@ -1280,8 +1283,8 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         for (int k = 0; k < 6; ++k) {
           const double cnt = (double)f[k * 16 + 15];
           if (cnt > 0)
-            fprintf(stderr, "[bstep prof]   %-9s cycles (CTA 0): stage %.0f  mma-wait %.0f  epilogue %.0f  bulk-wait %.0f\n", kinds[k], f[k * 16] / cnt,
-                    f[k * 16 + 1] / cnt, f[k * 16 + 2] / cnt, f[k * 16 + 3] / cnt);
+            fprintf(stderr, "[bstep prof]   %-9s cycles per run (CTA 0): stage %.0f  sync %.0f  hook (other waves' arrivals) %.0f  mma-wait %.0f  epilogue %.0f\n", kinds[k],
+                    f[k * 16] / cnt, f[k * 16 + 3] / cnt, f[k * 16 + 4] / cnt, f[k * 16 + 1] / cnt, f[k * 16 + 2] / cnt);
         }
       }
     }

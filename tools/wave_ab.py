@@ -52,4 +52,4 @@ for waves in [w for w in a.waves.split(",") if w]:
     if first is None:
         first = toks
     same = sum(x == y for x, y in zip(first, toks))
-    print("waves %s: decode %.4f ms/step (%d steps), tokens identical to the first setting in %d of %d chunks" % (waves, best, t["decode_steps"], same, len(toks)), flush=True)
+    print("%swaves %s: decode %.4f ms/step (%d steps), tokens identical to the first setting in %d of %d chunks" % (os.environ.get("B2W_LIBRARY", "") and "[other build] ", waves, best, t["decode_steps"], same, len(toks)), flush=True)
