@@ -476,101 +476,132 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
   rstd = rsqrtf(fmaxf(s.y / d - mean * mean, 0.f) + 1e-5f);
 }
 
-// Stage this CTA's activation slices of one wave as UMMA B tiles: tile i = [NPw rows][64 K values] fp16, 128-byte swizzle, rows
-// beyond the wave's zero.
-//   X == true : source = fp32 residual stream, n-block-major (converted raw; the LayerNorm is applied by the consumer of the GEMM
-//               output); sum(x), sum(x^2) of every K slice are accumulated into `st` by exactly one of the CTAs that stage it
-//   X == false: source = fp16 activations [R][ld]
-// Index math without divisions: thread = (row tid >> 3 of a 32-row pass, 16-byte chunk tid & 7); PASSES = 32-row passes that
-// cover the wave's rows; as many tiles as the registers allow are in flight together (one memory round trip per group).
-template <bool X, int PASSES>
-__device__ __noinline__ void bs_stage(const BStepArgs& a, int s, int r0, int Rw, int NPw, const void* src, int ld, float* st, unsigned char* xs) {
-  const BsRange rg = bs_range(a, s);  // recomputed here: an out-of-line call with a by-reference range would put it on the stack
-  const int tid = threadIdx.x, R = a.R;
-  const int nblocks = (((s % 6) == 0 ? 3 * a.d : ((s % 6) == 4 ? 4 * a.d : a.d)) + 127) >> 7;
-  const int natoms = rg.a1 - rg.a0;
-  const int c = tid & 7, r_lo = tid >> 3;
-  constexpr int GRP = X ? (PASSES == 3 ? 3 : (PASSES == 2 ? 4 : 6)) : (PASSES == 3 ? 4 : 6);
+// ---- staging: this CTA's activation slices of one wave as UMMA B tiles ---------------------------------------------------------
+// tile i = [NPw rows][64 K values] fp16, 128-byte swizzle (16-byte chunk c of row r at c ^ (r & 7)), rows beyond the wave's zero.
+// These functions run once per GEMM run on eight warps, so their cost is their INSTRUCTION COUNT (the first version, 2 240 SASS
+// instructions fully unrolled with per-unit 64-bit address math and statistics, took 7-14 k cycles no matter how many rows): the work
+// is flattened into units (atom, 32-row pass), G units are in flight per thread, and a unit is a handful of instructions.
+__device__ __forceinline__ void bs_sts64(uint32_t addr, uint32_t v0, uint32_t v1) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v0), "r"(v1) : "memory");
+}
+__device__ __forceinline__ void bs_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// atom i of the run -> k-atom: the first n0 atoms belong to the run's first segment (starting at ka00), the rest to the second
+__device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < n0 ? ka00 + i : i - n0; }
+
+// fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Lane c of a row's
+// eight lanes loads the float4s c and 8 + c of the row's 64 values: each instruction of a warp reads whole 128-byte lines.
+template <int PASSES>
+__device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+  constexpr int G = 9;  // 18 x 16 bytes in flight per thread
+  const int row_off = (r0 + r_lo) * 128 + c * 4;          // this thread's first float inside an n-block's [R x 128] block, pass 0
+  const int st_off = 8 * c;                                // its 8 bytes inside the row's first 64-byte half (before the swizzle)
+  const uint32_t xs_s = smem_u32(xs);
+  int li = 0, lp = 0, si = 0, sp = 0;                      // load / store cursors (atom, pass)
 #pragma unroll 1
-  for (int i0 = 0; i0 < natoms; i0 += GRP) {
-    uint4 v0[GRP][PASSES], v1[X ? GRP : 1][X ? PASSES : 1];
-    int duty[GRP];
+  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
+    float4 f0[G], f1[G];
 #pragma unroll
-    for (int ii = 0; ii < GRP; ++ii) {
-      const int i = i0 + ii;
-      const bool on = i < natoms;
-      const int sg = i < rg.n0 ? 0 : 1;
-      const int ka = sg == 0 ? rg.ka00 + i : i - rg.n0;
-      duty[ii] = (X && on && rg.nb(sg) == ka % nblocks) ? 1 : 0;  // every k-atom is accounted once, the duty spread over the n-blocks
-#pragma unroll
-      for (int p = 0; p < PASSES; ++p) {
-        const int r = r_lo + 32 * p;
-        v0[ii][p] = make_uint4(0u, 0u, 0u, 0u);
-        if constexpr (X) v1[ii][p] = make_uint4(0u, 0u, 0u, 0u);
-        if (on && r < Rw) {
-          if constexpr (X) {
-            const float4* ptr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + bs_bidx(R, r0 + r, ka * 64 + c * 8));
-            const float4 f0 = __ldcg(ptr), f1 = __ldcg(ptr + 1);
-            v0[ii][p] = *reinterpret_cast<const uint4*>(&f0);
-            v1[ii][p] = *reinterpret_cast<const uint4*>(&f1);
-          } else {
-            v0[ii][p] = __ldcg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + (long long)(r0 + r) * ld + ka * 64 + c * 8));
-          }
-        }
+    for (int g = 0; g < G; ++g) {
+      f0[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      f1[g] = f0[g];
+      if (li < natoms && r_lo + 32 * lp < Rw) {
+        const int ka = bs_atom_ka(li, n0, ka00);
+        const float* ptr = x + ((ka >> 1) * R + 32 * lp) * 128 + (ka & 1) * 64 + row_off;
+        f0[g] = __ldcg(reinterpret_cast<const float4*>(ptr));
+        f1[g] = __ldcg(reinterpret_cast<const float4*>(ptr + 32));
+      }
+      if (++lp == PASSES) {
+        lp = 0;
+        ++li;
       }
     }
 #pragma unroll
-    for (int ii = 0; ii < GRP; ++ii) {
-      const int i = i0 + ii;
-      if (i >= natoms) break;
-      unsigned char* tile = xs + (size_t)i * (NPw * 128);
-#pragma unroll
-      for (int p = 0; p < PASSES; ++p) {
-        const int r = r_lo + 32 * p;
-        if constexpr (X) {
-          const float4 f0 = *reinterpret_cast<const float4*>(&v0[ii][p]), f1 = *reinterpret_cast<const float4*>(&v1[ii][p]);
-          if (duty[ii]) {  // uniform over the CTA
-            float s1 = (f0.x + f0.y) + (f0.z + f0.w) + (f1.x + f1.y) + (f1.z + f1.w);
-            float s2 = (f0.x * f0.x + f0.y * f0.y) + (f0.z * f0.z + f0.w * f0.w) + (f1.x * f1.x + f1.y * f1.y) + (f1.z * f1.z + f1.w * f1.w);
-            // the eight 16-byte chunks of a row sit in eight consecutive lanes
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-            if (c == 0 && r < Rw) {
-              atomicAdd(st + 2 * (r0 + r), s1);
-              atomicAdd(st + 2 * (r0 + r) + 1, s2);
-            }
-          }
-          if (r < NPw)
-            *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) =
-                make_uint4(pack_half2(f0.x, f0.y), pack_half2(f0.z, f0.w), pack_half2(f1.x, f1.y), pack_half2(f1.z, f1.w));
-        } else {
-          if (r < NPw) *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = v0[ii][p];
-        }
+    for (int g = 0; g < G; ++g) {
+      const int r = r_lo + 32 * sp;
+      if (si < natoms && r < NPw) {
+        const uint32_t row = xs_s + si * (NPw * 128) + r * 128;
+        const int sw = (r & 7) << 4;
+        bs_sts64(row + (st_off ^ sw), pack_half2(f0[g].x, f0[g].y), pack_half2(f0[g].z, f0[g].w));
+        bs_sts64(row + ((64 + st_off) ^ sw), pack_half2(f1[g].x, f1[g].y), pack_half2(f1[g].z, f1[g].w));
+      }
+      if (++sp == PASSES) {
+        sp = 0;
+        ++si;
       }
     }
   }
 }
-// Staging of GEMM s for wave w, out of line and called first thing in a run: only a handful of values are live across the
-// call (every value that is costs a local-memory round trip, and with 220 KB of shared memory the L1 is tiny).
-__device__ __noinline__ void bs_stage_run(const BStepArgs& a, const BsShared& sh, int s, int w, unsigned char* xs) {
-  const int l = s / 6, j = s - 6 * l, d = a.d;
-  const int r0 = sh.wv[w].r0, Rw = sh.wv[w].Rw, NPw = sh.wv[w].NPw;
-  const int passes = NPw <= 32 ? 1 : (NPw <= 64 ? 2 : 3);
-  if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream + LayerNorm statistics
-    float* st = a.stats + (long long)(3 * l + (j >> 1)) * a.R * 2;
-    if (passes == 1) bs_stage<true, 1>(a, s, r0, Rw, NPw, a.x, d, st, xs);
-    else if (passes == 2) bs_stage<true, 2>(a, s, r0, Rw, NPw, a.x, d, st, xs);
-    else bs_stage<true, 3>(a, s, r0, Rw, NPw, a.x, d, st, xs);
-  } else {
-    const __half* src = j == 5 ? a.h16 : a.ao;
-    const int ld = j == 5 ? 4 * d : d;
-    if (passes == 1) bs_stage<false, 1>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
-    else if (passes == 2) bs_stage<false, 2>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
-    else bs_stage<false, 3>(a, s, r0, Rw, NPw, src, ld, nullptr, xs);
+
+// fp16 activations [R][ld] row-major: one 16-byte chunk per unit
+template <int PASSES>
+__device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+  constexpr int G = 12;
+  const int row_off = (r0 + r_lo) * ld + c * 8;
+  const uint32_t xs_s = smem_u32(xs);
+  int li = 0, lp = 0, si = 0, sp = 0;
+#pragma unroll 1
+  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
+    uint4 v[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      v[g] = make_uint4(0u, 0u, 0u, 0u);
+      if (li < natoms && r_lo + 32 * lp < Rw)
+        v[g] = __ldcg(reinterpret_cast<const uint4*>(src + row_off + 32 * lp * ld + bs_atom_ka(li, n0, ka00) * 64));
+      if (++lp == PASSES) {
+        lp = 0;
+        ++li;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int r = r_lo + 32 * sp;
+      if (si < natoms && r < NPw) bs_sts128(xs_s + si * (NPw * 128) + r * 128 + ((c ^ (r & 7)) << 4), v[g]);
+      if (++sp == PASSES) {
+        sp = 0;
+        ++si;
+      }
+    }
+  }
+}
+
+// sum(x), sum(x^2) of the rows of a residual-stream input, from the staged fp16 tiles (i.e. of exactly the values the GEMM multiplies).
+// Every k-atom is accounted by exactly one of the CTAs that stage it (the duty is spread over the n-blocks: n-block ka % nblocks).
+// Runs after the MMA thread has been signalled — the few CTAs with a duty atom do this while their UMMAs execute.
+__device__ __forceinline__ void bs_red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __noinline__ void bs_tile_stats(float* st, int r0, int Rw, int NPw, int natoms, int n0, int ka00, int nb0, int nblocks, const unsigned char* xs) {
+  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+#pragma unroll 1
+  for (int i = 0; i < natoms; ++i) {
+    const int ka = bs_atom_ka(i, n0, ka00), nb = i < n0 ? nb0 : nb0 + 1;
+    if (nb != ka % nblocks) continue;  // uniform over the CTA
+    const unsigned char* tile = xs + i * (NPw * 128);
+#pragma unroll 1
+    for (int rb = 0; rb < NPw; rb += 32) {  // uniform trip count: the shuffles below involve whole warps
+      const int r = rb + r_lo;
+      float s1 = 0.f, s2 = 0.f;
+      if (r < Rw) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+        s1 = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+        s2 = ((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y)) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y));
+      }
+      // the eight chunks of a row sit in eight consecutive lanes
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+      if (c == 0 && r < Rw) {
+        bs_red_add_f32(st + 2 * (r0 + r), s1);
+        bs_red_add_f32(st + 2 * (r0 + r) + 1, s2);
+      }
+    }
   }
 }
 
@@ -642,20 +673,27 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
   } while (0)
 
 __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, int w, unsigned char* U, unsigned char* ring) {
-  {
-    const BsRange r0 = bs_range(a, s);
-    if (r0.a1 <= r0.a0) {  // no atoms of this matrix here: only the lazy arrivals of the other waves
-      if (threadIdx.x == 0) bs_flush_all(a, sh);
-      return;
-    }
-  }
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) sh.t_start = clock64();
-  bs_stage_run(a, sh, s, w, U);
   const BsRange rg = bs_range(a, s);
+  if (rg.a1 <= rg.a0) {  // no atoms of this matrix here: only the lazy arrivals of the other waves
+    if (threadIdx.x == 0) bs_flush_all(a, sh);
+    return;
+  }
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long tp = (a.prof && blockIdx.x == 0 && tid == 0) ? sh.t_start : 0;
+  long long tp = (a.prof && blockIdx.x == 0 && tid == 0) ? clock64() : 0;
   const BLayer& lay = sh.lay[l];
   const BsWave wv = sh.wv[w];
+  {
+    const int natoms = rg.a1 - rg.a0;
+    if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
+      if (wv.NPw <= 64) bs_stage_x<2>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_x<3>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+    } else {
+      const __half* src = j == 5 ? a.h16 : a.ao;
+      const int ld = j == 5 ? 4 * d : d;
+      if (wv.NPw <= 64) bs_stage_h<2>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_h<3>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+    }
+  }
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
   const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
   const float* bias = (j == 1 || j == 3 || j == 5) ? lay.bias[j] : nullptr;
@@ -664,6 +702,8 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   bs_sync();
   if (tid == 0) mbar_arrive(&sh.xs_ready);
   BS_TICK(3);
+  if (j == 0 || j == 2 || j == 4)  // LayerNorm statistics of the rows (the CTAs with a duty atom), while the UMMAs run
+    bs_tile_stats(a.stats + (long long)(3 * l + (j >> 1)) * a.R * 2, wv.r0, wv.Rw, wv.NPw, rg.a1 - rg.a0, rg.n0, rg.ka00, rg.nb0, (N + 127) >> 7, U);
   if (tid == 0) bs_flush_all(a, sh);  // the hook: the other waves' reductions were issued a whole run ago
   BS_TICK(4);
   // bias / scale of the first segment's channel: requested now, a global-memory round trip before the epilogue needs them
@@ -1166,40 +1206,44 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
 }
 
 // h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums.
-// Three float4 per thread are in flight together (one memory round trip for a CTA's whole slice at 80 rows).
+// A thread keeps ONE column group (4 channels: folded row sum and bias loaded once) and walks the wave's rows with a stride, the next
+// row's loads in flight while the current one is evaluated: one index division per run, a rolled loop, ~200 instructions instead of
+// the 900 of an unrolled version (this runs once per layer and wave: its cost is its instruction count).
 __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l, int w) {
-  const int d = a.d, R = a.R, wr0 = sh.wv[w].r0;
+  const int d = a.d, R = a.R, wr0 = sh.wv[w].r0, r_end = wr0 + sh.wv[w].Rw;
   const BLayer& lay = sh.lay[l];
-  const float* st = a.stats + (long long)(3 * l + 2) * R * 2;
-  const int per_row = d;  // float4 units per row of 4d
-  const int total = sh.wv[w].Rw * per_row, stride = gridDim.x * kBsThreads;
-  constexpr int UNR = 3;
-#pragma unroll 1
-  for (int i0 = blockIdx.x * kBsThreads + threadIdx.x; i0 < total; i0 += UNR * stride) {
-    float4 hv[UNR], w[UNR], bb[UNR];
-    float2 sv[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int i = min(i0 + u * stride, total - 1);  // clamped: the loads are unconditional, only the stores are predicated
-      const int rl = i / per_row, n = (i - rl * per_row) * 4, r = wr0 + rl;
-      hv[u] = __ldcg(reinterpret_cast<const float4*>(a.h32 + bs_bidx(R, r, n)));
-      w[u] = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n));
-      bb[u] = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
-      sv[u] = __ldcg(reinterpret_cast<const float2*>(st) + r);
+  const float2* st = reinterpret_cast<const float2*>(a.stats + (long long)(3 * l + 2) * R * 2);
+  const int gtid = blockIdx.x * kBsThreads + threadIdx.x, per_row = d;  // float4 units per row of 4d
+  const int rstride = (gridDim.x * kBsThreads) / per_row;               // rows one sweep of the grid covers (>= 1: grid >= 8 CTAs, d <= 1280)
+  const int rr = gtid / per_row, n = (gtid - rr * per_row) * 4;
+  if (rr < rstride) {
+    const float4 ws = __ldg(reinterpret_cast<const float4*>(lay.wsum[2] + n)), bb = __ldg(reinterpret_cast<const float4*>(lay.bias[4] + n));
+    int r = wr0 + rr;
+    float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 sv = make_float2(0.f, 0.f);
+    if (r < r_end) {
+      hv = __ldcg(reinterpret_cast<const float4*>(a.h32 + bs_bidx(R, r, n)));
+      sv = __ldcg(st + r);
     }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int i = i0 + u * stride;
-      if (i < total) {
-        const int rl = i / per_row, n = (i - rl * per_row) * 4, r = wr0 + rl;
-        const float mean = sv[u].x / d;
-        const float rstd = rsqrtf(fmaxf(sv[u].y / d - mean * mean, 0.f) + 1e-5f);
-        const float mr = mean * rstd;
-        const float y0 = gelu_erf(fmaf(rstd, hv[u].x, fmaf(-mr, w[u].x, bb[u].x))), y1 = gelu_erf(fmaf(rstd, hv[u].y, fmaf(-mr, w[u].y, bb[u].y)));
-        const float y2 = gelu_erf(fmaf(rstd, hv[u].z, fmaf(-mr, w[u].z, bb[u].z))), y3 = gelu_erf(fmaf(rstd, hv[u].w, fmaf(-mr, w[u].w, bb[u].w)));
-        *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
-        __stcg(reinterpret_cast<float4*>(a.h32 + bs_bidx(R, r, n)), make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll 1
+    while (r < r_end) {
+      const int rn = r + rstride;
+      float4 hn = hv;
+      float2 sn = sv;
+      if (rn < r_end) {  // the next row's loads fly while this one is evaluated
+        hn = __ldcg(reinterpret_cast<const float4*>(a.h32 + bs_bidx(R, rn, n)));
+        sn = __ldcg(st + rn);
       }
+      const float mean = sv.x / d;
+      const float rstd = rsqrtf(fmaxf(sv.y / d - mean * mean, 0.f) + 1e-5f);
+      const float mr = mean * rstd;
+      const float y0 = gelu_erf(fmaf(rstd, hv.x, fmaf(-mr, ws.x, bb.x))), y1 = gelu_erf(fmaf(rstd, hv.y, fmaf(-mr, ws.y, bb.y)));
+      const float y2 = gelu_erf(fmaf(rstd, hv.z, fmaf(-mr, ws.z, bb.z))), y3 = gelu_erf(fmaf(rstd, hv.w, fmaf(-mr, ws.w, bb.w)));
+      *reinterpret_cast<uint2*>(a.h16 + (long long)r * 4 * d + n) = make_uint2(pack_half2(y0, y1), pack_half2(y2, y3));
+      __stcg(reinterpret_cast<float4*>(a.h32 + bs_bidx(R, r, n)), make_float4(0.f, 0.f, 0.f, 0.f));
+      hv = hn;
+      sv = sn;
+      r = rn;
     }
   }
   if (threadIdx.x == 0) bs_flush_all(a, sh);  // the hook (a short run: at its end)

@@ -2,7 +2,7 @@
 # Wave-pipelined many-row step on hardware: baseline build vs this build, per-phase device timers, parity tests.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-if [ -f build/libb200whisper_r2base.so ]; then
+if [ -n "$WITH_BASE" ] && [ -f build/libb200whisper_r2base.so ]; then
   B2W_LIBRARY=$PWD/build/libb200whisper_r2base.so timeout -s KILL 300 python tools/wave_ab.py --waves 1 > gpurun_out/wave_base.log 2>&1; echo "base exit $?"; tail -n 2 gpurun_out/wave_base.log | cut -c1-300
 fi
 timeout -s KILL 600 python tools/wave_ab.py --waves ${WAVES:-1,2} > gpurun_out/wave_ab.log 2>&1; echo "wave_ab exit $?"; tail -n 8 gpurun_out/wave_ab.log | cut -c1-300
