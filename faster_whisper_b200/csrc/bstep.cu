@@ -80,6 +80,16 @@ __device__ __forceinline__ void bs_tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "memory");
 }
 
+// Atoms of one of the six matrices owned by this CTA (see bs_split); the same in every layer, computed once per launch.
+struct BsRange {  // scalars only: arrays indexed at run time would live in local memory (and the L1 next to 220 KB of smem is tiny)
+  int a0, a1, KA;
+  int nseg;
+  int nb0, nb1, ka00, ka01, n0, n1;
+  __device__ __forceinline__ int nb(int sg) const { return sg ? nb1 : nb0; }
+  __device__ __forceinline__ int ka0(int sg) const { return sg ? ka01 : ka00; }
+  __device__ __forceinline__ int n(int sg) const { return sg ? n1 : n0; }
+};
+
 // A wave = a contiguous group of chunks (and their rows) that walks the layer phases on its own barrier counter.
 struct BsWave {
   int r0, Rw, NPw;  // first row, rows, rows padded to the UMMA N
@@ -103,9 +113,12 @@ struct BsShared {
   uint64_t xs_ready;         // activations of the phase staged (compute -> MMA thread)
   uint64_t acc_full[2];      // accumulator complete (tcgen05.commit -> compute)
   uint64_t acc_empty[2];     // accumulator drained (compute -> MMA thread; logits phase only)
+  uint64_t wgo;              // gate bit 0: the activation loads of the current GEMM run are on their way (compute -> weight producer)
+  uint64_t kvgo;             // gate bit 1: the cross-q GEMM of the layer drains (compute -> K/V producer)
   uint64_t kvfull[2];        // cross-attention K/V tile landed
   uint64_t kvfree[2];        // K/V buffer may be overwritten
   // waves (thread 0 of the compute warps owns the barrier bookkeeping)
+  BsRange rng[6];                  // the CTA's atoms of qkv / out / cross_q / cross_out / ffn1 / ffn2
   BsWave wv[kBsMaxWaves];
   unsigned arrived[kBsMaxWaves];   // this CTA's arrivals on the wave's counter so far
   unsigned pend_seq[kBsMaxWaves];  // bulk groups committed when the wave's last run ended (its arrival waits for those)
@@ -124,14 +137,6 @@ __device__ __forceinline__ int bs_gemm_phase_index(int s) {
   const int ph = j == 0 ? 0 : (j == 1 ? 2 : (j == 2 ? 3 : (j == 3 ? 5 : (j == 4 ? 6 : 8))));
   return 1 + 9 * l + ph;
 }
-struct BsRange {  // scalars only: arrays indexed at run time would live in local memory (and the L1 next to 220 KB of smem is tiny)
-  int a0, a1, KA;
-  int nseg;
-  int nb0, nb1, ka00, ka01, n0, n1;
-  __device__ __forceinline__ int nb(int sg) const { return sg ? nb1 : nb0; }
-  __device__ __forceinline__ int ka0(int sg) const { return sg ? ka01 : ka00; }
-  __device__ __forceinline__ int n(int sg) const { return sg ? n1 : n0; }
-};
 // Atoms of GEMM s owned by this CTA.  The CTAs are dealt out to the n-blocks (as evenly as the counts allow) and the CTAs of an
 // n-block split its K atoms among themselves, so a CTA's run never crosses an n-block: one accumulator, one epilogue, one bulk
 // reduction per phase.  (A plain stream-K cut balances one atom better in FFN1 but gives ~10% of the CTAs a second segment whose
@@ -158,7 +163,7 @@ __host__ __device__ __forceinline__ void bs_split(int NB, int KA, int c, int G, 
   a0 = nb * KA + KA * idx / cnt;
   a1 = nb * KA + KA * (idx + 1) / cnt;
 }
-__device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
+__device__ __forceinline__ BsRange bs_range_compute(const BStepArgs& a, int s) {
   const int j = s % 6, d = a.d;
   const int N = j == 0 ? 3 * d : (j == 4 ? 4 * d : d);
   const int K = j == 5 ? 4 * d : d;
@@ -181,6 +186,7 @@ __device__ __forceinline__ BsRange bs_range(const BStepArgs& a, int s) {
   }
   return r;
 }
+__device__ __forceinline__ BsRange bs_range(const BsShared& sh, int s) { return sh.rng[s % 6]; }
 
 // ---- barriers (compute warps only) -------------------------------------------------------------------------------------------
 // arrive = red.release (cumulative through bar.sync), wait = relaxed polling.  Counter 0 synchronises the whole grid (embed, final
@@ -266,7 +272,7 @@ __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
 
 // ---- producer threads ------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh, unsigned char* ring) {
-  int n = 0;
+  int n = 0, runs = 0;
   const int nslots = a.w8 ? kBsSlots8 : kBsSlots;
   const uint32_t abytes = a.w8 ? kBsAtomBytes8 : kBsAtomBytes;
   auto push = [&](const unsigned char* src0, size_t index) {
@@ -280,12 +286,20 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
 #pragma unroll 1
   for (int s = 0; s < 6 * a.L; ++s) {
     if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
-    const BsRange r = bs_range(a, s);
+    const BsRange r = bs_range(sh, s);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(sh.lay[s / 6].wt[s % 6]);
 #pragma unroll 1
-    for (int w = 0; w < a.nw; ++w)  // every wave streams the CTA's atoms again (the later readers hit L2)
+    for (int w = 0; w < a.nw; ++w) {  // every wave streams the CTA's atoms again (the later readers hit L2)
+      if ((a.gate & 1) && r.a1 > r.a0) {
+        // Everything this SM requests from L2 shares one return path: 80 KB of weights requested the moment the previous run's
+        // UMMAs finish would arrive BEFORE the next run's activation loads, barrier polls and instruction fetches — all of which are on
+        // the critical path, while the weights are needed only once staging is done.  So they queue behind the activations.
+        mbar_wait(&sh.wgo, (uint32_t)(runs & 1));
+        runs += 1;
+      }
 #pragma unroll 1
       for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
+    }
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
   int nhalves, Rh, NPh;
@@ -329,7 +343,7 @@ __device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer,
 // or next layer) is fetched as soon as the previous run released it; buffer 1 lives in the multi-purpose region and is opened by
 // the compute warps when a cross-attention run starts.  Both sides count the uses of each buffer (mbarrier parities).
 __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, unsigned char* kv0, unsigned char* kv1) {
-  int u0 = 0, u1 = 0;
+  int u0 = 0, u1 = 0, gos = 0;
 #pragma unroll 1
   for (int l = 0; l < a.L; ++l) {
     if (!bs_enabled(a, 1 + 9 * l + 4)) return;
@@ -338,6 +352,10 @@ __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, un
       int t0, t1;
       bs_xrange(a, sh.wv[w], t0, t1);
       const int nt = t1 - t0;
+      if (a.gate & 2) {  // (one go per layer and wave, whether or not this CTA has tiles: the compute side signals unconditionally)
+        mbar_wait(&sh.kvgo, (uint32_t)(gos & 1));
+        gos += 1;
+      }
 #pragma unroll 1
       for (int k = 0; k < nt; ++k) {
         const int buf = k & 1;
@@ -385,7 +403,7 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
 #pragma unroll 1
   for (int s = 0; s < 6 * a.L; ++s) {
     if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
-    const BsRange r = bs_range(a, s);
+    const BsRange r = bs_range(sh, s);
     if (r.a1 <= r.a0) continue;
 #pragma unroll 1
     for (int w = 0; w < a.nw; ++w) {  // one run per wave: the wave's rows are the N of the UMMAs
@@ -493,7 +511,8 @@ __device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < 
 // fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Lane c of a row's
 // eight lanes loads the float4s c and 8 + c of the row's 64 values: each instruction of a warp reads whole 128-byte lines.
 template <int PASSES>
-__device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+__device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs,
+                                        uint64_t* go) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
   constexpr int G = 9;  // 18 x 16 bytes in flight per thread
   const int row_off = (r0 + r_lo) * 128 + c * 4;          // this thread's first float inside an n-block's [R x 128] block, pass 0
@@ -518,6 +537,7 @@ __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int 
         ++li;
       }
     }
+    if (go != nullptr && u0 == 0 && tid == 0) mbar_arrive(go);  // the first loads are on their way: the weight producer may follow
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int r = r_lo + 32 * sp;
@@ -537,7 +557,8 @@ __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int 
 
 // fp16 activations [R][ld] row-major: one 16-byte chunk per unit
 template <int PASSES>
-__device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+__device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs,
+                                        uint64_t* go) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
   constexpr int G = 12;
   const int row_off = (r0 + r_lo) * ld + c * 8;
@@ -556,6 +577,7 @@ __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, 
         ++li;
       }
     }
+    if (go != nullptr && u0 == 0 && tid == 0) mbar_arrive(go);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int r = r_lo + 32 * sp;
@@ -673,9 +695,12 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
   } while (0)
 
 __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, int w, unsigned char* U, unsigned char* ring) {
-  const BsRange rg = bs_range(a, s);
+  const BsRange rg = bs_range(sh, s);
   if (rg.a1 <= rg.a0) {  // no atoms of this matrix here: only the lazy arrivals of the other waves
-    if (threadIdx.x == 0) bs_flush_all(a, sh);
+    if (threadIdx.x == 0) {
+      bs_flush_all(a, sh);
+      if ((a.gate & 2) && s % 6 == 2) mbar_arrive(&sh.kvgo);
+    }
     return;
   }
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -684,14 +709,15 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   const BsWave wv = sh.wv[w];
   {
     const int natoms = rg.a1 - rg.a0;
+    uint64_t* go = (a.gate & 1) ? &sh.wgo : nullptr;
     if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
-      if (wv.NPw <= 64) bs_stage_x<2>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
-      else bs_stage_x<3>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+      if (wv.NPw <= 64) bs_stage_x<2>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
+      else bs_stage_x<3>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
     } else {
       const __half* src = j == 5 ? a.h16 : a.ao;
       const int ld = j == 5 ? 4 * d : d;
-      if (wv.NPw <= 64) bs_stage_h<2>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
-      else bs_stage_h<3>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U);
+      if (wv.NPw <= 64) bs_stage_h<2>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
+      else bs_stage_h<3>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
     }
   }
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
@@ -717,8 +743,10 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   tc_fence_after();
   bs_sync();
   BS_TICK(1);
-  if (tid == 0)
+  if (tid == 0) {
     for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
+    if ((a.gate & 2) && j == 2) mbar_arrive(&sh.kvgo);  // the cross-q GEMM drains: time to fetch the first K/V tile of the coming cross attention
+  }
   float* stg = reinterpret_cast<float*>(U);  // [NPw][128] fp32
   const int half_cols = wv.NPw >> 1, nch8 = half_cols >> 3;  // half_cols is a multiple of 8, <= 40
 #pragma unroll 1
@@ -1409,6 +1437,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
         mbar_init(&sh.fempty[i], 1);
       }
       sh.cons8 = sh.fcnt = 0;
+      for (int j = 0; j < 6; ++j) sh.rng[j] = bs_range_compute(a, j);
       sh.gseq = 0;
       sh.pending = 0;
       sh.kvu[0] = sh.kvu[1] = 0;
@@ -1424,6 +1453,8 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
         sh.wv[w] = v;
       }
       mbar_init(&sh.xs_ready, 1);
+      mbar_init(&sh.wgo, 1);
+      mbar_init(&sh.kvgo, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&sh.acc_full[i], 1);
         mbar_init(&sh.acc_empty[i], 1);

@@ -32,6 +32,8 @@ struct BStepArgs {
   int d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk;
   int u_bytes;                // size of the multi-purpose shared-memory region
   int stop_phase;             // debug: number of grid phases to run (<= 0: all)
+  int gate;                   // bit 0: a run's weight atoms are requested only after its activation loads have been issued; bit 1: the first K/V
+                              // tile of a cross-attention run is requested when the cross-q GEMM drains (not as soon as the buffer is free)
   int nw;                     // waves: the chunks are cut into nw independent groups that walk the phases software-pipelined (1..kBsMaxWaves)
   const RowInfo* rows;
   const int* tokens_in;

@@ -1132,6 +1132,8 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     // waves: independent groups of chunks walk the layer phases software-pipelined (bstep.cu); more rows -> more waves
     bs.nw = m->bstep_waves > 0 ? m->bstep_waves : (R >= 40 ? 2 : 1);
     if (const char* v = getenv("B2W_BSTEP_WAVES")) bs.nw = atoi(v);
+    bs.gate = m->bstep_gate;
+    if (const char* v = getenv("B2W_BSTEP_GATE")) bs.gate = atoi(v);
     bs.rows = sb.rows; bs.tokens_in = sb.tokens_in;
     bs.x = m->d_x; bs.qkv32 = m->d_qkv32; bs.cq32 = m->d_cq32; bs.h32 = m->d_h32; bs.ao = m->d_ao; bs.h16 = m->d_h16; bs.xn16 = m->d_xn16;
     bs.stats = m->d_stats; bs.logits = m->d_logits;
@@ -1179,7 +1181,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : (use_bstep ? 3 : 0), bs.stop_phase, bs.nw};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : (use_bstep ? 3 : 0), bs.stop_phase, bs.nw + 16 * bs.gate};
     memcpy(k, misc, sizeof misc);
   }
   if (sp.fake_logits == 0) {

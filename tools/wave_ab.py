@@ -16,7 +16,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--new-tokens", type=int, default=128)
 ap.add_argument("--beam", type=int, default=5)
 ap.add_argument("--repeat", type=int, default=2)
-ap.add_argument("--waves", default="1,2,3,4")
+ap.add_argument("--waves", default="1,2,3,4", help="comma list; an entry may carry a prefetch-gate mask as <waves>g<mask>, e.g. 1g3")
 ap.add_argument("--compute-type", default="float16")
 ap.add_argument("--prof", action="store_true")
 a = ap.parse_args()
@@ -38,7 +38,11 @@ enc = eng.encode_audio(chunks)
 eng.sync()
 first = None
 for waves in [w for w in a.waves.split(",") if w]:
-    os.environ["B2W_BSTEP_WAVES"] = waves
+    os.environ["B2W_BSTEP_WAVES"] = waves.split("g")[0]
+    if "g" in waves:
+        os.environ["B2W_BSTEP_GATE"] = waves.split("g")[1]
+    else:
+        os.environ.pop("B2W_BSTEP_GATE", None)
     best = None
     for it in range(1 + a.repeat):
         eng.timing(reset=True)
