@@ -90,14 +90,9 @@ struct BsRange {  // scalars only: arrays indexed at run time would live in loca
   __device__ __forceinline__ int n(int sg) const { return sg ? n1 : n0; }
 };
 
-// A wave = a contiguous group of chunks (and their rows) that walks the layer phases on its own barrier counter.
-struct BsWave {
-  int r0, Rw, NPw;  // first row, rows, rows padded to the UMMA N
-  int c0, nc;       // first chunk, chunks
-};
-
 struct BsShared {
   BLayer lay[32];
+  BsRange rng[6];            // the CTA's atoms of qkv / out / cross_q / cross_out / ffn1 / ffn2
   RowInfo rows[kBsMaxRows];
   unsigned epoch;
   int prof_i;
@@ -113,19 +108,8 @@ struct BsShared {
   uint64_t xs_ready;         // activations of the phase staged (compute -> MMA thread)
   uint64_t acc_full[2];      // accumulator complete (tcgen05.commit -> compute)
   uint64_t acc_empty[2];     // accumulator drained (compute -> MMA thread; logits phase only)
-  uint64_t wgo;              // gate bit 0: the activation loads of the current GEMM run are on their way (compute -> weight producer)
-  uint64_t kvgo;             // gate bit 1: the cross-q GEMM of the layer drains (compute -> K/V producer)
   uint64_t kvfull[2];        // cross-attention K/V tile landed
   uint64_t kvfree[2];        // K/V buffer may be overwritten
-  // waves (thread 0 of the compute warps owns the barrier bookkeeping)
-  BsRange rng[6];                  // the CTA's atoms of qkv / out / cross_q / cross_out / ffn1 / ffn2
-  BsWave wv[kBsMaxWaves];
-  unsigned arrived[kBsMaxWaves];   // this CTA's arrivals on the wave's counter so far
-  unsigned pend_seq[kBsMaxWaves];  // bulk groups committed when the wave's last run ended (its arrival waits for those)
-  unsigned gseq;                   // bulk groups committed so far (thread 0)
-  int pending;                     // bit w: wave w's last run has not been announced yet
-  int kvu[2];                      // uses of the two K/V buffers so far (consumer side; the producer thread keeps its own count)
-  long long t_start;               // B2W_DSTEP_PROF: clock at the start of the current GEMM run (CTA 0, thread 0)
 };
 
 // ---- phase numbering -------------------------------------------------------------------------------------------------------
@@ -188,82 +172,18 @@ __device__ __forceinline__ BsRange bs_range_compute(const BStepArgs& a, int s) {
 }
 __device__ __forceinline__ BsRange bs_range(const BsShared& sh, int s) { return sh.rng[s % 6]; }
 
-// ---- barriers (compute warps only) -------------------------------------------------------------------------------------------
-// arrive = red.release (cumulative through bar.sync), wait = relaxed polling.  Counter 0 synchronises the whole grid (embed, final
-// LayerNorm); counter 1 + w belongs to wave w.  A wave's run is announced LAZILY: when it ends the wave is only marked pending;
-// thread 0 makes the arrival (after the run's bulk reductions have completed) at a hook inside the NEXT run — which belongs to
-// another wave and does not depend on it — or at the latest before this CTA waits on the same wave again.  So neither the
-// completion latency of the bulk reductions nor the barrier round trip nor the skew between CTAs is on the critical path as long
-// as another wave has work.
-__device__ __forceinline__ unsigned* bs_bar_ptr(const BStepArgs& a, int i) { return a.bar + kBsBarStride * i; }
-__device__ __forceinline__ void bs_bar_arrive(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
-__device__ __forceinline__ void bs_bar_poll(const unsigned* p, unsigned target) {
-  unsigned v;
-  do {
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  } while (v < target);
-}
-// thread 0: wait until at most `allowed` of the most recently committed bulk groups are still in flight
-__device__ __forceinline__ void bs_bulk_wait_allow(unsigned allowed) {
-  if (allowed == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  else if (allowed == 1) asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-  else if (allowed == 2) asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-  else asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
-}
-// thread 0: announce wave w's last run if that is still pending
-__device__ __forceinline__ void bs_flush_wave(const BStepArgs& a, BsShared& sh, int w) {
-  if (!((sh.pending >> w) & 1)) return;
-  bs_bulk_wait_allow(sh.gseq - sh.pend_seq[w]);
-  bs_fence_async_all();
-  bs_bar_arrive(bs_bar_ptr(a, 1 + w));
-  sh.arrived[w] += 1;
-  sh.pending &= ~(1 << w);
-}
-// thread 0, the hook inside a run: announce every pending wave (their reductions were issued at least one run ago)
-__device__ __forceinline__ void bs_flush_all(const BStepArgs& a, BsShared& sh) {
-  if (sh.pending == 0) return;
-#pragma unroll 1
-  for (int w = 0; w < a.nw; ++w) bs_flush_wave(a, sh, w);
-}
-__device__ __noinline__ void bs_flush_all_ol(const BStepArgs& a, BsShared& sh) { bs_flush_all(a, sh); }  // for the register-starved attention runs
-// all compute threads, after a run of wave w: every global write of the run precedes the bar.sync, so thread 0 may announce it later
-__device__ __forceinline__ void bs_run_end(BsShared& sh, int w) {
-  bs_sync();
-  if (threadIdx.x == 0) {
-    sh.pend_seq[w] = sh.gseq;
-    sh.pending |= 1 << w;
-  }
-}
-// all compute threads, before a run of wave w: every CTA has announced the wave's previous run
-__device__ __noinline__ void bs_wave_wait(const BStepArgs& a, BsShared& sh, int w) {
-  if (threadIdx.x == 0) {
-    const bool prof = a.prof && blockIdx.x == 0;
-    long long t0 = prof ? clock64() : 0;
-    bs_flush_wave(a, sh, w);
-    long long t1 = prof ? clock64() : 0;
-    bs_bulk_wait_read();  // the staging tile of the last reduction lives in the multi-purpose region the coming run rewrites
-    long long t2 = prof ? clock64() : 0;
-    if (prof) a.prof[sh.prof_i] = ds_globaltimer();
-    bs_bar_poll(bs_bar_ptr(a, 1 + w), sh.arrived[w] * gridDim.x);
-    if (prof) {
-      a.prof[sh.prof_i + 1] = ds_globaltimer();
-      sh.ticks[6 * 8 + 0] += (unsigned)(t1 - t0);             // own-wave flush (bulk completion + arrival)
-      sh.ticks[6 * 8 + 1] += (unsigned)(t2 - t1);             // staging-tile read completion
-      sh.ticks[6 * 8 + 2] += (unsigned)(clock64() - t2);      // poll
-      sh.ticks[6 * 8 + 7] += 1;
-    }
-    sh.prof_i += 2;
-  }
-  bs_sync();
-}
-// whole-grid barrier (nothing may be pending)
+// Grid barrier (compute warps only): arrive = red.release (cumulative through bar.sync), wait = relaxed polling.
 __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
   bs_sync();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
-    bs_bar_arrive(bs_bar_ptr(a, 0));
-    bs_bar_poll(bs_bar_ptr(a, 0), sh.epoch);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+    const unsigned target = sh.epoch;
+    unsigned v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
+    } while (v < target);
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i + 1] = ds_globaltimer();
     sh.prof_i += 2;
   }
@@ -272,7 +192,7 @@ __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
 
 // ---- producer threads ------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh, unsigned char* ring) {
-  int n = 0, runs = 0;
+  int n = 0;
   const int nslots = a.w8 ? kBsSlots8 : kBsSlots;
   const uint32_t abytes = a.w8 ? kBsAtomBytes8 : kBsAtomBytes;
   auto push = [&](const unsigned char* src0, size_t index) {
@@ -289,17 +209,7 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
     const BsRange r = bs_range(sh, s);
     const unsigned char* base = reinterpret_cast<const unsigned char*>(sh.lay[s / 6].wt[s % 6]);
 #pragma unroll 1
-    for (int w = 0; w < a.nw; ++w) {  // every wave streams the CTA's atoms again (the later readers hit L2)
-      if ((a.gate & 1) && r.a1 > r.a0) {
-        // Everything this SM requests from L2 shares one return path: 80 KB of weights requested the moment the previous run's
-        // UMMAs finish would arrive BEFORE the next run's activation loads, barrier polls and instruction fetches — all of which are on
-        // the critical path, while the weights are needed only once staging is done.  So they queue behind the activations.
-        mbar_wait(&sh.wgo, (uint32_t)(runs & 1));
-        runs += 1;
-      }
-#pragma unroll 1
-      for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
-    }
+    for (int at = r.a0; at < r.a1; ++at) push(base, (size_t)at);
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
   int nhalves, Rh, NPh;
@@ -315,12 +225,10 @@ __device__ __noinline__ void bs_weight_producer(const BStepArgs& a, BsShared& sh
 }
 
 // cross-attention tiles (group-major: tile = (chunk * H + head) * splits + split) are dealt out as contiguous runs ("stream-K")
-// — per wave: the wave's tiles [base, base + NT) are cut over the whole grid
-__device__ __forceinline__ void bs_xrange(const BStepArgs& a, const BsWave& wv, int& t0, int& t1) {
-  const unsigned NT = (unsigned)(kDsXSplits * a.H * wv.nc);
-  const int base = kDsXSplits * a.H * wv.c0;
-  t0 = base + (int)(NT * blockIdx.x / gridDim.x);
-  t1 = base + (int)(NT * (blockIdx.x + 1) / gridDim.x);
+__device__ __forceinline__ void bs_xrange(const BStepArgs& a, int& t0, int& t1) {
+  const unsigned NT = (unsigned)(kDsXSplits * a.H * a.n_chunks);
+  t0 = (int)(NT * blockIdx.x / gridDim.x);
+  t1 = (int)(NT * (blockIdx.x + 1) / gridDim.x);
 }
 
 // TMA the K and V tiles of one cross-attention task (key split of one (chunk, head)) into kvbuf (one thread).
@@ -339,35 +247,29 @@ __device__ __forceinline__ void bs_issue_cross_kv(const BStepArgs& a, int layer,
   ds_bulk_g2s(kvbuf + kDsXKeysMax * 128, Vb, (uint32_t)nk * 128u, bar);
 }
 
-// K/V producer: the k-th tile of a run goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile of the next run (next wave
-// or next layer) is fetched as soon as the previous run released it; buffer 1 lives in the multi-purpose region and is opened by
-// the compute warps when a cross-attention run starts.  Both sides count the uses of each buffer (mbarrier parities).
+// K/V producer: the k-th tile of this CTA's run goes to buffer k & 1.  Buffer 0 is dedicated, so the first tile
+// of a layer is fetched as soon as the previous layer released it; buffer 1 lives in the multi-purpose region and is opened
+// by the compute warps when the cross-attention phase starts.
 __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, unsigned char* kv0, unsigned char* kv1) {
-  int u0 = 0, u1 = 0, gos = 0;
+  int t0, t1;
+  bs_xrange(a, t0, t1);
+  const int nt = t1 - t0;
+  if (nt == 0) return;
+  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
 #pragma unroll 1
   for (int l = 0; l < a.L; ++l) {
     if (!bs_enabled(a, 1 + 9 * l + 4)) return;
 #pragma unroll 1
-    for (int w = 0; w < a.nw; ++w) {
-      int t0, t1;
-      bs_xrange(a, sh.wv[w], t0, t1);
-      const int nt = t1 - t0;
-      if (a.gate & 2) {  // (one go per layer and wave, whether or not this CTA has tiles: the compute side signals unconditionally)
-        mbar_wait(&sh.kvgo, (uint32_t)(gos & 1));
-        gos += 1;
+    for (int k = 0; k < nt; ++k) {
+      const int buf = k & 1;
+      if (buf == 0) {
+        const int u = l * n_even + (k >> 1);
+        mbar_wait(&sh.kvfree[0], (uint32_t)((u & 1) ^ 1));
+      } else {
+        const int u = l * n_odd + (k >> 1);
+        mbar_wait(&sh.kvfree[1], (uint32_t)(u & 1));
       }
-#pragma unroll 1
-      for (int k = 0; k < nt; ++k) {
-        const int buf = k & 1;
-        if (buf == 0) {
-          mbar_wait(&sh.kvfree[0], (uint32_t)((u0 & 1) ^ 1));
-          u0 += 1;
-        } else {
-          mbar_wait(&sh.kvfree[1], (uint32_t)(u1 & 1));
-          u1 += 1;
-        }
-        bs_issue_cross_kv(a, l, t0 + k, buf ? kv1 : kv0, &sh.kvfull[buf]);
-      }
+      bs_issue_cross_kv(a, l, t0 + k, buf ? kv1 : kv0, &sh.kvfull[buf]);
     }
   }
 }
@@ -375,6 +277,8 @@ __device__ __noinline__ void bs_kv_producer(const BStepArgs& a, BsShared& sh, un
 // MMA thread: per GEMM phase wait for the staged activations, then per atom wait for the weights and issue four K=16 UMMAs.
 __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, unsigned char* ring, unsigned char* xs, unsigned char* xs_logits) {
   const uint32_t tmem = sh.tmem_base;
+  const uint32_t idesc = umma_idesc_f16(128, a.NP, false);
+  const uint32_t xs_tile = (uint32_t)a.NP * 128u;
   int consumed = 0, xs_uses = 0;
   const bool w8 = a.w8 != 0;
   unsigned char* ftiles = ring + (size_t)kBsSlots8 * kBsAtomBytes8;  // int8 path: the two widened fp16 tiles
@@ -405,24 +309,18 @@ __device__ __noinline__ void bs_mma_thread(const BStepArgs& a, BsShared& sh, uns
     if (!bs_enabled(a, bs_gemm_phase_index(s))) return;
     const BsRange r = bs_range(sh, s);
     if (r.a1 <= r.a0) continue;
+    mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
+    xs_uses += 1;
+    tc_fence_after();
+    int local = 0;
 #pragma unroll 1
-    for (int w = 0; w < a.nw; ++w) {  // one run per wave: the wave's rows are the N of the UMMAs
-      const int NPw = sh.wv[w].NPw;
-      const uint32_t idesc = umma_idesc_f16(128, NPw, false);
-      const uint32_t xs_tile = (uint32_t)NPw * 128u;
-      mbar_wait(&sh.xs_ready, (uint32_t)(xs_uses & 1));
-      xs_uses += 1;
-      tc_fence_after();
-      int local = 0;
+    for (int sg = 0; sg < r.nseg; ++sg) {
 #pragma unroll 1
-      for (int sg = 0; sg < r.nseg; ++sg) {
-#pragma unroll 1
-        for (int i = 0; i < r.n(sg); ++i) {
-          atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
-          local += 1;
-        }
-        tc_commit(&sh.acc_full[sg]);
+      for (int i = 0; i < r.n(sg); ++i) {
+        atom(tmem + sg * 128, smem_u32(xs) + local * xs_tile, idesc, i == 0);
+        local += 1;
       }
+      tc_commit(&sh.acc_full[sg]);
     }
   }
   if (!bs_enabled(a, 2 + 9 * a.L)) return;
@@ -456,16 +354,6 @@ __device__ __noinline__ void bs_zero_f32(float* p, long long n) {  // all comput
     __stcg(p4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
-// zero the rows [r0, r0 + Rw) of an n-block-major [R x N] buffer (all compute threads of all CTAs)
-__device__ __noinline__ void bs_zero_rows(float* p, int N, int R, int r0, int Rw) {
-  const int per_nb = Rw * 32;  // float4 units of the wave's rows inside one n-block
-  const int total = ((N + 127) >> 7) * per_nb;
-  for (int i = blockIdx.x * kBsThreads + threadIdx.x; i < total; i += gridDim.x * kBsThreads) {
-    const int nb = i / per_nb, rem = i - nb * per_nb;
-    __stcg(reinterpret_cast<float4*>(p + ((long long)nb * R + r0) * 128) + rem, make_float4(0.f, 0.f, 0.f, 0.f));
-  }
-}
-
 // The fp32 split-K accumulation buffers (x, qkv32, cq32, h32) are stored n-block-major: element (row r, channel n) lives at
 // ((n >> 7) * R + r) * 128 + (n & 127), so that the [R x 128] output tile of a GEMM segment is ONE contiguous block and its
 // reduction into L2 is a single cp.reduce.async.bulk (bulk instructions are warp-uniform: one per row would serialise 80 issues).
@@ -494,8 +382,8 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
   rstd = rsqrtf(fmaxf(s.y / d - mean * mean, 0.f) + 1e-5f);
 }
 
-// ---- staging: this CTA's activation slices of one wave as UMMA B tiles ---------------------------------------------------------
-// tile i = [NPw rows][64 K values] fp16, 128-byte swizzle (16-byte chunk c of row r at c ^ (r & 7)), rows beyond the wave's zero.
+// ---- staging: this CTA's activation slices as UMMA B tiles ---------------------------------------------------------
+// tile i = [NPw rows][64 K values] fp16, 128-byte swizzle (16-byte chunk c of row r at c ^ (r & 7)), rows beyond the last zero.
 // These functions run once per GEMM run on eight warps, so their cost is their INSTRUCTION COUNT (the first version, 2 240 SASS
 // instructions fully unrolled with per-unit 64-bit address math and statistics, took 7-14 k cycles no matter how many rows): the work
 // is flattened into units (atom, 32-row pass), G units are in flight per thread, and a unit is a handful of instructions.
@@ -511,8 +399,7 @@ __device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < 
 // fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Lane c of a row's
 // eight lanes loads the float4s c and 8 + c of the row's 64 values: each instruction of a warp reads whole 128-byte lines.
 template <int PASSES>
-__device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs,
-                                        uint64_t* go) {
+__device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
   constexpr int G = 9;  // 18 x 16 bytes in flight per thread
   const int row_off = (r0 + r_lo) * 128 + c * 4;          // this thread's first float inside an n-block's [R x 128] block, pass 0
@@ -537,7 +424,6 @@ __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int 
         ++li;
       }
     }
-    if (go != nullptr && u0 == 0 && tid == 0) mbar_arrive(go);  // the first loads are on their way: the weight producer may follow
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int r = r_lo + 32 * sp;
@@ -557,8 +443,7 @@ __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int 
 
 // fp16 activations [R][ld] row-major: one 16-byte chunk per unit
 template <int PASSES>
-__device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs,
-                                        uint64_t* go) {
+__device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
   constexpr int G = 12;
   const int row_off = (r0 + r_lo) * ld + c * 8;
@@ -577,7 +462,6 @@ __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, 
         ++li;
       }
     }
-    if (go != nullptr && u0 == 0 && tid == 0) mbar_arrive(go);
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int r = r_lo + 32 * sp;
@@ -666,15 +550,6 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
   bs_sync();
 }
 
-// cycle counters inside the attention loops: compiled in only with -DB2W_BSTEP_TICKS (they hold two registers across loops that
-// have none to spare)
-#ifndef B2W_BSTEP_TICKS
-#define BS_ATICK(kind, point, tp) do { } while (0)
-#define BS_ATICK_DECL(tp)
-#define BS_ATICK_COUNT(kind) do { } while (0)
-#else
-#define BS_ATICK_DECL(tp) long long tp = clock64()
-#define BS_ATICK_COUNT(kind) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) sh.ticks[(kind) * 8 + 7] += 1; } while (0)
 #define BS_ATICK(kind, point, tp)                                        \
   do {                                                                   \
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -683,7 +558,6 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
       (tp) = _now;                                                       \
     }                                                                    \
   } while (0)
-#endif
 
 #define BS_TICK(point)                                                   \
   do {                                                                   \
@@ -694,30 +568,22 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
     }                                                                    \
   } while (0)
 
-__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, int w, unsigned char* U, unsigned char* ring) {
+__device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U, unsigned char* ring) {
   const BsRange rg = bs_range(sh, s);
-  if (rg.a1 <= rg.a0) {  // no atoms of this matrix here: only the lazy arrivals of the other waves
-    if (threadIdx.x == 0) {
-      bs_flush_all(a, sh);
-      if ((a.gate & 2) && s % 6 == 2) mbar_arrive(&sh.kvgo);
-    }
-    return;
-  }
+  if (rg.a1 <= rg.a0) return;
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long tp = (a.prof && blockIdx.x == 0 && tid == 0) ? clock64() : 0;
+  long long tp = clock64();
   const BLayer& lay = sh.lay[l];
-  const BsWave wv = sh.wv[w];
   {
     const int natoms = rg.a1 - rg.a0;
-    uint64_t* go = (a.gate & 1) ? &sh.wgo : nullptr;
     if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
-      if (wv.NPw <= 64) bs_stage_x<2>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
-      else bs_stage_x<3>(a.x, a.R, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
+      if (a.NP <= 64) bs_stage_x<2>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_x<3>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     } else {
       const __half* src = j == 5 ? a.h16 : a.ao;
       const int ld = j == 5 ? 4 * d : d;
-      if (wv.NPw <= 64) bs_stage_h<2>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
-      else bs_stage_h<3>(src, ld, wv.r0, wv.Rw, wv.NPw, natoms, rg.n0, rg.ka00, U, go);
+      if (a.NP <= 64) bs_stage_h<2>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_h<3>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     }
   }
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
@@ -727,28 +593,25 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   fence_proxy_async();
   bs_sync();
   if (tid == 0) mbar_arrive(&sh.xs_ready);
-  BS_TICK(3);
-  if (j == 0 || j == 2 || j == 4)  // LayerNorm statistics of the rows (the CTAs with a duty atom), while the UMMAs run
-    bs_tile_stats(a.stats + (long long)(3 * l + (j >> 1)) * a.R * 2, wv.r0, wv.Rw, wv.NPw, rg.a1 - rg.a0, rg.n0, rg.ka00, rg.nb0, (N + 127) >> 7, U);
-  if (tid == 0) bs_flush_all(a, sh);  // the hook: the other waves' reductions were issued a whole run ago
   BS_TICK(4);
+  if (j == 0 || j == 2 || j == 4)  // LayerNorm statistics of the rows (the CTAs with a duty atom), while the UMMAs run
+    bs_tile_stats(a.stats + (long long)(3 * l + (j >> 1)) * a.R * 2, 0, a.R, a.NP, rg.a1 - rg.a0, rg.n0, rg.ka00, rg.nb0, (N + 127) >> 7, U);
+  BS_TICK(5);
   // bias / scale of the first segment's channel: requested now, a global-memory round trip before the epilogue needs them
   const int q = warp & 3, ch = warp >> 2;
   const int n_glob0 = rg.nb0 * 128 + q * 32 + lane;
   const float bv0 = (bias && rg.ka00 == 0 && n_glob0 < N) ? __ldg(bias + n_glob0) : 0.f;
   const float wsc0 = (a.w8 && n_glob0 < N) ? __ldg(lay.scale[j] + n_glob0) : 1.f;
   if (a.w8) bs_widen_atoms(sh, rg.a1 - rg.a0, ring);
-  // all accumulators of the run must be complete before the staging tile (which aliases the activation tiles) is written
+  // all accumulators of the phase must be complete before the staging tile (which aliases the activation tiles) is written
   for (int sg = 0; sg < rg.nseg; ++sg) mbar_wait(&sh.acc_full[sg], (uint32_t)sh.acc_par[sg]);
   tc_fence_after();
   bs_sync();
   BS_TICK(1);
-  if (tid == 0) {
+  if (tid == 0)
     for (int sg = 0; sg < rg.nseg; ++sg) sh.acc_par[sg] ^= 1;
-    if ((a.gate & 2) && j == 2) mbar_arrive(&sh.kvgo);  // the cross-q GEMM drains: time to fetch the first K/V tile of the coming cross attention
-  }
-  float* stg = reinterpret_cast<float*>(U);  // [NPw][128] fp32
-  const int half_cols = wv.NPw >> 1, nch8 = half_cols >> 3;  // half_cols is a multiple of 8, <= 40
+  float* stg = reinterpret_cast<float*>(U);  // [NP][128] fp32
+  const int half_cols = a.NP >> 1;  // a multiple of 8
 #pragma unroll 1
   for (int sg = 0; sg < rg.nseg; ++sg) {
     float bv = bv0, wsc = wsc0;
@@ -758,29 +621,30 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
       wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
     }
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
-    uint32_t v[5][8];  // all of the warp's columns are requested before the one wait
+#pragma unroll 1
+    for (int c = 0; c < half_cols; c += 8) {  // (wider batches of TMEM loads cost registers that the whole call graph then pays for in spills)
+      uint32_t v[8];
+      bs_tmem_ld8(taddr + c, v);
+      tc_wait_ld();
 #pragma unroll
-    for (int c8 = 0; c8 < 5; ++c8)
-      if (c8 < nch8) bs_tmem_ld8(taddr + 8 * c8, v[c8]);
-    tc_wait_ld();
-#pragma unroll
-    for (int c8 = 0; c8 < 5; ++c8)
-      if (c8 < nch8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) stg[(ch * half_cols + 8 * c8 + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[c8][i]), wsc, bv);
-      }
+      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[i]), wsc, bv);
+    }
     fence_proxy_async();
     bs_sync();
-    if (tid == 0) {  // rows 0 .. Rw-1 of the staging tile = the wave's contiguous [Rw x 128] block of the n-block-major output
-      bs_bulk_reduce_f32(out + ((long long)rg.nb(sg) * a.R + wv.r0) * 128, stg, (uint32_t)wv.Rw * 512u);
+    if (tid == 0) {  // rows 0 .. R-1 of the staging tile = the segment's contiguous [R x 128] block of the n-block-major output
+      bs_bulk_reduce_f32(out + (long long)rg.nb(sg) * a.R * 128, stg, (uint32_t)a.R * 512u);
       bs_bulk_commit();
-      sh.gseq += 1;
       if (sg + 1 < rg.nseg) bs_bulk_wait_read();
     }
     if (sg + 1 < rg.nseg) bs_sync();
   }
   tc_fence_before();
   BS_TICK(2);
+  if (tid == 0) {
+    bs_bulk_wait_all();
+    bs_fence_async_all();
+  }
+  BS_TICK(3);
   if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[j * 8 + 7] += 1;
 }
 
@@ -791,7 +655,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
 // touches 4 cache lines, not 32 — and double buffered: the copies of block b + 1 are in flight while block b is scored.  With only
 // eight compute warps per SM this is what keeps enough bytes in flight (registers cannot: 64 data registers per block spill).
 constexpr int kBsSelfTile = 2 * 2 * 16 * 64 * 2;  // per warp: two buffers x (K + V) x 16 keys x 64 halves = 8 KB
-__device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, int w, unsigned char* U) {
+__device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* U) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = a.d, H = a.H, n_ctx = a.n_ctx;
   __half* tiles = reinterpret_cast<__half*>(U + (size_t)warp * kBsSelfTile);  // [buf][K|V][16 keys][64]; 16-byte chunks at chunk ^ (key & 7)
@@ -801,16 +665,27 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const float* st = a.stats + (long long)(3 * l) * a.R * 2;
   __half* kc = a.kcache + (long long)l * a.kv_layer_stride;
   __half* vc = a.vcache + (long long)l * a.kv_layer_stride;
-  const int ntasks = H * (sh.wv[w].r0 + sh.wv[w].Rw), e0 = 2 * lane;  // the wave's (row, head) tasks are [H r0, ntasks)
+  const int ntasks = H * a.R, e0 = 2 * lane;
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
-  const int task0 = H * sh.wv[w].r0 + blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
+  // The coherent loads a task starts with (raw q/k/v, statistics: a post-barrier L2 round trip, ~2 500 cycles) are requested one task
+  // ahead, so a warp's second task finds them in registers.
+  float2 nrq = make_float2(0.f, 0.f), nrk = nrq, nrv = nrq, nst = nrq;
+  auto prefetch = [&](int tsk) {
+    const int r = tsk / H, h = tsk - r * H;
+    nst = __ldcg(reinterpret_cast<const float2*>(st) + r);
+    nrq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0)));
+    nrk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0)));
+    nrv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
+  };
+  const int task0 = blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
+  if (task0 < ntasks) prefetch(task0);
 #pragma unroll 1
   for (int task = task0; task < ntasks; task += tstride) {
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
-    BS_ATICK_DECL(tp);
+    long long tp = clock64();
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
     uint32_t slots[4] = {0u, 0u, 0u, 0u};  // lane holds the slot byte of key 32 i + lane for i < 14 (n_ctx <= 448)
 #pragma unroll
@@ -819,12 +694,10 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       const uint32_t sv = (jj < pos) ? (uint32_t)__ldg(anc + jj) : 0u;
       slots[i >> 2] |= sv << (8 * (i & 3));
     }
-    // (with two or more waves a warp has at most one task per run: nothing to prefetch for a second one)
-    float mean, rstd;
-    bs_row_stats(st, r, d, mean, rstd);
-    const float2 rq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0))),
-                 rk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0))),
-                 rv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
+    const float2 rq = nrq, rk = nrk, rv = nrv;
+    const float mean = nst.x / d;
+    const float rstd = rsqrtf(fmaxf(nst.y / d - mean * mean, 0.f) + 1e-5f);
+    if (task + tstride < ntasks) prefetch(task + tstride);
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
     const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),
@@ -952,7 +825,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       }
       __syncwarp();  // the buffer may be refilled by the copies issued in the next iteration
       BS_ATICK(6, 3, tp);
-      BS_ATICK_COUNT(6);
+      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
     }
     float l_run = l_part;
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
@@ -964,7 +837,6 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(o + 8 * dt) = pack_half2(oacc[dt][0] * inv, oacc[dt][1] * inv);
     }
   }
-  if (tid == 0) bs_flush_all_ol(a, sh);  // the hook: after this thread's tasks (one or two of them)
 }
 
 // Beam-shared cross attention, stream-K over key tiles.  The 1500 keys of a (chunk, head) group are 7 tiles of ~214 keys; all
@@ -973,26 +845,22 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
 // sum per query in shared memory, output accumulators in registers across the tiles of a group.  A group that lies entirely inside
 // one run is written straight to `ao`; a group cut by a run boundary leaves one partial record per piece and the piece that
 // completes the group (ticket = tiles done) merges them.  With 16 chunks a run is ~15 tiles: two groups whole, two cut.
-__device__ __forceinline__ bool bs_piece_starts_at(int t, unsigned NT) {  // is tile t (wave-relative) the first tile of some CTA's run?
+__device__ __forceinline__ bool bs_piece_starts_at(int t, unsigned NT) {  // is tile t the first tile of some CTA's run?
   const unsigned G = gridDim.x;
   const unsigned c = ((unsigned)(t + 1) * G + NT - 1) / NT - 1;
   return (int)(NT * c / G) == t;
 }
 
-__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, int w, unsigned char* kv0, unsigned char* U) {
+__device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& sh, int l, unsigned char* kv0, unsigned char* U) {
   int t0, t1;
-  bs_xrange(a, sh.wv[w], t0, t1);
+  bs_xrange(a, t0, t1);
   const int nt = t1 - t0;
-  if (nt == 0) {
-    if (threadIdx.x == 0) bs_flush_all_ol(a, sh);
-    return;
-  }
-  const int ku0 = sh.kvu[0], ku1 = sh.kvu[1];  // uses of the two K/V buffers before this run
+  if (nt == 0) return;
+  const int n_even = (nt + 1) >> 1, n_odd = nt >> 1;
   const int T = a.T, S = kDsXSplits, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nq = a.rows_per_chunk, d = a.d;
-  const unsigned NT = (unsigned)(S * a.H * sh.wv[w].nc);  // tiles of the wave
-  const int tbase = S * a.H * sh.wv[w].c0;
+  const unsigned NT = (unsigned)(S * a.H * a.n_chunks);
   unsigned char* kv1 = U;
   unsigned char* scratch = U + kBsKvBytes;
   __half* qs_all = reinterpret_cast<__half*>(scratch);                          // [kBsXGroups][8][96], pre-scaled by 1/8
@@ -1038,7 +906,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     const int tile = t0 + k, grp = tile / S, split = tile - grp * S, gi = grp - g_first;
     const int buf = k & 1;
     unsigned char* kvbuf = buf ? kv1 : kv0;
-    const int u = (buf ? ku1 : ku0) + (k >> 1);
+    const int u = l * (buf ? n_odd : n_even) + (k >> 1);
     const int k0 = T * split / S, k1 = T * (split + 1) / S, nk = k1 - k0;
     const __half* kt = reinterpret_cast<const __half*>(kvbuf);  // [224][64], 16-byte chunks at chunk ^ (encoder position & 7)
     __half* vt = reinterpret_cast<__half*>(kvbuf) + kDsXKeysMax * 64;
@@ -1052,7 +920,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       qf0 = *reinterpret_cast<const uint4*>(qs + 8 * t);
       qf1 = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
     }
-    BS_ATICK_DECL(tp);
+    long long tp = clock64();
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
     BS_ATICK(7, 0, tp);
     const int ngroups16 = (nk + 15) >> 4;
@@ -1157,9 +1025,8 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     // release the tile (one arrival per warp): buffer 0 always, buffer 1 only when another tile of this phase will use it
     __syncwarp();
     if (lane == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
-    if (k == 0 && tid == 0) bs_flush_all_ol(a, sh);  // the hook: after the first tile
     BS_ATICK(7, 1, tp);
-    BS_ATICK_COUNT(7);
+    if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[7 * 8 + 7] += 1;
     if (!piece_ends) continue;
     bs_sync();
     const int h = grp % a.H, b = grp / a.H, row0 = b * nq;
@@ -1186,18 +1053,30 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       }
     }
     if (n_piece != S) {
+      // A cut group is merged by the piece that holds its FIRST split.  The runs are walked in tile order and start together, so
+      // that piece is the last thing its CTA does, while the group's other pieces open the runs of the following CTAs and were
+      // recorded a whole run earlier: those only post their record (a release add, no round trip), and the merger's poll finds the
+      // count complete.  (Previously every piece took a ticket — an atomic round trip at the START of a run, on the critical path of
+      // every CTA — and whoever came last merged.)
       bs_sync();
+      const bool merger = piece_first == 0;
       if (tid == 0) {
-        int ticket;
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(ticket) : "l"(a.xcounters + grp), "r"(n_piece) : "memory");
-        sh.flag = (ticket + n_piece == S);
-        if (sh.flag) a.xcounters[grp] = 0;
+        unsigned* cnt = reinterpret_cast<unsigned*>(a.xcounters + grp);
+        if (!merger) {
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((unsigned)n_piece) : "memory");
+        } else {
+          unsigned v;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+          } while (v < (unsigned)(S - n_piece));
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(0u) : "memory");  // next use: the next layer, a grid barrier away
+        }
       }
-      bs_sync();
-      if (sh.flag) {  // this piece completed the group: merge the pieces (their first splits are where some CTA's run starts, or 0)
+      if (merger) bs_sync();
+      if (merger) {  // merge the pieces (their first splits are where some CTA's run starts, or 0)
         const float* pg = a.xpart + (long long)grp * S * (kBsXQ * 66);
         unsigned present = 1u;
-        for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2 - tbase, NT) ? (1u << s2) : 0u;
+        for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2, NT) ? (1u << s2) : 0u;
 #pragma unroll 1
         for (int i = tid; i < nq * 64; i += kBsThreads) {
           const int q = i >> 6, e = i & 63;
@@ -1227,18 +1106,14 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     bs_sync();  // the per-warp partials are reused by the next piece
     BS_ATICK(7, 2, tp);
   }
-  if (tid == 0) {  // (the last tile of a run always ends a piece: every thread passed its bar.sync after reading the counts)
-    sh.kvu[0] = ku0 + ((nt + 1) >> 1);
-    sh.kvu[1] = ku1 + (nt >> 1);
-  }
 }
 
 // h16 = GELU(rstd (h32 - mean rowsum(W1)) + b1), evaluated once per element; h32 is zeroed for the next layer's sums.
-// A thread keeps ONE column group (4 channels: folded row sum and bias loaded once) and walks the wave's rows with a stride, the next
+// A thread keeps ONE column group (4 channels: folded row sum and bias loaded once) and walks the rows with a stride, the next
 // row's loads in flight while the current one is evaluated: one index division per run, a rolled loop, ~200 instructions instead of
-// the 900 of an unrolled version (this runs once per layer and wave: its cost is its instruction count).
-__device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l, int w) {
-  const int d = a.d, R = a.R, wr0 = sh.wv[w].r0, r_end = wr0 + sh.wv[w].Rw;
+// the 900 of an unrolled version (this runs once per layer: its cost is its instruction count).
+__device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int l) {
+  const int d = a.d, R = a.R, wr0 = 0, r_end = R;
   const BLayer& lay = sh.lay[l];
   const float2* st = reinterpret_cast<const float2*>(a.stats + (long long)(3 * l + 2) * R * 2);
   const int gtid = blockIdx.x * kBsThreads + threadIdx.x, per_row = d;  // float4 units per row of 4d
@@ -1274,7 +1149,6 @@ __device__ __noinline__ void bs_gelu_phase(const BStepArgs& a, BsShared& sh, int
       r = rn;
     }
   }
-  if (threadIdx.x == 0) bs_flush_all(a, sh);  // the hook (a short run: at its end)
 }
 
 // xn16[r] = (x[r] - mean) * rstd  (CTA r; the final LayerNorm's affine part is folded into the output embedding)
@@ -1378,33 +1252,6 @@ __device__ __noinline__ void bs_logits_phase(const BStepArgs& a, BsShared& sh, u
   }
 }
 
-// One run = phase ph of layer l for wave w (compute warps).  Out of line, with the shared-memory carve-up recomputed inside, so
-// that the phase loop of the kernel keeps next to nothing live across the calls.
-__device__ __noinline__ void bs_layer_run(const BStepArgs& a, BsShared& sh, int l, int ph, int w, unsigned char* smem) {
-  unsigned char* ring = smem;
-  unsigned char* kv0 = ring + (size_t)kBsSlots * kBsAtomBytes;
-  unsigned char* U = kv0 + kBsKvBytes;
-  bs_wave_wait(a, sh, w);
-  switch (ph) {
-    case 0: bs_gemm_phase(a, sh, 6 * l + 0, w, U, ring); break;
-    case 1: bs_self_attn_phase(a, sh, l, w, U); break;
-    case 2:
-      bs_zero_rows(a.qkv32, 3 * a.d, a.R, sh.wv[w].r0, sh.wv[w].Rw);  // consumed by the self-attention of this layer
-      bs_gemm_phase(a, sh, 6 * l + 1, w, U, ring);
-      break;
-    case 3: bs_gemm_phase(a, sh, 6 * l + 2, w, U, ring); break;
-    case 4: bs_cross_attn_phase(a, sh, l, w, kv0, U); break;
-    case 5:
-      bs_zero_rows(a.cq32, a.d, a.R, sh.wv[w].r0, sh.wv[w].Rw);  // consumed by the cross attention of this layer
-      bs_gemm_phase(a, sh, 6 * l + 3, w, U, ring);
-      break;
-    case 6: bs_gemm_phase(a, sh, 6 * l + 4, w, U, ring); break;
-    case 7: bs_gelu_phase(a, sh, l, w); break;
-    default: bs_gemm_phase(a, sh, 6 * l + 5, w, U, ring); break;
-  }
-  bs_run_end(sh, w);
-}
-
 __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_param) {
   extern __shared__ unsigned char bs_smem_raw[];
   __shared__ BStepArgs a_sh;
@@ -1438,23 +1285,7 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
       }
       sh.cons8 = sh.fcnt = 0;
       for (int j = 0; j < 6; ++j) sh.rng[j] = bs_range_compute(a, j);
-      sh.gseq = 0;
-      sh.pending = 0;
-      sh.kvu[0] = sh.kvu[1] = 0;
-      for (int w = 0; w < kBsMaxWaves; ++w) {
-        sh.arrived[w] = 0;
-        sh.pend_seq[w] = 0;
-        BsWave v;
-        v.c0 = w < a.nw ? a.n_chunks * w / a.nw : a.n_chunks;
-        v.nc = w < a.nw ? a.n_chunks * (w + 1) / a.nw - v.c0 : 0;
-        v.r0 = v.c0 * a.rows_per_chunk;
-        v.Rw = v.nc * a.rows_per_chunk;
-        v.NPw = bs_ceil16(v.Rw);
-        sh.wv[w] = v;
-      }
       mbar_init(&sh.xs_ready, 1);
-      mbar_init(&sh.wgo, 1);
-      mbar_init(&sh.kvgo, 1);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&sh.acc_full[i], 1);
         mbar_init(&sh.acc_empty[i], 1);
@@ -1476,24 +1307,33 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
     if (threadIdx.x == kBsThreads + 64) bs_mma_thread(a, sh, ring, U, kv0);
   } else {
     int phase = 0;  // grid phases executed so far
-    const int nw = a.nw;
     bs_embed_phase(a, sh);
     bool run = bs_enabled(a, ++phase);  // phase 0 done after the barrier; `phase` is the index of the next one
     bs_grid_barrier(a, sh);
-    // The waves walk the nine phases of every layer one behind the other.  A run of wave w starts when every CTA has announced
-    // the wave's previous run; it never waits for another wave, whose runs fill the time a dependency needs to resolve.
 #pragma unroll 1
     for (int l = 0; l < L && run; ++l) {
 #pragma unroll 1
       for (int ph = 0; ph < 9 && run; ++ph) {
-#pragma unroll 1
-        for (int w = 0; w < nw; ++w) bs_layer_run(a, sh, l, ph, w, smem);
+        switch (ph) {
+          case 0: bs_gemm_phase(a, sh, 6 * l + 0, U, ring); break;
+          case 1: bs_self_attn_phase(a, sh, l, U); break;
+          case 2:
+            bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer
+            bs_gemm_phase(a, sh, 6 * l + 1, U, ring);
+            break;
+          case 3: bs_gemm_phase(a, sh, 6 * l + 2, U, ring); break;
+          case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
+          case 5:
+            bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer
+            bs_gemm_phase(a, sh, 6 * l + 3, U, ring);
+            break;
+          case 6: bs_gemm_phase(a, sh, 6 * l + 4, U, ring); break;
+          case 7: bs_gelu_phase(a, sh, l); break;
+          default: bs_gemm_phase(a, sh, 6 * l + 5, U, ring); break;
+        }
         run = bs_enabled(a, ++phase);
+        bs_grid_barrier(a, sh);
       }
-    }
-    if (run || a.stop_phase > 0) {  // every wave's last run has to be complete (and announced) before anything reads across waves
-#pragma unroll 1
-      for (int w = 0; w < nw; ++w) bs_wave_wait(a, sh, w);
     }
     if (run) {
       bs_final_ln_phase(a, red);
@@ -1604,7 +1444,6 @@ static int bstep_max_dynamic_smem() {
 void bstep_configure() { B2W_CUDA(cudaFuncSetAttribute(bstep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bstep_max_dynamic_smem())); }
 
 int bstep_phase_count(int L) { return 3 + 9 * L; }
-int bstep_sync_points(int L, int nw) { return 2 + 9 * L * nw + nw; }  // barrier waits of one launch, in order (profile stamps)
 
 size_t bstep_xpart_floats(const BStepArgs& a) { return (size_t)a.n_chunks * a.H * kDsXSplits * kBsXQ * 66; }
 
@@ -1615,8 +1454,6 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
     const int NT = kDsXSplits * a.H * a.n_chunks, run = (NT + num_sms - 1) / num_sms;
     if ((run + kDsXSplits - 1) / kDsXSplits + 1 > kBsXGroups) return false;
   }
-  if (a.R != a.n_chunks * a.rows_per_chunk) return false;  // rows are chunk-major: a wave is a contiguous range of both
-  a.nw = std::max(1, std::min(std::min(a.nw, kBsMaxWaves), a.n_chunks));
   a.NP = bs_ceil16(a.R);
   const int d = a.d, G = num_sms;
   // activation tiles of the busiest GEMM phase (an even share of the atoms, rounded up) and the condition for two segments
@@ -1648,7 +1485,7 @@ bool bstep_supported(int num_sms, BStepArgs& a) {
 
 void bstep_launch(const BStepArgs& a, int grid, cudaStream_t s) {
   const size_t smem = bstep_smem_bytes(a);
-  B2W_CUDA(cudaMemsetAsync(a.bar, 0, (size_t)(1 + kBsMaxWaves) * kBsBarStride * sizeof(unsigned), s));
+  B2W_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned), s));
   BStepArgs copy = a;
   void* args[] = {&copy};
   B2W_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(bstep_kernel), dim3(grid), dim3(kBsLaunch), args, smem, s));

@@ -6,8 +6,6 @@ namespace b2w {
 
 constexpr int kBsAtomBytes = 16384;  // one weight atom: 128 output channels x 64 K values, fp16, 128-byte swizzle (a ready-made UMMA A tile)
 constexpr int kBsMaxRows = 80;
-constexpr int kBsMaxWaves = 4;
-constexpr int kBsBarStride = 32;     // unsigned words between the barrier counters (one 128-byte line each): [0] whole grid, [1 + w] wave w
 
 // Per layer: the six weight matrices as atom streams (order: qkv, out, cross_q, cross_out, ffn1, ffn2), their fp32 biases and, for the
 // three matrices that consume a LayerNorm, the row sums of the (LayerNorm-folded, fp16-rounded) weights — the mean term of the
@@ -32,9 +30,6 @@ struct BStepArgs {
   int d, H, n_ctx, slots, T, vpad, n_vocab, n_chunks, rows_per_chunk;
   int u_bytes;                // size of the multi-purpose shared-memory region
   int stop_phase;             // debug: number of grid phases to run (<= 0: all)
-  int gate;                   // bit 0: a run's weight atoms are requested only after its activation loads have been issued; bit 1: the first K/V
-                              // tile of a cross-attention run is requested when the cross-q GEMM drains (not as soon as the buffer is free)
-  int nw;                     // waves: the chunks are cut into nw independent groups that walk the phases software-pipelined (1..kBsMaxWaves)
   const RowInfo* rows;
   const int* tokens_in;
   float* x;       // [R][d]   fp32 residual stream
@@ -54,8 +49,8 @@ struct BStepArgs {
   const DecBindings* bind;
   float* xpart;
   int* xcounters;
-  unsigned* bar;             // (1 + kBsMaxWaves) counters, kBsBarStride words apart
-  unsigned long long* prof;  // optional: %globaltimer around every barrier wait (CTA 0)
+  unsigned* bar;
+  unsigned long long* prof;  // optional: %globaltimer at every barrier (CTA 0)
 };
 
 // atom stream of W[N][K] (row-major fp16): atoms ordered (n-block, k-atom); rows beyond N are zero
@@ -72,6 +67,5 @@ bool bstep_supported(int num_sms, BStepArgs& a);  // fills a.NP / a.u_bytes; fal
 size_t bstep_xpart_floats(const BStepArgs& a);
 void bstep_launch(const BStepArgs& a, int grid, cudaStream_t s);
 int bstep_phase_count(int L);
-int bstep_sync_points(int L, int nw);
 
 }  // namespace b2w

@@ -533,8 +533,8 @@ static void build_model(Model* m, const b2w_config& cfg, const TensorTable& tt) 
       B2W_CUDA(cudaMemcpy(m->d_blayers, bl.data(), L * sizeof(BLayer), cudaMemcpyHostToDevice));
       m->bstep_packed = true;
     }
-    m->d_bar = dalloc<unsigned>((1 + kBsMaxWaves) * kBsBarStride);
-    B2W_CUDA(cudaMemset(m->d_bar, 0, (1 + kBsMaxWaves) * kBsBarStride * sizeof(unsigned)));
+    m->d_bar = dalloc<unsigned>(4);
+    B2W_CUDA(cudaMemset(m->d_bar, 0, 4 * sizeof(unsigned)));
   }
   for (int l = L / 2; l < L; ++l)  // default alignment heads: every head of the last half of the decoder (OpenAI Whisper's default)
     for (int hh = 0; hh < cfg.n_text_head; ++hh) m->align_heads.push_back(make_int2(l, hh));
@@ -1129,11 +1129,6 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     bs.vpad = m->vpad; bs.n_vocab = c.n_vocab; bs.n_chunks = n; bs.rows_per_chunk = K;
     bs.stop_phase = m->bstep_stop;
     if (const char* v = getenv("B2W_BSTEP_STOP")) bs.stop_phase = atoi(v);  // re-read per call: tools/bstep_bisect.py steps it
-    // waves: independent groups of chunks walk the layer phases software-pipelined (bstep.cu); more rows -> more waves
-    bs.nw = m->bstep_waves > 0 ? m->bstep_waves : (R >= 40 ? 2 : 1);
-    if (const char* v = getenv("B2W_BSTEP_WAVES")) bs.nw = atoi(v);
-    bs.gate = m->bstep_gate;
-    if (const char* v = getenv("B2W_BSTEP_GATE")) bs.gate = atoi(v);
     bs.rows = sb.rows; bs.tokens_in = sb.tokens_in;
     bs.x = m->d_x; bs.qkv32 = m->d_qkv32; bs.cq32 = m->d_cq32; bs.h32 = m->d_h32; bs.ao = m->d_ao; bs.h16 = m->d_h16; bs.xn16 = m->d_xn16;
     bs.stats = m->d_stats; bs.logits = m->d_logits;
@@ -1181,7 +1176,7 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     uint8_t* k = key.data();
     const void* ptrs[4] = {m->kcache, m->sb_blob, m->d_xpart, m->d_logits};
     memcpy(k, ptrs, sizeof ptrs); k += sizeof ptrs;
-    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : (use_bstep ? 3 : 0), bs.stop_phase, bs.nw + 16 * bs.gate};
+    int misc[8] = {splits, m->use_ref_gemv ? 1 : 0, n, K, sp.fake_logits, use_dstep ? 1 : (use_bstep ? 3 : 0), bs.stop_phase, 0};
     memcpy(k, misc, sizeof misc);
   }
   if (sp.fake_logits == 0) {
@@ -1247,34 +1242,30 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
     m->decode_steps += steps_run;
     if (m->d_prof && use_bstep) {
       B2W_CUDA(cudaStreamSynchronize(s));
-      // stamps: [0] = start; sync point i (in program order: the embed barrier, the wave wait before every run (l, ph, w), the
-      // closing wait of every wave, the final-LN barrier) has (wait begin, wait end) at [1 + 2 i], [2 + 2 i]; the last stamp = end
-      const int L = c.n_text_layer, nw = bs.nw, npts = bstep_sync_points(L, nw), nstamps = 1 + 2 * npts + 1;
+      const int L = c.n_text_layer, nstamps = 1 + 2 * (2 + 9 * L) + 1;
       std::vector<unsigned long long> t(nstamps);
       B2W_CUDA(cudaMemcpy(t.data(), m->d_prof, nstamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
       static const char* names[9] = {"qkv", "self_attn", "out_proj", "cross_q", "cross_attn", "cross_out", "ffn1", "gelu", "ffn2"};
       double work[9] = {0}, wait[9] = {0};
+      unsigned long long prev = t[2];
       for (int l = 0; l < L; ++l)
-        for (int ph = 0; ph < 9; ++ph)
-          for (int w = 0; w < nw; ++w) {
-            const int i = 1 + (l * 9 + ph) * nw + w;        // the wait before this run
-            wait[ph] += double(t[2 + 2 * i] - t[1 + 2 * i]);
-            work[ph] += double(t[1 + 2 * (i + 1)] - t[2 + 2 * i]);  // until the next wait begins
-          }
-      const int ifin = 1 + 9 * L * nw + nw;  // the final-LN barrier
-      fprintf(stderr, "[bstep prof] last step (R=%d, %d wave%s): total %.1f us; embed %.1f us; final-LN %.1f us; logits %.1f us\n", R, nw, nw > 1 ? "s" : "",
-              (t[nstamps - 1] - t[0]) / 1e3, (t[2] - t[0]) / 1e3, (t[1 + 2 * ifin] - t[2 + 2 * (ifin - 1)]) / 1e3, (t[nstamps - 1] - t[2 + 2 * ifin]) / 1e3);
+        for (int ph = 0; ph < 9; ++ph) {
+          const int bi = 1 + 2 * (1 + l * 9 + ph);
+          work[ph] += double(t[bi] - prev);
+          wait[ph] += double(t[bi + 1] - t[bi]);
+          prev = t[bi + 1];
+        }
+      const int bf = 1 + 2 * (1 + 9 * L);
+      fprintf(stderr, "[bstep prof] last step (R=%d): total %.1f us; embed %.1f us; final-LN %.1f us; logits %.1f us\n", R, (t[nstamps - 1] - t[0]) / 1e3,
+              (t[2] - t[0]) / 1e3, (t[bf] - prev) / 1e3, (t[nstamps - 1] - t[bf + 1]) / 1e3);
       for (int ph = 0; ph < 9; ++ph)
-        fprintf(stderr, "[bstep prof]   %-10s work %.2f us  wait before %.2f us (CTA 0, per layer, all waves, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
+        fprintf(stderr, "[bstep prof]   %-10s work %.2f us  barrier wait %.2f us (CTA 0, mean over %d layers)\n", names[ph], work[ph] / L / 1e3,
                 wait[ph] / L / 1e3, L);
       {
         std::vector<unsigned long long> f(8 * 16);
         B2W_CUDA(cudaMemcpy(f.data(), m->d_prof + 3000, f.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         B2W_CUDA(cudaMemset(m->d_prof + 3000, 0, f.size() * sizeof(unsigned long long)));
-        if (f[6 * 16 + 15] > 0 && f[6 * 16 + 3] == 0)
-          fprintf(stderr, "[bstep prof]   wave wait, cycles per wait (CTA 0): own arrival (bulk completion) %.0f  staging-tile read %.0f  poll %.0f  (%llu waits)\n",
-                  (double)f[6 * 16] / f[6 * 16 + 15], (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], f[6 * 16 + 15]);
-        else if (f[6 * 16 + 15] > 0)
+        if (f[6 * 16 + 15] > 0)
           fprintf(stderr, "[bstep prof]   self-attn cycles per 16-key block (CTA 0 warp 0): (unused) %.0f  issue+copy-wait %.0f  compute %.0f; prologue per task total %.0f over %llu blocks\n",
                   (double)f[6 * 16 + 1] / f[6 * 16 + 15], (double)f[6 * 16 + 2] / f[6 * 16 + 15], (double)f[6 * 16 + 3] / f[6 * 16 + 15], (double)f[6 * 16],
                   f[6 * 16 + 15]);
@@ -1285,8 +1276,8 @@ static void generate_group(Model* m, Encoded* e, int chunk0, int n, const int32_
         for (int k = 0; k < 6; ++k) {
           const double cnt = (double)f[k * 16 + 15];
           if (cnt > 0)
-            fprintf(stderr, "[bstep prof]   %-9s cycles per run (CTA 0): stage %.0f  sync %.0f  hook (other waves' arrivals) %.0f  mma-wait %.0f  epilogue %.0f\n", kinds[k],
-                    f[k * 16] / cnt, f[k * 16 + 3] / cnt, f[k * 16 + 4] / cnt, f[k * 16 + 1] / cnt, f[k * 16 + 2] / cnt);
+            fprintf(stderr, "[bstep prof]   %-9s cycles (CTA 0): stage %.0f  sync %.0f  row statistics %.0f  mma-wait %.0f  epilogue %.0f  bulk-wait %.0f\n", kinds[k],
+                    f[k * 16] / cnt, f[k * 16 + 4] / cnt, f[k * 16 + 5] / cnt, f[k * 16 + 1] / cnt, f[k * 16 + 2] / cnt, f[k * 16 + 3] / cnt);
         }
       }
     }

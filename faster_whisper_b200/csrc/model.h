@@ -131,8 +131,6 @@ struct Model {
   bool use_bstep = true;     // B2W_BSTEP=0 falls back to the multi-kernel step for R > 8
   bool bstep_all = false;    // B2W_BSTEP=all: also for R <= 8 (instead of dstep_kernel)
   int bstep_stop = 0;        // B2W_BSTEP_STOP=n: run only the first n grid phases of every step (debug)
-  int bstep_gate = 0;        // B2W_BSTEP_GATE: prefetch gates of the many-row step kernel (bstep.h)
-  int bstep_waves = 0;       // B2W_BSTEP_WAVES=n: force the number of waves of the many-row step kernel (0: by row count)
   bool bstep_packed = false;
   BLayer* d_blayers = nullptr;
   const void* logit_atoms = nullptr;

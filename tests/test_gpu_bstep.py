@@ -129,37 +129,3 @@ def test_many_row_kernel_other_beam_shapes(micro, n_chunks, beam, extra):
     prompts = [[st.sot_prev, 900, 901, st.sot]] * n_chunks  # timestamps on
     exact, n = compare(eng, micro, feats, prompts, beam_size=beam, max_length=40, repetition_penalty=1.2, no_repeat_ngram_size=3, **extra)
     assert 2 * exact >= n, (exact, n)
-
-
-@pytest.mark.parametrize("n_chunks,beam,waves", [(16, 5, 1), (16, 5, 3), (16, 5, 4), (9, 2, 2), (9, 2, 4), (7, 5, 3), (4, 5, 2), (3, 1, 3), (2, 5, 4)])
-def test_wave_pipelined_step_matches_oracle(micro, n_chunks, beam, waves, monkeypatch):
-    """The chunks of a step walk the layer phases as `waves` independent groups, software-pipelined on their own barrier counters
-    (B2W_BSTEP_WAVES; the default is by row count).  Even and uneven splits, more waves than the default, waves of a single chunk, more
-    waves requested than chunks: same tokens as the oracle."""
-    st = micro["tokens"]
-    eng = make_engine(micro, B2W_BSTEP="all")
-    monkeypatch.setenv("B2W_BSTEP_WAVES", str(waves))
-    feats = features_for(micro, n_chunks, seed=350)
-    prompts = [[st.sot, st.no_timestamps]] * n_chunks
-    exact, n = compare(eng, micro, feats, prompts, beam_size=beam, max_length=40, repetition_penalty=1.3, no_repeat_ngram_size=3,
-                       suppress_tokens=[st.eot, st.sot, st.no_speech])
-    assert 2 * exact >= n, (exact, n)
-
-
-def test_wave_count_does_not_change_the_tokens(micro_ml, monkeypatch):
-    """One engine, the same call with 1, 2 and 4 waves: identical sequences (scores within the split-K summation noise)."""
-    st = micro_ml["tokens"]
-    eng = make_engine(micro_ml)
-    feats = features_for(micro_ml, 12, seed=360)
-    prompts = [[st.sot, st.lang_begin + 2, st.transcribe]] * 12
-    kw = dict(beam_size=5, max_length=36, return_scores=True, repetition_penalty=1.2, no_repeat_ngram_size=3)
-    out = {}
-    for waves in (1, 2, 4):
-        monkeypatch.setenv("B2W_BSTEP_WAVES", str(waves))
-        out[waves] = eng.generate(eng.encode(feats), prompts, **kw)
-    for waves in (2, 4):
-        same = sum(x.sequences_ids[0] == y.sequences_ids[0] for x, y in zip(out[1], out[waves]))
-        assert same >= 11, (waves, same)
-        for x, y in zip(out[1], out[waves]):
-            if x.sequences_ids[0] == y.sequences_ids[0]:
-                assert abs(x.scores[0] - y.scores[0]) < 5e-3

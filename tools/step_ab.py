@@ -1,8 +1,9 @@
-"""A/B of the many-row step kernel's wave count in ONE process: large-v3 (synthetic), B chunks x beam 5, prompt 4 + N new tokens.
+"""A/B of decode-step settings in ONE process: large-v3 (synthetic), B chunks x beam 5, prompt 4 + N new tokens.
 
-For each value of B2W_BSTEP_WAVES (re-read by the engine on every generate call) one warm-up and `--repeat` timed generate calls;
-prints the decode time per step from the engine's stage timers (CUDA events on its stream) and checks that every wave count
-produces the same tokens as the first one.  With --prof the per-phase device timers of the last step are printed too.
+For each entry of --configs (environment assignments the engine re-reads on every generate call, e.g. "B2W_BSTEP=0") one warm-up and
+`--repeat` timed generate calls; prints the decode time per step from the engine's stage timers (CUDA events on its stream) and checks
+that every setting produces the same tokens as the first one.  B2W_LIBRARY=<other build of the C ABI> compares kernel versions on the
+same box; with --prof the per-phase device timers of the last step are printed too.
 """
 import argparse
 import os
@@ -16,7 +17,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--new-tokens", type=int, default=128)
 ap.add_argument("--beam", type=int, default=5)
 ap.add_argument("--repeat", type=int, default=2)
-ap.add_argument("--waves", default="1,2,3,4", help="comma list; an entry may carry a prefetch-gate mask as <waves>g<mask>, e.g. 1g3")
+ap.add_argument("--configs", default="-", help="';'-separated settings, each a ','-separated list of NAME=VALUE environment assignments ('-' = none)")
 ap.add_argument("--compute-type", default="float16")
 ap.add_argument("--prof", action="store_true")
 a = ap.parse_args()
@@ -37,12 +38,10 @@ eng.timing(enable=True)
 enc = eng.encode_audio(chunks)
 eng.sync()
 first = None
-for waves in [w for w in a.waves.split(",") if w]:
-    os.environ["B2W_BSTEP_WAVES"] = waves.split("g")[0]
-    if "g" in waves:
-        os.environ["B2W_BSTEP_GATE"] = waves.split("g")[1]
-    else:
-        os.environ.pop("B2W_BSTEP_GATE", None)
+for waves in [w for w in a.configs.split(";") if w]:
+    assigned = [kv.split("=", 1) for kv in waves.split(",") if "=" in kv]
+    for k, v in assigned:
+        os.environ[k] = v
     best = None
     for it in range(1 + a.repeat):
         eng.timing(reset=True)
@@ -56,4 +55,6 @@ for waves in [w for w in a.waves.split(",") if w]:
     if first is None:
         first = toks
     same = sum(x == y for x, y in zip(first, toks))
-    print("%swaves %s: decode %.4f ms/step (%d steps), tokens identical to the first setting in %d of %d chunks" % (os.environ.get("B2W_LIBRARY", "") and "[other build] ", waves, best, t["decode_steps"], same, len(toks)), flush=True)
+    for k, _ in assigned:
+        os.environ.pop(k, None)
+    print("%s[%s] decode %.4f ms/step (%d steps), tokens identical to the first setting in %d of %d chunks" % (os.environ.get("B2W_LIBRARY", "") and "[other build] ", waves, best, t["decode_steps"], same, len(toks)), flush=True)
