@@ -396,44 +396,38 @@ __device__ __forceinline__ void bs_sts128(uint32_t addr, const uint4& v) {
 // atom i of the run -> k-atom: the first n0 atoms belong to the run's first segment (starting at ka00), the rest to the second
 __device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < n0 ? ka00 + i : i - n0; }
 
-// fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Lane c of a row's
-// eight lanes loads the float4s c and 8 + c of the row's 64 values: each instruction of a warp reads whole 128-byte lines.
-template <int PASSES>
+// fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Sixteen lanes
+// read the sixteen float4s of a row's 64 values (two whole 128-byte lines per row), a unit is (atom, 16-row pass): 80 rows are
+// exactly five passes, and G = 25 units = five atoms — a CTA's usual share of a matrix — are one memory round trip.
 __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
-  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
-  constexpr int G = 9;  // 18 x 16 bytes in flight per thread
-  const int row_off = (r0 + r_lo) * 128 + c * 4;          // this thread's first float inside an n-block's [R x 128] block, pass 0
-  const int st_off = 8 * c;                                // its 8 bytes inside the row's first 64-byte half (before the swizzle)
-  const uint32_t xs_s = smem_u32(xs);
+  const int tid = threadIdx.x, c = tid & 15, r_lo = tid >> 4;
+  constexpr int G = 25;
+  const int passes = NPw >> 4;                              // NPw is a multiple of 16
+  const int row_off = (r0 + r_lo) * 128 + c * 4;           // this thread's float4 inside an n-block's [R x 128] block, pass 0
+  const uint32_t xs_s = smem_u32(xs) + 8 * c;              // its 8 bytes of fp16 inside a tile row (before the swizzle)
   int li = 0, lp = 0, si = 0, sp = 0;                      // load / store cursors (atom, pass)
 #pragma unroll 1
-  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
-    float4 f0[G], f1[G];
+  for (int u0 = 0; u0 < natoms * passes; u0 += G) {
+    float4 f[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      f0[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-      f1[g] = f0[g];
-      if (li < natoms && r_lo + 32 * lp < Rw) {
+      f[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (li < natoms && r_lo + 16 * lp < Rw) {
         const int ka = bs_atom_ka(li, n0, ka00);
-        const float* ptr = x + ((ka >> 1) * R + 32 * lp) * 128 + (ka & 1) * 64 + row_off;
-        f0[g] = __ldcg(reinterpret_cast<const float4*>(ptr));
-        f1[g] = __ldcg(reinterpret_cast<const float4*>(ptr + 32));
+        f[g] = __ldcg(reinterpret_cast<const float4*>(x + ((ka >> 1) * R + 16 * lp) * 128 + (ka & 1) * 64 + row_off));
       }
-      if (++lp == PASSES) {
+      if (++lp == passes) {
         lp = 0;
         ++li;
       }
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      const int r = r_lo + 32 * sp;
-      if (si < natoms && r < NPw) {
-        const uint32_t row = xs_s + si * (NPw * 128) + r * 128;
-        const int sw = (r & 7) << 4;
-        bs_sts64(row + (st_off ^ sw), pack_half2(f0[g].x, f0[g].y), pack_half2(f0[g].z, f0[g].w));
-        bs_sts64(row + ((64 + st_off) ^ sw), pack_half2(f1[g].x, f1[g].y), pack_half2(f1[g].z, f1[g].w));
+      if (si < natoms) {
+        const int r = r_lo + 16 * sp;
+        bs_sts64((xs_s + si * (NPw * 128) + r * 128) ^ ((r & 7) << 4), pack_half2(f[g].x, f[g].y), pack_half2(f[g].z, f[g].w));
       }
-      if (++sp == PASSES) {
+      if (++sp == passes) {
         sp = 0;
         ++si;
       }
@@ -445,7 +439,7 @@ __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int 
 template <int PASSES>
 __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
-  constexpr int G = 12;
+  constexpr int G = PASSES == 3 ? 18 : 12;  // six atoms of 80 rows = one round trip
   const int row_off = (r0 + r_lo) * ld + c * 8;
   const uint32_t xs_s = smem_u32(xs);
   int li = 0, lp = 0, si = 0, sp = 0;
@@ -479,34 +473,30 @@ __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, 
 // Runs after the MMA thread has been signalled — the few CTAs with a duty atom do this while their UMMAs execute.
 __device__ __forceinline__ void bs_red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __noinline__ void bs_tile_stats(float* st, int r0, int Rw, int NPw, int natoms, int n0, int ka00, int nb0, int nblocks, const unsigned char* xs) {
-  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+  // thread 2 r + half reads the four 16-byte chunks of its half of row r (with the swizzle the eight rows of a quarter warp hit eight
+  // different bank groups), sums locally, one shuffle joins the halves: a single pass, no loop over rows
+  const int tid = threadIdx.x, r = tid >> 1, half = tid & 1;
 #pragma unroll 1
   for (int i = 0; i < natoms; ++i) {
     const int ka = bs_atom_ka(i, n0, ka00), nb = i < n0 ? nb0 : nb0 + 1;
     if (nb != ka % nblocks) continue;  // uniform over the CTA
-    const unsigned char* tile = xs + i * (NPw * 128);
-#pragma unroll 1
-    for (int rb = 0; rb < NPw; rb += 32) {  // uniform trip count: the shuffles below involve whole warps
-      const int r = rb + r_lo;
-      float s1 = 0.f, s2 = 0.f;
-      if (r < Rw) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+    const unsigned char* row = xs + i * (NPw * 128) + r * 128;
+    float s1 = 0.f, s2 = 0.f;
+    if (r < Rw) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(row + (((4 * half + c) ^ (r & 7)) << 4));
         const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-        s1 = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
-        s2 = ((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y)) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y));
+        s1 += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+        s2 += ((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y)) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y));
       }
-      // the eight chunks of a row sit in eight consecutive lanes
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
-      if (c == 0 && r < Rw) {
-        bs_red_add_f32(st + 2 * (r0 + r), s1);
-        bs_red_add_f32(st + 2 * (r0 + r) + 1, s2);
-      }
+    }
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    if (half == 0 && r < Rw) {
+      bs_red_add_f32(st + 2 * (r0 + r), s1);
+      bs_red_add_f32(st + 2 * (r0 + r) + 1, s2);
     }
   }
 }
@@ -577,8 +567,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   {
     const int natoms = rg.a1 - rg.a0;
     if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
-      if (a.NP <= 64) bs_stage_x<2>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
-      else bs_stage_x<3>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      bs_stage_x(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     } else {
       const __half* src = j == 5 ? a.h16 : a.ao;
       const int ld = j == 5 ? 4 * d : d;
