@@ -397,75 +397,84 @@ __device__ __forceinline__ void bs_sts128(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < n0 ? ka00 + i : i - n0; }
 
 // fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Sixteen lanes
-// read the sixteen float4s of a row's 64 values (two whole 128-byte lines per row), a unit is (atom, 16-row pass): 80 rows are
-// exactly five passes, and G = 25 units = five atoms — a CTA's usual share of a matrix — are one memory round trip.
+// read the sixteen float4s of a row's 64 values (two whole 128-byte lines per row); P16 = 16-row passes per atom (80 rows are exactly
+// five), GA = atoms in flight together (one memory round trip per GA atoms).  Every unit is predicated, not branched around (register
+// arrays that are defined under a branch end up in local memory), so a switched-off unit still costs its issue slots: a CTA with one
+// or two atoms (the N = d matrices) takes the GA = 2 instance, the others GA = 5 — a CTA's usual share of the wide matrices.
+template <int P16, int GA>
 __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 15, r_lo = tid >> 4;
-  constexpr int G = 25;
-  const int passes = NPw >> 4;                              // NPw is a multiple of 16
   const int row_off = (r0 + r_lo) * 128 + c * 4;           // this thread's float4 inside an n-block's [R x 128] block, pass 0
   const uint32_t xs_s = smem_u32(xs) + 8 * c;              // its 8 bytes of fp16 inside a tile row (before the swizzle)
-  int li = 0, lp = 0, si = 0, sp = 0;                      // load / store cursors (atom, pass)
 #pragma unroll 1
-  for (int u0 = 0; u0 < natoms * passes; u0 += G) {
-    float4 f[G];
+  for (int i0 = 0; i0 < natoms; i0 += GA) {
+    float4 f[GA][P16];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      f[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (li < natoms && r_lo + 16 * lp < Rw) {
-        const int ka = bs_atom_ka(li, n0, ka00);
-        f[g] = __ldcg(reinterpret_cast<const float4*>(x + ((ka >> 1) * R + 16 * lp) * 128 + (ka & 1) * 64 + row_off));
-      }
-      if (++lp == passes) {
-        lp = 0;
-        ++li;
+    for (int at = 0; at < GA; ++at) {
+      const int ka = bs_atom_ka(i0 + at, n0, ka00);
+      const float* base = x + ((ka >> 1) * R) * 128 + (ka & 1) * 64 + row_off;
+#pragma unroll
+      for (int p = 0; p < P16; ++p) {
+        f[at][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i0 + at < natoms && r_lo + 16 * p < Rw) f[at][p] = __ldcg(reinterpret_cast<const float4*>(base + 16 * p * 128));
       }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (si < natoms) {
-        const int r = r_lo + 16 * sp;
-        bs_sts64((xs_s + si * (NPw * 128) + r * 128) ^ ((r & 7) << 4), pack_half2(f[g].x, f[g].y), pack_half2(f[g].z, f[g].w));
-      }
-      if (++sp == passes) {
-        sp = 0;
-        ++si;
+    for (int at = 0; at < GA; ++at) {
+      const uint32_t tile = xs_s + (i0 + at) * (NPw * 128);
+#pragma unroll
+      for (int p = 0; p < P16; ++p) {
+        const int r = r_lo + 16 * p;
+        if (i0 + at < natoms) bs_sts64((tile + r * 128) ^ ((r & 7) << 4), pack_half2(f[at][p].x, f[at][p].y), pack_half2(f[at][p].z, f[at][p].w));
       }
     }
   }
 }
+__device__ __forceinline__ void bs_stage_x_any(const float* x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+  switch (NPw >> 4) {  // NPw is a multiple of 16, <= 80
+    case 1: bs_stage_x<1, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
+    case 2: bs_stage_x<2, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
+    case 3: bs_stage_x<3, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
+    case 4: bs_stage_x<4, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
+    default:
+      if (natoms <= 2) bs_stage_x<5, 2>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs);
+      else bs_stage_x<5, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs);
+      break;
+  }
+}
 
-// fp16 activations [R][ld] row-major: one 16-byte chunk per unit
-template <int PASSES>
+// fp16 activations [R][ld] row-major: eight lanes read a row's eight 16-byte chunks, PASSES 32-row passes per atom, GA atoms in flight
+template <int PASSES, int GA>
 __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
-  constexpr int G = PASSES == 3 ? 18 : 12;  // six atoms of 80 rows = one round trip
   const int row_off = (r0 + r_lo) * ld + c * 8;
   const uint32_t xs_s = smem_u32(xs);
-  int li = 0, lp = 0, si = 0, sp = 0;
 #pragma unroll 1
-  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
-    uint4 v[G];
+  for (int i0 = 0; i0 < natoms; i0 += GA) {
+    uint4 v[GA][PASSES];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      v[g] = make_uint4(0u, 0u, 0u, 0u);
-      if (li < natoms && r_lo + 32 * lp < Rw)
-        v[g] = __ldcg(reinterpret_cast<const uint4*>(src + row_off + 32 * lp * ld + bs_atom_ka(li, n0, ka00) * 64));
-      if (++lp == PASSES) {
-        lp = 0;
-        ++li;
+    for (int at = 0; at < GA; ++at) {
+      const __half* base = src + row_off + bs_atom_ka(i0 + at, n0, ka00) * 64;
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        v[at][p] = make_uint4(0u, 0u, 0u, 0u);
+        if (i0 + at < natoms && r_lo + 32 * p < Rw) v[at][p] = __ldcg(reinterpret_cast<const uint4*>(base + 32 * p * ld));
       }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int r = r_lo + 32 * sp;
-      if (si < natoms && r < NPw) bs_sts128(xs_s + si * (NPw * 128) + r * 128 + ((c ^ (r & 7)) << 4), v[g]);
-      if (++sp == PASSES) {
-        sp = 0;
-        ++si;
+    for (int at = 0; at < GA; ++at) {
+#pragma unroll
+      for (int p = 0; p < PASSES; ++p) {
+        const int r = r_lo + 32 * p;
+        if (i0 + at < natoms && r < NPw) bs_sts128(xs_s + (i0 + at) * (NPw * 128) + r * 128 + ((c ^ (r & 7)) << 4), v[at][p]);
       }
     }
   }
+}
+__device__ __forceinline__ void bs_stage_h_any(const __half* src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
+  if (NPw <= 64) bs_stage_h<2, 6>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
+  else if (natoms <= 2) bs_stage_h<3, 2>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
+  else bs_stage_h<3, 6>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
 }
 
 // sum(x), sum(x^2) of the rows of a residual-stream input, from the staged fp16 tiles (i.e. of exactly the values the GEMM multiplies).
@@ -567,12 +576,11 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   {
     const int natoms = rg.a1 - rg.a0;
     if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
-      bs_stage_x(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      bs_stage_x_any(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     } else {
       const __half* src = j == 5 ? a.h16 : a.ao;
       const int ld = j == 5 ? 4 * d : d;
-      if (a.NP <= 64) bs_stage_h<2>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
-      else bs_stage_h<3>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      bs_stage_h_any(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     }
   }
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));

@@ -106,6 +106,7 @@ class GenerationResult:
     # diagnostics for near-tie analysis in tests (not part of the CT2 surface)
     min_margin: float = float("inf")
     steps: int = 0
+    step_margins: Optional[List[float]] = None  # greedy rows: top-1 / top-2 log-prob gap at every step of the best hypothesis
 
 
 def _t(x):
@@ -410,6 +411,7 @@ class WhisperOracle:
         cum = [0.0] * R
         done = [False] * R
         margin = [float("inf")] * R
+        step_margin: List[List[float]] = [[] for _ in range(R)]
         steps = 0
         for step in range(max_steps):
             logits = forward(last, step, r2c, hist)
@@ -429,6 +431,7 @@ class WhisperOracle:
                     order = np.argsort(-logp[r], kind="stable")[:2]
                     t = int(order[0])
                     margin[r] = min(margin[r], float(logp[r, order[0]] - logp[r, order[1]]))
+                    step_margin[r].append(float(logp[r, order[0]] - logp[r, order[1]]))
                     sc = float(logp[r, t])
                 else:
                     t, sc = self._sample(logp[r], topk, temperature, seed, r, step)
@@ -448,7 +451,7 @@ class WhisperOracle:
             cands = [(self._finalize_score(cum[r], len(hist[r]), lp), r) for r in rows]
             cands.sort(key=lambda x: (-x[0] if not math.isnan(x[0]) else float("inf"), x[1]))
             out.append(GenerationResult([hist[r] for _, r in cands], [s for s, _ in cands], no_speech[b],
-                                        min(margin[r] for r in rows), steps))
+                                        min(margin[r] for r in rows), steps, step_margin[cands[0][1]] if topk == 1 else None))
         return out
 
     @staticmethod

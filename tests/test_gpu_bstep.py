@@ -48,9 +48,14 @@ def compare(eng, m, feats, prompts, **kw):
             assert abs(g.scores[0] - w.scores[0]) < 0.05, (i, g.scores[0], w.scores[0])
         else:
             first = next((j for j, (x, y) in enumerate(zip(g.sequences_ids[0], w.sequences_ids[0])) if x != y), -1)
-            print("chunk %d diverges at token %d, oracle min margin %.4f" % (i, first, w.min_margin))
             compare.first_divergence.append(first)
-            assert w.min_margin < 2 * LOGIT_TOL, (i, first, w.min_margin, g.sequences_ids[0][:12], w.sequences_ids[0][:12])
+            if w.step_margins is not None and 0 <= first < len(w.step_margins):
+                # greedy rows: the oracle's own top-1 / top-2 gap AT the step where the sequences part must be a near-tie
+                print("chunk %d diverges at token %d, oracle margin at that step %.4f" % (i, first, w.step_margins[first]))
+                assert w.step_margins[first] < 2 * LOGIT_TOL, (i, first, w.step_margins[first], g.sequences_ids[0][:12], w.sequences_ids[0][:12])
+            else:
+                print("chunk %d diverges at token %d, oracle min margin %.4f" % (i, first, w.min_margin))
+                assert w.min_margin < 2 * LOGIT_TOL, (i, first, w.min_margin, g.sequences_ids[0][:12], w.sequences_ids[0][:12])
     return exact, len(want)
 
 
@@ -105,12 +110,13 @@ def test_many_row_kernel_matches_multikernel_path(micro):
             assert abs(x.scores[0] - y.scores[0]) < 5e-3
 
 
-@pytest.mark.parametrize("n_chunks,beam,late", [(2, 5, 64), (3, 1, 100)])
+@pytest.mark.parametrize("n_chunks,beam,late", [(2, 5, 64), (6, 1, 0)])
 def test_many_row_kernel_long_context(micro_ml, n_chunks, beam, late):
     """236 steps: up to 15 sixteen-key blocks per self-attention task, double-buffer wrap-around, slot bytes of all eight 32-key
-    groups; tokens vs the oracle (exact unless the oracle reports a near-tie).  Beam 5 on the micro model produces duplicate beams,
-    i.e. exact ties (margin 0) whose resolution depends on the fp32 summation order of the split-K reductions, so a divergence is
-    only required to come late; the greedy rows have no such ties."""
+    groups; tokens vs the oracle.  Beam 5 on the micro model produces duplicate beams, i.e. exact ties (margin 0) whose resolution
+    depends on the fp32 summation order of the split-K reductions, so there a divergence is only required to come late.  The six
+    greedy rows are checked exactly: a row may part from the oracle only at a step where the oracle's own top-1 / top-2 gap is below
+    twice the logit tolerance (compare() looks the gap up at that very step), and most rows must run the whole length identical."""
     st = micro_ml["tokens"]
     eng = make_engine(micro_ml, B2W_BSTEP="all")
     feats = features_for(micro_ml, n_chunks, seed=330)
@@ -118,6 +124,8 @@ def test_many_row_kernel_long_context(micro_ml, n_chunks, beam, late):
     exact, n = compare(eng, micro_ml, feats, prompts, beam_size=beam, max_length=240, suppress_tokens=[st.eot], repetition_penalty=1.3, no_repeat_ngram_size=3)
     # a divergence (only ever at a near-tie of the oracle, checked in compare) must come late
     assert all(f >= late for f in compare.first_divergence), compare.first_divergence
+    if beam == 1:
+        assert 2 * exact >= n, (exact, n)
 
 
 @pytest.mark.parametrize("n_chunks,beam,extra", [(2, 8, {}), (7, 5, dict(patience=2.0, length_penalty=0.6)), (5, 3, dict(num_hypotheses=2))])
