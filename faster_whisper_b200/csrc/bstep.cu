@@ -177,6 +177,8 @@ __device__ __noinline__ void bs_grid_barrier(const BStepArgs& a, BsShared& sh) {
   bs_sync();
   if (threadIdx.x == 0) {
     sh.epoch += gridDim.x;
+    bs_bulk_wait_all();  // this CTA's split-K reductions of the phase have landed in L2 ...
+    bs_fence_async_all();
     if (a.prof && blockIdx.x == 0) a.prof[sh.prof_i] = ds_globaltimer();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
     const unsigned target = sh.epoch;
@@ -387,6 +389,8 @@ __device__ __forceinline__ void bs_row_stats(const float* st, int r, int d, floa
 // These functions run once per GEMM run on eight warps, so their cost is their INSTRUCTION COUNT (the first version, 2 240 SASS
 // instructions fully unrolled with per-unit 64-bit address math and statistics, took 7-14 k cycles no matter how many rows): the work
 // is flattened into units (atom, 32-row pass), G units are in flight per thread, and a unit is a handful of instructions.
+// (Measured alternatives, same box: sixteen lanes per row with five exact 16-row passes and whole-atom groups sized by the CTA's atom
+// count had shorter staging timers but a 4 % slower step — 3.46 vs 3.31 ms; this version is the one that won.)
 __device__ __forceinline__ void bs_sts64(uint32_t addr, uint32_t v0, uint32_t v1) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v0), "r"(v1) : "memory");
 }
@@ -396,85 +400,82 @@ __device__ __forceinline__ void bs_sts128(uint32_t addr, const uint4& v) {
 // atom i of the run -> k-atom: the first n0 atoms belong to the run's first segment (starting at ka00), the rest to the second
 __device__ __forceinline__ int bs_atom_ka(int i, int n0, int ka00) { return i < n0 ? ka00 + i : i - n0; }
 
-// fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Sixteen lanes
-// read the sixteen float4s of a row's 64 values (two whole 128-byte lines per row); P16 = 16-row passes per atom (80 rows are exactly
-// five), GA = atoms in flight together (one memory round trip per GA atoms).  Every unit is predicated, not branched around (register
-// arrays that are defined under a branch end up in local memory), so a switched-off unit still costs its issue slots: a CTA with one
-// or two atoms (the N = d matrices) takes the GA = 2 instance, the others GA = 5 — a CTA's usual share of the wide matrices.
-template <int P16, int GA>
+// fp32 residual stream, n-block-major -> raw fp16 (the LayerNorm is applied by the consumer of the GEMM output).  Lane c of a row's
+// eight lanes loads the float4s c and 8 + c of the row's 64 values: each instruction of a warp reads whole 128-byte lines.
+template <int PASSES>
 __device__ __noinline__ void bs_stage_x(const float* __restrict__ x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
-  const int tid = threadIdx.x, c = tid & 15, r_lo = tid >> 4;
-  const int row_off = (r0 + r_lo) * 128 + c * 4;           // this thread's float4 inside an n-block's [R x 128] block, pass 0
-  const uint32_t xs_s = smem_u32(xs) + 8 * c;              // its 8 bytes of fp16 inside a tile row (before the swizzle)
+  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+  constexpr int G = 9;  // 18 x 16 bytes in flight per thread
+  const int row_off = (r0 + r_lo) * 128 + c * 4;          // this thread's first float inside an n-block's [R x 128] block, pass 0
+  const int st_off = 8 * c;                                // its 8 bytes inside the row's first 64-byte half (before the swizzle)
+  const uint32_t xs_s = smem_u32(xs);
+  int li = 0, lp = 0, si = 0, sp = 0;                      // load / store cursors (atom, pass)
 #pragma unroll 1
-  for (int i0 = 0; i0 < natoms; i0 += GA) {
-    float4 f[GA][P16];
+  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
+    float4 f0[G], f1[G];
 #pragma unroll
-    for (int at = 0; at < GA; ++at) {
-      const int ka = bs_atom_ka(i0 + at, n0, ka00);
-      const float* base = x + ((ka >> 1) * R) * 128 + (ka & 1) * 64 + row_off;
-#pragma unroll
-      for (int p = 0; p < P16; ++p) {
-        f[at][p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i0 + at < natoms && r_lo + 16 * p < Rw) f[at][p] = __ldcg(reinterpret_cast<const float4*>(base + 16 * p * 128));
+    for (int g = 0; g < G; ++g) {
+      f0[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      f1[g] = f0[g];
+      if (li < natoms && r_lo + 32 * lp < Rw) {
+        const int ka = bs_atom_ka(li, n0, ka00);
+        const float* ptr = x + ((ka >> 1) * R + 32 * lp) * 128 + (ka & 1) * 64 + row_off;
+        f0[g] = __ldcg(reinterpret_cast<const float4*>(ptr));
+        f1[g] = __ldcg(reinterpret_cast<const float4*>(ptr + 32));
+      }
+      if (++lp == PASSES) {
+        lp = 0;
+        ++li;
       }
     }
 #pragma unroll
-    for (int at = 0; at < GA; ++at) {
-      const uint32_t tile = xs_s + (i0 + at) * (NPw * 128);
-#pragma unroll
-      for (int p = 0; p < P16; ++p) {
-        const int r = r_lo + 16 * p;
-        if (i0 + at < natoms) bs_sts64((tile + r * 128) ^ ((r & 7) << 4), pack_half2(f[at][p].x, f[at][p].y), pack_half2(f[at][p].z, f[at][p].w));
+    for (int g = 0; g < G; ++g) {
+      const int r = r_lo + 32 * sp;
+      if (si < natoms && r < NPw) {
+        const uint32_t row = xs_s + si * (NPw * 128) + r * 128;
+        const int sw = (r & 7) << 4;
+        bs_sts64(row + (st_off ^ sw), pack_half2(f0[g].x, f0[g].y), pack_half2(f0[g].z, f0[g].w));
+        bs_sts64(row + ((64 + st_off) ^ sw), pack_half2(f1[g].x, f1[g].y), pack_half2(f1[g].z, f1[g].w));
+      }
+      if (++sp == PASSES) {
+        sp = 0;
+        ++si;
       }
     }
-  }
-}
-__device__ __forceinline__ void bs_stage_x_any(const float* x, int R, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
-  switch (NPw >> 4) {  // NPw is a multiple of 16, <= 80
-    case 1: bs_stage_x<1, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
-    case 2: bs_stage_x<2, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
-    case 3: bs_stage_x<3, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
-    case 4: bs_stage_x<4, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs); break;
-    default:
-      if (natoms <= 2) bs_stage_x<5, 2>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs);
-      else bs_stage_x<5, 5>(x, R, r0, Rw, NPw, natoms, n0, ka00, xs);
-      break;
   }
 }
 
-// fp16 activations [R][ld] row-major: eight lanes read a row's eight 16-byte chunks, PASSES 32-row passes per atom, GA atoms in flight
-template <int PASSES, int GA>
+// fp16 activations [R][ld] row-major: one 16-byte chunk per unit
+template <int PASSES>
 __device__ __noinline__ void bs_stage_h(const __half* __restrict__ src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
   const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
+  constexpr int G = 12;
   const int row_off = (r0 + r_lo) * ld + c * 8;
   const uint32_t xs_s = smem_u32(xs);
+  int li = 0, lp = 0, si = 0, sp = 0;
 #pragma unroll 1
-  for (int i0 = 0; i0 < natoms; i0 += GA) {
-    uint4 v[GA][PASSES];
+  for (int u0 = 0; u0 < natoms * PASSES; u0 += G) {
+    uint4 v[G];
 #pragma unroll
-    for (int at = 0; at < GA; ++at) {
-      const __half* base = src + row_off + bs_atom_ka(i0 + at, n0, ka00) * 64;
-#pragma unroll
-      for (int p = 0; p < PASSES; ++p) {
-        v[at][p] = make_uint4(0u, 0u, 0u, 0u);
-        if (i0 + at < natoms && r_lo + 32 * p < Rw) v[at][p] = __ldcg(reinterpret_cast<const uint4*>(base + 32 * p * ld));
+    for (int g = 0; g < G; ++g) {
+      v[g] = make_uint4(0u, 0u, 0u, 0u);
+      if (li < natoms && r_lo + 32 * lp < Rw)
+        v[g] = __ldcg(reinterpret_cast<const uint4*>(src + row_off + 32 * lp * ld + bs_atom_ka(li, n0, ka00) * 64));
+      if (++lp == PASSES) {
+        lp = 0;
+        ++li;
       }
     }
 #pragma unroll
-    for (int at = 0; at < GA; ++at) {
-#pragma unroll
-      for (int p = 0; p < PASSES; ++p) {
-        const int r = r_lo + 32 * p;
-        if (i0 + at < natoms && r < NPw) bs_sts128(xs_s + (i0 + at) * (NPw * 128) + r * 128 + ((c ^ (r & 7)) << 4), v[at][p]);
+    for (int g = 0; g < G; ++g) {
+      const int r = r_lo + 32 * sp;
+      if (si < natoms && r < NPw) bs_sts128(xs_s + si * (NPw * 128) + r * 128 + ((c ^ (r & 7)) << 4), v[g]);
+      if (++sp == PASSES) {
+        sp = 0;
+        ++si;
       }
     }
   }
-}
-__device__ __forceinline__ void bs_stage_h_any(const __half* src, int ld, int r0, int Rw, int NPw, int natoms, int n0, int ka00, unsigned char* xs) {
-  if (NPw <= 64) bs_stage_h<2, 6>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
-  else if (natoms <= 2) bs_stage_h<3, 2>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
-  else bs_stage_h<3, 6>(src, ld, r0, Rw, NPw, natoms, n0, ka00, xs);
 }
 
 // sum(x), sum(x^2) of the rows of a residual-stream input, from the staged fp16 tiles (i.e. of exactly the values the GEMM multiplies).
@@ -482,30 +483,34 @@ __device__ __forceinline__ void bs_stage_h_any(const __half* src, int ld, int r0
 // Runs after the MMA thread has been signalled — the few CTAs with a duty atom do this while their UMMAs execute.
 __device__ __forceinline__ void bs_red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __noinline__ void bs_tile_stats(float* st, int r0, int Rw, int NPw, int natoms, int n0, int ka00, int nb0, int nblocks, const unsigned char* xs) {
-  // thread 2 r + half reads the four 16-byte chunks of its half of row r (with the swizzle the eight rows of a quarter warp hit eight
-  // different bank groups), sums locally, one shuffle joins the halves: a single pass, no loop over rows
-  const int tid = threadIdx.x, r = tid >> 1, half = tid & 1;
+  const int tid = threadIdx.x, c = tid & 7, r_lo = tid >> 3;
 #pragma unroll 1
   for (int i = 0; i < natoms; ++i) {
     const int ka = bs_atom_ka(i, n0, ka00), nb = i < n0 ? nb0 : nb0 + 1;
     if (nb != ka % nblocks) continue;  // uniform over the CTA
-    const unsigned char* row = xs + i * (NPw * 128) + r * 128;
-    float s1 = 0.f, s2 = 0.f;
-    if (r < Rw) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 v = *reinterpret_cast<const uint4*>(row + (((4 * half + c) ^ (r & 7)) << 4));
+    const unsigned char* tile = xs + i * (NPw * 128);
+#pragma unroll 1
+    for (int rb = 0; rb < NPw; rb += 32) {  // uniform trip count: the shuffles below involve whole warps
+      const int r = rb + r_lo;
+      float s1 = 0.f, s2 = 0.f;
+      if (r < Rw) {
+        const uint4 v = *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
         const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
         const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z)), a3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-        s1 += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
-        s2 += ((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y)) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y));
+        s1 = ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+        s2 = ((a0.x * a0.x + a0.y * a0.y) + (a1.x * a1.x + a1.y * a1.y)) + ((a2.x * a2.x + a2.y * a2.y) + (a3.x * a3.x + a3.y * a3.y));
       }
-    }
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-    if (half == 0 && r < Rw) {
-      bs_red_add_f32(st + 2 * (r0 + r), s1);
-      bs_red_add_f32(st + 2 * (r0 + r) + 1, s2);
+      // the eight chunks of a row sit in eight consecutive lanes
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+      if (c == 0 && r < Rw) {
+        bs_red_add_f32(st + 2 * (r0 + r), s1);
+        bs_red_add_f32(st + 2 * (r0 + r) + 1, s2);
+      }
     }
   }
 }
@@ -567,6 +572,27 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
     }                                                                    \
   } while (0)
 
+// Drain this warp's share of one accumulator ([128 channels] x [half_cols rows]) into the fp32 staging tile: y = acc * wsc + bv.
+// A leaf function on purpose: the 32 data registers of the wide TMEM load stay out of the GEMM phase's own live ranges (which the
+// whole call graph pays for in spills).
+__device__ __noinline__ void bs_drain_acc(uint32_t taddr, float* stg_col, int half_cols, float wsc, float bv) {
+  // stg_col = &stg[first row of this warp's half][this thread's channel]; rows are 128 floats apart
+#pragma unroll 1
+  for (int c = 0; c < half_cols; c += 16) {  // half_cols is a multiple of 8
+    uint32_t v0[8], v1[8];
+    const bool two = c + 8 < half_cols;
+    bs_tmem_ld8(taddr + c, v0);
+    if (two) bs_tmem_ld8(taddr + c + 8, v1);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) stg_col[(c + i) * 128] = fmaf(__uint_as_float(v0[i]), wsc, bv);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) stg_col[(c + 8 + i) * 128] = fmaf(__uint_as_float(v1[i]), wsc, bv);
+    }
+  }
+}
+
 __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int s, unsigned char* U, unsigned char* ring) {
   const BsRange rg = bs_range(sh, s);
   if (rg.a1 <= rg.a0) return;
@@ -576,11 +602,13 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   {
     const int natoms = rg.a1 - rg.a0;
     if (j == 0 || j == 2 || j == 4) {  // fp32 residual stream
-      bs_stage_x_any(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      if (a.NP <= 64) bs_stage_x<2>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_x<3>(a.x, a.R, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     } else {
       const __half* src = j == 5 ? a.h16 : a.ao;
       const int ld = j == 5 ? 4 * d : d;
-      bs_stage_h_any(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      if (a.NP <= 64) bs_stage_h<2>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
+      else bs_stage_h<3>(src, ld, 0, a.R, a.NP, natoms, rg.n0, rg.ka00, U);
     }
   }
   float* out = j == 0 ? a.qkv32 : (j == 2 ? a.cq32 : (j == 4 ? a.h32 : a.x));
@@ -618,14 +646,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
       wsc = (a.w8 && n_glob < N) ? __ldg(lay.scale[j] + n_glob) : 1.f;
     }
     const uint32_t taddr = sh.tmem_base + (uint32_t(q * 32) << 16) + sg * 128 + ch * half_cols;
-#pragma unroll 1
-    for (int c = 0; c < half_cols; c += 8) {  // (wider batches of TMEM loads cost registers that the whole call graph then pays for in spills)
-      uint32_t v[8];
-      bs_tmem_ld8(taddr + c, v);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) stg[(ch * half_cols + c + i) * 128 + q * 32 + lane] = fmaf(__uint_as_float(v[i]), wsc, bv);
-    }
+    bs_drain_acc(taddr, stg + (ch * half_cols) * 128 + q * 32 + lane, half_cols, wsc, bv);
     fence_proxy_async();
     bs_sync();
     if (tid == 0) {  // rows 0 .. R-1 of the staging tile = the segment's contiguous [R x 128] block of the n-block-major output
@@ -637,11 +658,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   }
   tc_fence_before();
   BS_TICK(2);
-  if (tid == 0) {
-    bs_bulk_wait_all();
-    bs_fence_async_all();
-  }
-  BS_TICK(3);
+  // (the bulk reductions are awaited in the grid barrier: whatever the phase still has to do — zeroing a consumed buffer — overlaps them)
   if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[j * 8 + 7] += 1;
 }
 
@@ -898,6 +915,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
   float oacc[8][4];
   uint4 qf0 = make_uint4(0u, 0u, 0u, 0u), qf1 = make_uint4(0u, 0u, 0u, 0u);
   int piece_first = 0;
+  unsigned early_cnt = 0u;  // thread 0: the piece counter of the group the run ends in, requested one tile ahead
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
     const int tile = t0 + k, grp = tile / S, split = tile - grp * S, gi = grp - g_first;
@@ -918,6 +936,8 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       qf1 = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
     }
     long long tp = clock64();
+    if (k == nt - 1 && tid == 0 && split != S - 1)  // the run ends inside this group: if it holds the first split it will merge the group
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(early_cnt) : "l"(a.xcounters + grp) : "memory");
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
     BS_ATICK(7, 0, tp);
     const int ngroups16 = (nk + 15) >> 4;
@@ -1057,20 +1077,18 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       // every CTA — and whoever came last merged.)
       bs_sync();
       const bool merger = piece_first == 0;
-      if (tid == 0) {
-        unsigned* cnt = reinterpret_cast<unsigned*>(a.xcounters + grp);
-        if (!merger) {
-          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((unsigned)n_piece) : "memory");
-        } else {
-          unsigned v;
-          do {
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
-          } while (v < (unsigned)(S - n_piece));
+      unsigned* cnt = reinterpret_cast<unsigned*>(a.xcounters + grp);
+      if (!merger) {
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"((unsigned)n_piece) : "memory");
+      } else {  // merge the pieces (their first splits are where some CTA's run starts, or 0)
+        if (tid == 0) {
+          // `early_cnt` was requested before this tile was processed: normally it already shows the count complete, and no
+          // round trip is spent on polling (the records are then read AFTER the count was seen complete, as the ordering requires)
+          unsigned v = early_cnt;
+          while (v < (unsigned)(S - n_piece)) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
           asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cnt), "r"(0u) : "memory");  // next use: the next layer, a grid barrier away
         }
-      }
-      if (merger) bs_sync();
-      if (merger) {  // merge the pieces (their first splits are where some CTA's run starts, or 0)
+        bs_sync();
         const float* pg = a.xpart + (long long)grp * S * (kBsXQ * 66);
         unsigned present = 1u;
         for (int s2 = 1; s2 < S; ++s2) present |= bs_piece_starts_at(grp * S + s2, NT) ? (1u << s2) : 0u;
@@ -1315,14 +1333,14 @@ __global__ void __launch_bounds__(kBsLaunch, 1) bstep_kernel(const BStepArgs a_p
           case 0: bs_gemm_phase(a, sh, 6 * l + 0, U, ring); break;
           case 1: bs_self_attn_phase(a, sh, l, U); break;
           case 2:
-            bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer
             bs_gemm_phase(a, sh, 6 * l + 1, U, ring);
+            bs_zero_f32(a.qkv32, bs_bsize(a.R, 3 * a.d));  // consumed by the self-attention of this layer; overlaps the bulk reduction
             break;
           case 3: bs_gemm_phase(a, sh, 6 * l + 2, U, ring); break;
           case 4: bs_cross_attn_phase(a, sh, l, kv0, U); break;
           case 5:
-            bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer
             bs_gemm_phase(a, sh, 6 * l + 3, U, ring);
+            bs_zero_f32(a.cq32, bs_bsize(a.R, a.d));  // consumed by the cross attention of this layer; overlaps the bulk reduction
             break;
           case 6: bs_gemm_phase(a, sh, 6 * l + 4, U, ring); break;
           case 7: bs_gelu_phase(a, sh, l); break;
