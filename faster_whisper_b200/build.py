@@ -37,9 +37,13 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, ticks: bool = False) -> str:
+    """``ticks=True`` builds libb200whisper_ticks.so with the cycle counters of the persistent step kernels compiled in
+    (-DB2W_STEP_TICKS); point B2W_LIBRARY at it for a B2W_DSTEP_PROF=1 profile run."""
     nvcc = _nvcc()
-    obj_dir = os.path.join(ROOT, "build", "obj")
+    obj_dir = os.path.join(ROOT, "build", "obj_ticks" if ticks else "obj")
+    lib = LIB.replace(".so", "_ticks.so") if ticks else LIB
+    flags = NVCC_FLAGS + (["-DB2W_STEP_TICKS"] if ticks else [])
     os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(ROOT, "include", "b200whisper.h"))
@@ -50,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -64,13 +68,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             list(pool.map(run, jobs))
-    if jobs or force or _stale(LIB, objs):
+    if jobs or force or _stale(lib, objs):
         # link to a temporary name and rename: a concurrent reader (a gpurun snapshot, another process) never sees a half-written library
-        tmp = LIB + ".tmp%d" % os.getpid()
+        tmp = lib + ".tmp%d" % os.getpid()
         run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-Xcompiler", "-fPIC"])
-        os.replace(tmp, LIB)
-    return LIB
+        os.replace(tmp, lib)
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ticks="--ticks" in sys.argv))

@@ -554,6 +554,12 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
   bs_sync();
 }
 
+// Cycle counters of CTA 0 (B2W_DSTEP_PROF) are compiled in only with -DB2W_STEP_TICKS (python -m faster_whisper_b200.build --ticks
+// builds libb200whisper_ticks.so): the phase code runs once per phase on eight warps, so every instruction of it counts, and the
+// counters hold registers across loops that have none to spare.  The %globaltimer stamps at the grid barriers stay in both builds.
+#ifdef B2W_STEP_TICKS
+#define BS_TICK_DECL(tp) long long tp = clock64()
+#define BS_TICK_COUNT(kind) do { if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) sh.ticks[(kind) * 8 + 7] += 1; } while (0)
 #define BS_ATICK(kind, point, tp)                                        \
   do {                                                                   \
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
@@ -562,15 +568,12 @@ __device__ __noinline__ void bs_widen_atoms(BsShared& sh, int natoms, unsigned c
       (tp) = _now;                                                       \
     }                                                                    \
   } while (0)
-
-#define BS_TICK(point)                                                   \
-  do {                                                                   \
-    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {                 \
-      const long long _now = clock64();                                  \
-      sh.ticks[j * 8 + (point)] += (unsigned)(_now - tp);                \
-      tp = _now;                                                         \
-    }                                                                    \
-  } while (0)
+#else
+#define BS_TICK_DECL(tp) do { } while (0)
+#define BS_TICK_COUNT(kind) do { } while (0)
+#define BS_ATICK(kind, point, tp) do { } while (0)
+#endif
+#define BS_TICK(point) BS_ATICK(j, point, tp)
 
 // Drain this warp's share of one accumulator ([128 channels] x [half_cols rows]) into the fp32 staging tile: y = acc * wsc + bv.
 // A leaf function on purpose: the 32 data registers of the wide TMEM load stay out of the GEMM phase's own live ranges (which the
@@ -597,7 +600,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   const BsRange rg = bs_range(sh, s);
   if (rg.a1 <= rg.a0) return;
   const int l = s / 6, j = s - 6 * l, d = a.d, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long tp = clock64();
+  BS_TICK_DECL(tp);
   const BLayer& lay = sh.lay[l];
   {
     const int natoms = rg.a1 - rg.a0;
@@ -659,7 +662,7 @@ __device__ __noinline__ void bs_gemm_phase(const BStepArgs& a, BsShared& sh, int
   tc_fence_before();
   BS_TICK(2);
   // (the bulk reductions are awaited in the grid barrier: whatever the phase still has to do — zeroing a consumed buffer — overlaps them)
-  if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[j * 8 + 7] += 1;
+  BS_TICK_COUNT(j);
 }
 
 // Masked self-attention: one (row, head) task per warp.  q, k, v of the new token come from the raw QKV sums (deferred LayerNorm +
@@ -682,24 +685,13 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
   const int ntasks = H * a.R, e0 = 2 * lane;
   const int pos_stride = a.slots * d;  // elements between consecutive positions of a chunk
   const int crow = lane >> 3, cchunk = lane & 7;  // copy role: row (of four per instruction) and 16-byte chunk
-  // The coherent loads a task starts with (raw q/k/v, statistics: a post-barrier L2 round trip, ~2 500 cycles) are requested one task
-  // ahead, so a warp's second task finds them in registers.
-  float2 nrq = make_float2(0.f, 0.f), nrk = nrq, nrv = nrq, nst = nrq;
-  auto prefetch = [&](int tsk) {
-    const int r = tsk / H, h = tsk - r * H;
-    nst = __ldcg(reinterpret_cast<const float2*>(st) + r);
-    nrq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0)));
-    nrk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0)));
-    nrv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
-  };
   const int task0 = blockIdx.x * kBsWarps + warp, tstride = gridDim.x * kBsWarps;
-  if (task0 < ntasks) prefetch(task0);
 #pragma unroll 1
   for (int task = task0; task < ntasks; task += tstride) {
     const int r = task / H, h = task - r * H;
     const RowInfo ri = sh.rows[r];
     const int pos = ri.pos;
-    long long tp = clock64();
+    BS_TICK_DECL(tp);
     const uint8_t* anc = a.anc + (pos & 1) * a.anc_buf_stride + ((long long)ri.chunk * a.slots + ri.slot) * n_ctx;
     uint32_t slots[4] = {0u, 0u, 0u, 0u};  // lane holds the slot byte of key 32 i + lane for i < 14 (n_ctx <= 448)
 #pragma unroll
@@ -708,10 +700,12 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       const uint32_t sv = (jj < pos) ? (uint32_t)__ldg(anc + jj) : 0u;
       slots[i >> 2] |= sv << (8 * (i & 3));
     }
-    const float2 rq = nrq, rk = nrk, rv = nrv;
-    const float mean = nst.x / d;
-    const float rstd = rsqrtf(fmaxf(nst.y / d - mean * mean, 0.f) + 1e-5f);
-    if (task + tstride < ntasks) prefetch(task + tstride);
+    // (requesting a warp's second task's coherent loads one task ahead was measured: no gain, and its eight registers cost spills)
+    float mean, rstd;
+    bs_row_stats(st, r, d, mean, rstd);
+    const float2 rq = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, h * 64 + e0))),
+                 rk = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, d + h * 64 + e0))),
+                 rv = __ldcg(reinterpret_cast<const float2*>(a.qkv32 + bs_bidx(a.R, r, 2 * d + h * 64 + e0)));
     const float* ws = lay.wsum[0] + h * 64 + e0;
     const float* bs = lay.bias[0] + h * 64 + e0;
     const float2 wq = __ldg(reinterpret_cast<const float2*>(ws)), wk = __ldg(reinterpret_cast<const float2*>(ws + d)),
@@ -839,7 +833,7 @@ __device__ __noinline__ void bs_self_attn_phase(const BStepArgs& a, BsShared& sh
       }
       __syncwarp();  // the buffer may be refilled by the copies issued in the next iteration
       BS_ATICK(6, 3, tp);
-      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[6 * 8 + 7] += 1;
+      BS_TICK_COUNT(6);
     }
     float l_run = l_part;
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
@@ -935,7 +929,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
       qf0 = *reinterpret_cast<const uint4*>(qs + 8 * t);
       qf1 = *reinterpret_cast<const uint4*>(qs + 32 + 8 * t);
     }
-    long long tp = clock64();
+    BS_TICK_DECL(tp);
     if (k == nt - 1 && tid == 0 && split != S - 1)  // the run ends inside this group: if it holds the first split it will merge the group
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(early_cnt) : "l"(a.xcounters + grp) : "memory");
     mbar_wait(&sh.kvfull[buf], (uint32_t)(u & 1));
@@ -1043,7 +1037,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     __syncwarp();
     if (lane == 0 && (buf == 0 || k + 2 < nt)) mbar_arrive(&sh.kvfree[buf]);
     BS_ATICK(7, 1, tp);
-    if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[7 * 8 + 7] += 1;
+    BS_TICK_COUNT(7);
     if (!piece_ends) continue;
     bs_sync();
     const int h = grp % a.H, b = grp / a.H, row0 = b * nq;

@@ -51,7 +51,11 @@ constexpr int kDsXScratch = kDsXQ * kDsQLd * 2 + kDsXQ * kDsScLd * 4 + kDsXQ * k
 // barrier of the 256 compute threads (the producer warps never join it)
 __device__ __forceinline__ void ds_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// fine-grained cycle accounting for CTA 0 (B2W_DSTEP_PROF): accumulated in shared memory, dumped to prof[3000 + kind*16 + point] at the end
+// fine-grained cycle accounting for CTA 0 (B2W_DSTEP_PROF): accumulated in shared memory, dumped to prof[3000 + kind*16 + point] at the
+// end.  Compiled in only with -DB2W_STEP_TICKS (libb200whisper_ticks.so): the phase code runs once per phase, every instruction counts.
+#ifdef B2W_STEP_TICKS
+#define DS_TICK_DECL(tp) long long tp = clock64()
+#define DS_TICK_COUNT(a, kind) do { if ((a).prof && blockIdx.x == 0 && threadIdx.x == 0) sh.ticks[(kind) * 8 + 7] += 1; } while (0)
 #define DS_TICK(a, kind, point, tprev)                                    \
   do {                                                                    \
     if ((a).prof && blockIdx.x == 0 && threadIdx.x == 0) {                \
@@ -60,6 +64,11 @@ __device__ __forceinline__ void ds_sync() { asm volatile("bar.sync 1, 256;" ::: 
       (tprev) = _now;                                                     \
     }                                                                     \
   } while (0)
+#else
+#define DS_TICK_DECL(tp) do { } while (0)
+#define DS_TICK_COUNT(a, kind) do { } while (0)
+#define DS_TICK(a, kind, point, tprev) do { } while (0)
+#endif
 
 // per-CTA state that lives in shared memory (pointers/tables are never re-fetched from L2 inside the layer loop)
 struct DsShared {
@@ -177,7 +186,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     case 5: mode = DS_RESID; src16 = a.h + (blockIdx.x & 3) * d; src_ld = 4 * d; break;
     default: mode = DS_F32; ln = 1; break;
   }
-  long long tp = clock64();
+  DS_TICK_DECL(tp);
   // ---- input rows -> xs [8][d + 32] halves, straight from L2 (one round trip) ----
   if (ln) {
     if (warp < a.R) {  // one warp per row: single-pass LayerNorm from registers (affine part folded into the weights)
@@ -313,7 +322,7 @@ __device__ __noinline__ int ds_gemv_phase(const DStepArgs& a, DsShared& sh, int 
     }
     if (first) {
       DS_TICK(a, sub, 3, tp);  // epilogue
-      if (a.prof && blockIdx.x == 0 && tid == 0) sh.ticks[sub * 8 + 7] += 1;
+      DS_TICK_COUNT(a, sub);
     }
     first = false;
   }

@@ -15,3 +15,12 @@ if [ -n "$TESTS" ]; then
   timeout -s KILL 900 python -m pytest -q -m gpu -p no:cacheprovider $TESTS -rs > gpurun_out/test_bstep.log 2>&1; echo "pytest exit $?"
   tail -n 8 gpurun_out/test_bstep.log | cut -c1-300
 fi
+if [ -n "$SINGLE_LIBS" ]; then  # the single-chunk step (dstep_kernel): one chunk, beam 5
+  for lib in $SINGLE_LIBS; do
+    if [ "$lib" = intree ]; then unset B2W_LIBRARY; else export B2W_LIBRARY=$PWD/$lib; fi
+    echo "== single-chunk $lib" >> gpurun_out/libs_ab.log
+    timeout -s KILL 300 python tools/step_ab.py --batch 1 --repeat ${REPEAT:-3} >> gpurun_out/libs_ab.log 2>&1; echo "single $lib exit $?"
+  done
+  unset B2W_LIBRARY
+  grep -A1 "^== single" gpurun_out/libs_ab.log | cut -c1-200
+fi
