@@ -874,6 +874,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
   __half* qs_all = reinterpret_cast<__half*>(scratch);                          // [kBsXGroups][8][96], pre-scaled by 1/8
   float* mb = reinterpret_cast<float*>(qs_all + kBsXGroups * kBsXQ * kBsQLd);  // [8 warps][8 queries][64 + m + l]
   const BLayer& lay = sh.lay[l];
+  BS_TICK_DECL(tp0);
   if (lane == 0 && nt > 1) mbar_arrive(&sh.kvfree[1]);  // the multi-purpose region is free for K/V tiles now (one arrival per warp)
   // ---- queries of every group this run touches, in one round trip (deferred LayerNorm + bias, fp16 rounding, then the exact 1/8) ----
   const int g_first = t0 / S, n_groups = (t1 - 1) / S - g_first + 1;
@@ -904,6 +905,7 @@ __device__ __noinline__ void bs_cross_attn_phase(const BStepArgs& a, BsShared& s
     *reinterpret_cast<uint4*>(qs_all + (gi * kBsXQ + q) * kBsQLd + c * 8) = v;
   }
   bs_sync();
+  BS_ATICK(7, 3, tp0);  // prologue: queries staged
   // per-thread state of the current piece: query row g (the accumulator rows g + 8 are padding), this warp's share of the keys
   float m_run = -INFINITY, l_run = 0.f;
   float oacc[8][4];
