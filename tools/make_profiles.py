@@ -1,6 +1,6 @@
 """Turn the scratch output of a profiling gpurun (gpurun_out/) into the committed evidence under profiles/ (round 2).
 
-    python tools/make_profiles.py            # after tools/gpu_profile.sh, tools/gpu_bench_final.sh, tools/gpu_bstep3.sh ran on the GPU box
+    python tools/make_profiles.py            # after tools/gpu_profile.sh and tools/gpu_final.sh ran on the GPU box
 """
 import csv
 import gzip
@@ -106,12 +106,14 @@ def main():
         with open(os.path.join(PROF, f"{TAG}_launches_batched_summary.txt"), "w") as f:
             f.write("ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary`\n"
                     "(the default batched line: 16 chunks per step; per-launch times are cold-cache and serialised — compare SHARES, not absolutes)\n\n" + summ)
-    err = os.path.join(OUT, "bench_b16.err")
-    if os.path.exists(err):
-        lines = [ln for ln in open(err) if "bstep prof" in ln]
-        with open(os.path.join(PROF, f"{TAG}_bstep_phase_profile.txt"), "w") as f:
-            f.write("B2W_DSTEP_PROF=1 python bench.py --workload batched --steps 3: device timers of bstep_kernel, CTA 0 (last decode step of each generate, t = 132;\n"
-                    "globaltimer at every grid barrier = work / barrier wait per phase; clock64 counters inside the GEMM and attention phases)\n\n" + "".join(lines[-17:]))
+    for log, out, kern in (("step_prof.log", "bstep_phase_profile", "bstep"), ("step_prof_single.log", "dstep_phase_profile", "dstep")):
+        err = os.path.join(OUT, log)
+        if os.path.exists(err):
+            lines = [ln for ln in open(err) if f"{kern} prof" in ln or "decode" in ln]
+            with open(os.path.join(PROF, f"{TAG}_{out}.txt"), "w") as f:
+                f.write(f"B2W_LIBRARY=libb200whisper_ticks.so python tools/step_ab.py --prof (large-v3, prompt 4 + 128 tokens): device timers of {kern}_kernel, CTA 0\n"
+                        "(last decode step, t = 132; %globaltimer at every grid barrier = work / barrier wait per phase; clock64 counters inside the phases —\n"
+                        "the counters are compiled in only in the ticks build, which is ~3 % slower than the default one)\n\n" + "".join(lines[-22:]))
     for src, dst in (("bench_default.json", "bench_default"), ("bench_reference.json", "bench_reference"), ("bench_b16_int8.json", "bench_batched_int8"),
                      ("bench_b1_dstep.json", "bench_single")):
         p = os.path.join(OUT, src)
