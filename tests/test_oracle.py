@@ -156,3 +156,18 @@ def test_align_shapes_and_probabilities(micro):
     assert ti[0] == 0 and ti[-1] == len(text[0]) and fi[0] == 0 and fi[-1] == 1499  # rows predict text + eot
     assert (np.diff(ti) >= 0).all() and (np.diff(fi) >= 0).all()
     assert len(res.text_token_probs) == len(text[0]) and all(0.0 <= p <= 1.0 for p in res.text_token_probs)
+
+
+def test_greedy_rows_report_the_margin_of_every_step(micro):
+    """The GPU parity tests accept a divergence only where the oracle's own top-1 / top-2 gap AT THAT STEP is a near-tie: greedy rows
+    carry one gap per generated token, their minimum is min_margin; beam search has no per-step list."""
+    o, st = micro["oracle"], micro["tokens"]
+    rng = np.random.default_rng(5)
+    feats = rng.standard_normal((2, micro["dims"].n_mels, 3000)).astype(np.float32) * 0.1
+    enc = o.encode(feats)
+    res = o.generate(enc, [[st.sot, st.no_timestamps]] * 2, beam_size=1, max_length=14, suppress_tokens=[st.eot])
+    for r in res:
+        assert r.step_margins is not None and len(r.step_margins) == len(r.sequences_ids[0]) == r.steps
+        assert all(m >= 0 for m in r.step_margins) and abs(min(r.step_margins) - r.min_margin) < 1e-12
+    res = o.generate(enc, [[st.sot, st.no_timestamps]] * 2, beam_size=3, max_length=10)
+    assert all(r.step_margins is None for r in res)
