@@ -17,7 +17,7 @@ ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--new-tokens", type=int, default=128)
 ap.add_argument("--beam", type=int, default=5)
 ap.add_argument("--repeat", type=int, default=2)
-ap.add_argument("--configs", default="-", help="';'-separated settings, each a ','-separated list of NAME=VALUE environment assignments ('-' = none)")
+ap.add_argument("--configs", default="none", help="';'-separated settings, each a ','-separated list of NAME=VALUE environment assignments ('none' = no assignment)")
 ap.add_argument("--compute-type", default="float16")
 ap.add_argument("--prof", action="store_true")
 a = ap.parse_args()
