@@ -151,6 +151,15 @@ def test_word_timestamps_match_reference(both):
     dict(language="en", beam_size=2, max_new_tokens=6, chunk_length=20, max_initial_timestamp=0.5, suppress_blank=False,
          suppress_tokens=[-1, 100, 200], length_penalty=0.8, patience=1.5, repetition_penalty=1.2, no_repeat_ngram_size=2, **COMMON),
     dict(language="en", beam_size=1, max_new_tokens=8, clip_timestamps=[2.0, 21.5], word_timestamps=True, **COMMON),
+    # sampling fallback chain driven by the compression-ratio and log-prob tests; prompt given as token ids; empty suppress list
+    dict(language="en", beam_size=2, best_of=3, max_new_tokens=8, temperature=[0.0, 0.5, 1.0], compression_ratio_threshold=0.1, log_prob_threshold=-0.01,
+         no_speech_threshold=0.99, initial_prompt=[100, 200, 300], suppress_tokens=[]),
+    # best_of sampling only, previous-text conditioning across windows, language detection on a later window
+    dict(beam_size=1, best_of=2, temperature=0.7, max_new_tokens=6, condition_on_previous_text=True, language_detection_segments=2,
+         language_detection_threshold=0.05, **COMMON),
+    # hotwords without a prompt, timestamps on, vad parameters given although the filter is off, short chunk length
+    dict(language="it", task="transcribe", beam_size=2, max_new_tokens=7, hotwords="uno due tre", chunk_length=15, vad_filter=False,
+         vad_parameters=dict(threshold=0.4), **COMMON),
 ])
 def test_more_sequential_options_match_reference(both, kw):
     fw, ref_model, our_model, calls_ref, calls_our = both
