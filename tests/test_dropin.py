@@ -88,6 +88,12 @@ def test_sequential_transcribe_matches_reference(both, kw):
 @pytest.mark.parametrize("kw", [
     dict(language="en", beam_size=2, batch_size=2, max_new_tokens=8),
     dict(beam_size=1, batch_size=3, max_new_tokens=6, without_timestamps=False, multilingual=True),
+    # prompt and hotwords, search options, a temperature list (the batched path takes its first entry), one chunk per call
+    dict(language="fr", task="translate", beam_size=3, batch_size=1, max_new_tokens=7, initial_prompt="bonjour", hotwords="alpha beta", patience=2.0,
+         length_penalty=0.7, repetition_penalty=1.1, no_repeat_ngram_size=3, temperature=[0.2, 0.8], suppress_tokens=[-1, 50]),
+    # more chunks per call than there are chunks; thresholds that drop segments; timestamps on
+    dict(language="en", beam_size=2, batch_size=8, max_new_tokens=9, without_timestamps=False, log_prob_threshold=-0.2, no_speech_threshold=0.3,
+         compression_ratio_threshold=1.2),
 ])
 def test_batched_transcribe_matches_reference(both, kw):
     fw, ref_model, our_model, calls_ref, calls_our = both
@@ -97,7 +103,7 @@ def test_batched_transcribe_matches_reference(both, kw):
     ref_segs = [seg_tuple(s) for s in ref_segs]
     our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)
     our_segs = [seg_tuple(s) for s in our_segs]
-    assert our_segs == ref_segs and len(ref_segs) >= 4
+    assert our_segs == ref_segs and (len(ref_segs) >= 4 or "log_prob_threshold" in kw)
     assert (our_info.language, our_info.duration, our_info.duration_after_vad) == (ref_info.language, ref_info.duration, ref_info.duration_after_vad)
 
 
