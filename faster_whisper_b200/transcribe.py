@@ -347,8 +347,8 @@ class BatchedInferencePipeline:
         model.logger.info("VAD filter removed %s of audio", format_timestamp(duration - duration_after_vad))
         if not duration_after_vad:
             audio_chunks, chunks_metadata = [], []
-        # a chunk never contributes more than 30 s (the reference trims features to 3000 frames)
-        audio_chunks = [c[: 30 * sr] for c in audio_chunks]
+        # (a chunk longer than 30 s — only possible with user-supplied clips — is not cut here: like the reference, its log-mel is computed
+        #  over the whole clip and the FEATURES are trimmed to 3000 frames, see _batched_segments_generator)
 
         # ---- language ---------------------------------------------------------------------------------------
         all_language_probs = None
@@ -410,7 +410,13 @@ class BatchedInferencePipeline:
         for lo in range(0, total, batch_size):
             block = features[lo : lo + batch_size]
             if fused:
-                block = self.model.model.encode_audio(block)
+                if any(len(c) > 30 * self.model.feature_extractor.sampling_rate for c in block):
+                    # the reference's order of operations (transcribe.py:463-467,514-516): log-mel of the whole clip — its clamp maximum and
+                    # its last frames see the audio beyond 30 s — then pad_or_trim of the features
+                    fe = self.model.feature_extractor
+                    block = self.model.encode(np.stack([pad_or_trim(fe(c)[..., :-1]) for c in block]))
+                else:
+                    block = self.model.model.encode_audio(block)
             for rows in self.forward(block, tokenizer, chunks_metadata[lo : lo + batch_size], options):
                 for row in rows:
                     seg_id += 1

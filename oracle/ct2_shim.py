@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE ONLY.  Two uses, both on CPU in tests:
 Comparing the two runs checks that our host layer is a drop-in for the reference's (same segments, same info).
 """
 import types
+import zlib
 from dataclasses import dataclass, field
 from typing import List
 
@@ -59,8 +60,8 @@ def make_whisper_class(dims, weights, calls=None):
 
         def encode(self, features, to_cpu=False):
             arr = features.numpy() if hasattr(features, "numpy") else np.asarray(features)
-            if calls is not None:
-                calls.append(("encode", arr.shape))
+            if calls is not None:  # shape + checksum of the features: the drop-in tests compare what reaches the engine, bit for bit
+                calls.append(("encode", arr.shape, zlib.crc32(np.ascontiguousarray(arr, dtype=np.float32).tobytes())))
             return StorageView(tensor=oracle.encode(arr))
 
         def generate(self, features, prompts, **kw):
@@ -85,6 +86,7 @@ def make_whisper_class(dims, weights, calls=None):
         def encode_audio(self, chunks, return_features=False):
             from oracle.whisper_oracle import log_mel, pad_or_trim
 
+            assert all(len(c) <= 30 * 16000 for c in chunks), "the fused audio path is specified for chunks of at most 30 s"
             feats = np.stack([pad_or_trim(log_mel(c, dims.n_mels)[:, :-1]) for c in chunks])
             sv = self.encode(StorageView.from_array(np.ascontiguousarray(feats)))
             return (sv, feats) if return_features else sv

@@ -294,3 +294,25 @@ def test_batched_language_detection_window_spans_chunks(both):
     assert our_info.language == ref_info.language and our_info.language_probability == pytest.approx(ref_info.language_probability)
     assert [x[0] for x in our_info.all_language_probs[:5]] == [x[0] for x in ref_info.all_language_probs[:5]]
     assert our_segs == ref_segs and len(ref_segs) >= 3
+
+
+def test_batched_clip_longer_than_30s_matches_reference(both):
+    """A user-supplied clip of more than 30 s: the reference computes the log-mel of the WHOLE clip (clamp maximum, last frames) and then trims
+    the features to 3000 frames; so do we (the fused audio path is bypassed for such a block).  Also through language detection, whose
+    window is cut out of the concatenated, untrimmed chunk features."""
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    loud_tail = np.concatenate([synthetic_audio(90, 30.0), 4.0 * synthetic_audio(91, 11.0)])  # the maximum sits beyond 30 s
+    audio = np.concatenate([loud_tail, synthetic_audio(92, 20.0)])
+    clips = [{"start": 0.0, "end": 41.0}, {"start": 41.0, "end": 61.0}]
+    for kw in (dict(language="en", beam_size=2, batch_size=2, max_new_tokens=8), dict(beam_size=1, batch_size=1, max_new_tokens=6)):
+        calls_ref.clear()
+        calls_our.clear()
+        ref_segs, ref_info = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)
+        ref_segs = [seg_tuple(s) for s in ref_segs]
+        our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)
+        our_segs = [seg_tuple(s) for s in our_segs]
+        assert our_segs == ref_segs and len(ref_segs) >= 2
+        # the features that reached the encoder are the reference's, bit for bit (shape + checksum per engine call)
+        assert [c for c in calls_our if c[0] == "encode"] == [c for c in calls_ref if c[0] == "encode"]
+        assert (our_info.language, round(our_info.language_probability, 5), our_info.duration) == (
+            ref_info.language, round(ref_info.language_probability, 5), ref_info.duration)
