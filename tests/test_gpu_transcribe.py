@@ -75,3 +75,16 @@ def test_tiny_en_batched_pipeline_token_exact(tiny_en):
     want = _with_shim(mp, lambda: list(T.BatchedInferencePipeline(cpu).transcribe(audio.copy(), **kw)[0]))
     assert len(want) >= 3
     assert _tokens(got) == _tokens(want)
+
+
+def test_tiny_en_batched_clip_longer_than_30s(tiny_en):
+    """A user clip of 41 s next to a 19 s one: the long clip's block goes log-mel (whole clip, CUDA kernel) -> features trimmed -> encode,
+    the rest through the fused audio path; tokens as over the oracle shim."""
+    gpu, cpu, mp, _ = tiny_en
+    audio = np.concatenate([synthetic_audio(140, 30.0), 3.0 * synthetic_audio(141, 11.0), synthetic_audio(142, 19.0)])
+    clips = [{"start": 0.0, "end": 41.0}, {"start": 41.0, "end": 60.0}]
+    kw = dict(beam_size=1, batch_size=1, vad_filter=False, clip_timestamps=clips, max_new_tokens=24, repetition_penalty=1.2, no_repeat_ngram_size=3)
+    got = list(T.BatchedInferencePipeline(gpu).transcribe(audio.copy(), **kw)[0])
+    want = _with_shim(mp, lambda: list(T.BatchedInferencePipeline(cpu).transcribe(audio.copy(), **kw)[0]))
+    assert len(want) >= 2
+    assert _tokens(got) == _tokens(want)
