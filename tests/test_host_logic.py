@@ -212,3 +212,30 @@ def test_unloaded_model_is_never_dereferenced():
         assert len(rep._lib.destroyed) == 1
     finally:
         E._lib = old_lib
+
+
+@pytest.mark.skipif(not __import__("oracle.refload", fromlist=["reference_available"]).reference_available(), reason="reference tree not mounted (build container only)")
+def test_tokenizer_matches_the_reference_class_on_random_sequences():
+    """Our Tokenizer wrapper against the reference's own class (faster_whisper/tokenizer.py, imported unmodified) over the same HF tokenizer:
+    sot sequence, non-speech set, decode, decode_with_timestamps and the word splitting (space-based languages and the unicode path of
+    zh / ja / th / yue) on random token sequences, with and without a trailing eot."""
+    import sys
+
+    from oracle.refload import load_reference
+
+    fw = load_reference()
+    ref_cls = sys.modules[fw.__name__ + ".tokenizer"].Tokenizer
+    hf = make_tokenizer(51866)
+    rng = np.random.default_rng(0)
+    for lang in ["en", "zh", "ja", "th", "de", "yue"]:
+        ours, ref = Tokenizer(hf, True, task="transcribe", language=lang), ref_cls(hf, True, task="transcribe", language=lang)
+        assert ours.sot_sequence == ref.sot_sequence and ours.non_speech_tokens == ref.non_speech_tokens
+        assert (ours.transcribe, ours.translate, ours.sot, ours.sot_lm, ours.sot_prev, ours.eot, ours.no_timestamps, ours.no_speech, ours.timestamp_begin) == (
+            ref.transcribe, ref.translate, ref.sot, ref.sot_lm, ref.sot_prev, ref.eot, ref.no_timestamps, ref.no_speech, ref.timestamp_begin)
+        for trial in range(120):
+            n = int(rng.integers(1, 24))
+            ids = [int(x) for x in rng.integers(0, ours.eot, size=n)] + ([ours.eot] if trial % 3 == 0 else [])
+            assert ours.split_to_word_tokens(ids) == ref.split_to_word_tokens(ids), (lang, ids)
+            ts = [ours.timestamp_begin + 3] + ids[: n // 2] + [ours.timestamp_begin + 40] * 2 + ids[n // 2:] + [ours.timestamp_begin + 90]
+            assert ours.decode_with_timestamps(ts) == ref.decode_with_timestamps(ts)
+            assert ours.decode(ids) == ref.decode(ids) and ours.encode(" hello wor") == ref.encode(" hello wor")
