@@ -18,7 +18,7 @@ import numpy as np
 
 from .config import MODEL_DIMS, SpecialTokens, WhisperDims, special_tokens
 
-# B2W_LIBRARY: measurement hook — another build of the same C ABI (tools/wave_ab.py compares kernel versions on one box)
+# B2W_LIBRARY: measurement hook — another build of the same C ABI (tools/step_ab.py compares kernel versions on one box)
 _LIB_PATH = os.environ.get("B2W_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200whisper.so")
 _lib = None
 _lib_lock = threading.Lock()
