@@ -316,3 +316,37 @@ def test_batched_clip_longer_than_30s_matches_reference(both):
         assert [c for c in calls_our if c[0] == "encode"] == [c for c in calls_ref if c[0] == "encode"]
         assert (our_info.language, round(our_info.language_probability, 5), our_info.duration) == (
             ref_info.language, round(ref_info.language_probability, 5), ref_info.duration)
+
+
+def test_empty_audio_matches_reference(both):
+    """The reference's own test_empty_audio (tests/test_transcribe.py:91-97): an empty waveform gives no segments from either front end and
+    language detection still answers; same results and same info from ours."""
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.asarray([], dtype="float32")
+    ref_segs, ref_info = ref_model.transcribe(audio.copy())
+    our_segs, our_info = our_model.transcribe(audio.copy())
+    assert list(ref_segs) == [] and list(our_segs) == []
+    assert (our_info.language, our_info.duration, our_info.duration_after_vad) == (ref_info.language, ref_info.duration, ref_info.duration_after_vad)
+    ref_segs, ref_info = fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), vad_filter=False)
+    our_segs, our_info = T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), vad_filter=False)
+    assert list(ref_segs) == [] and list(our_segs) == []
+    assert (our_info.language, our_info.duration, our_info.duration_after_vad) == (ref_info.language, ref_info.duration, ref_info.duration_after_vad)
+    a, b = ref_model.detect_language(audio.copy()), our_model.detect_language(audio.copy())
+    assert a[0] == b[0] and abs(a[1] - b[1]) < 1e-6 and [x for x, _ in a[2]] == [x for x, _ in b[2]]
+
+
+def test_batched_clips_with_gaps_match_reference(both):
+    """The reference's test_cliptimestamps_timings (tests/test_transcribe.py:295-310) shape: user clips of uneven length with gaps between
+    them, with and without timestamps and word timestamps: segment times (and word times) are restored per clip exactly like the reference's."""
+    fw, ref_model, our_model, calls_ref, calls_our = both
+    audio = np.concatenate([synthetic_audio(150, 20.0), synthetic_audio(151, 15.0)])
+    clips = [{"start": 0.0, "end": 5.0}, {"start": 6.0, "end": 15.0}, {"start": 20.5, "end": 31.25}]
+    for kw in (dict(language="en", beam_size=1, batch_size=2, max_new_tokens=8), dict(language="en", beam_size=2, batch_size=3, max_new_tokens=8,
+                                                                                   without_timestamps=False, word_timestamps=True)):
+        ref = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in
+               fw.BatchedInferencePipeline(ref_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)[0]]
+        our = [(seg_tuple(s), [word_tuple(w) for w in (s.words or [])]) for s in
+               T.BatchedInferencePipeline(our_model).transcribe(audio.copy(), vad_filter=False, clip_timestamps=clips, **kw)[0]]
+        assert our == ref and len(ref) >= 3
+        if kw.get("without_timestamps", True):
+            assert [(s[0][2], s[0][3]) for s in ref] == [(c["start"], c["end"]) for c in clips]  # one segment per clip, at the clip's bounds
