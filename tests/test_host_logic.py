@@ -239,3 +239,19 @@ def test_tokenizer_matches_the_reference_class_on_random_sequences():
             ts = [ours.timestamp_begin + 3] + ids[: n // 2] + [ours.timestamp_begin + 40] * 2 + ids[n // 2:] + [ours.timestamp_begin + 90]
             assert ours.decode_with_timestamps(ts) == ref.decode_with_timestamps(ts)
             assert ours.decode(ids) == ref.decode(ids) and ours.encode(" hello wor") == ref.encode(" hello wor")
+
+
+@pytest.mark.skipif(not __import__("oracle.refload", fromlist=["reference_available"]).reference_available(), reason="reference tree not mounted (build container only)")
+def test_model_names_and_hub_repositories_match_the_reference():
+    """available_models() and the size -> hub repository table are the reference's (utils.py:12-47), entry for entry and in order."""
+    import sys
+
+    from faster_whisper_b200 import utils as ours
+    from oracle.refload import load_reference
+
+    fw = load_reference()
+    ref = sys.modules[fw.__name__ + ".utils"]
+    assert ours.available_models() == ref.available_models()
+    assert ours._HUB_REPOS == ref._MODELS
+    assert ours.format_timestamp(3723.456, always_include_hours=True, decimal_marker=",") == ref.format_timestamp(3723.456, always_include_hours=True, decimal_marker=",")
+    assert ours.format_timestamp(59.999) == ref.format_timestamp(59.999)
