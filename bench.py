@@ -364,7 +364,7 @@ def run_engine(args):
 
 def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed `ncu --set full` capture
-    (profiles/r2_ncu_traffic.json).  The file records the sha256 of the kernel's source at capture time: when the source has
+    (profiles/r2_ncu_traffic.json).  The file records a fingerprint of the kernel's source code at capture time: when the code has
     changed since, the number is stale and is NOT reported (traffic = null, and a loud note on stderr)."""
     import hashlib
 
@@ -376,8 +376,9 @@ def ncu_traffic(kernel: str):
         if not ent:
             return None, "no capture committed for " + kernel
         src = os.path.join(ROOT, "faster_whisper_b200", "csrc", ent["source_file"])
-        with open(src, "rb") as f:
-            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+        from faster_whisper_b200.build import source_fingerprint
+
+        sha = source_fingerprint(src)  # code only: blank lines and whole-line comments do not count
         if sha != ent.get("source_sha16"):
             sys.stderr.write(f"[bench] profiles/r2_ncu_traffic.json is STALE for {kernel}: {ent['source_file']} changed since the ncu capture "
                              f"({ent.get('source_sha16')} -> {sha}); roofline.traffic is reported as null\n")

@@ -23,6 +23,20 @@ NVCC_FLAGS = [
 ]
 
 
+def source_fingerprint(path: str) -> str:
+    """sha256 (16 hex digits) of a source file's CODE: blank lines and lines that are entirely a ``//`` comment do not count, so a comment can
+    be corrected without orphaning the ncu capture that profiles/r2_ncu_traffic.json ties to the kernel source."""
+    import hashlib
+
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for line in f:
+            t = line.strip()
+            if t and not t.startswith(b"//"):
+                h.update(t + b"\n")
+    return h.hexdigest()[:16]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

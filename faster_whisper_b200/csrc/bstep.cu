@@ -16,10 +16,16 @@
 //     cp.reduce.async.bulk (.add.f32) per row — scalar red.global would cost ~1.3 clk per lane per SM;
 //   * since no CTA ever sees a whole row of a GEMM output, everything that needs one is deferred to the consumer: the
 //     LayerNorm of a residual-stream input is applied algebraically, y = rstd (W x - mean rowsum(W)) + b, with sum(x) and
-//     sum(x^2) accumulated by the CTAs that stage the first n-block; biases of q/k/v/cross-q/hidden are added by the consumer;
-//     GELU gets its own (cheap) phase so that it is evaluated once per element;
+//     sum(x^2) taken from the staged fp16 tiles (each k-atom accounted by exactly one CTA, while its UMMAs run); biases of
+//     q/k/v/cross-q/hidden are added by the consumer; GELU gets its own (cheap, rolled) phase so that it is evaluated once per element;
 //   * a weight-producer thread keeps a 5-slot ring of atoms full across phase boundaries, a K/V-producer thread double
-//     buffers the cross-attention tiles, an MMA thread issues the UMMAs; eight compute warps do the rest.
+//     buffers the cross-attention tiles, an MMA thread issues the UMMAs; eight compute warps do the rest;
+//   * the phase code runs ONCE per phase on eight warps (two per scheduler) and the ~110 KB of it cycle through a 32 KB instruction
+//     cache: its cost is its instruction count.  Staging is flattened into (atom, pass) units of a handful of instructions, the atom
+//     ranges are computed once per launch, wide register arrays live in leaf functions (ptxas allocates across the call graph: 40
+//     registers in the GEMM phase made the self-attention loop spill), cycle counters are compiled in only with -DB2W_STEP_TICKS.
+//     DESIGN.md section 4 has the measurements, including the ones that did not work (wave pipelining of independent chunks, prefetch
+//     gates, a 16-lane staging, out-of-lined merges).
 //
 // Replaces the per-token body of CTranslate2's batched Whisper.generate loop (reference call sites
 // faster_whisper/transcribe.py:222-236 driven by :580-617) for BASELINE.json configs[2..4].

@@ -31,8 +31,6 @@ def test_reference_arm_is_silent_on_other_ranks():
 def test_committed_bench_line_of_our_arm_meets_the_contract():
     """The GPU arm cannot run here; the line the last GPU run produced (profiles/r2_bench_default.json, written by bench.py itself) must carry
     every key of the driver's contract, be internally consistent, and cite an ncu traffic capture of the kernel source that is in the tree."""
-    import hashlib
-
     with open(os.path.join(ROOT, "profiles", "r2_bench_default.json")) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
@@ -53,6 +51,8 @@ def test_committed_bench_line_of_our_arm_meets_the_contract():
     assert r["traffic"] is not None and 0.9 < r["traffic"] / r["alg_bytes_per_step"] < 1.2
     with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
         cap = json.load(f)["bstep_kernel"]
-    with open(os.path.join(ROOT, "faster_whisper_b200", "csrc", cap["source_file"]), "rb") as f:
-        assert hashlib.sha256(f.read()).hexdigest()[:16] == cap["source_sha16"], "the ncu capture is older than the kernel source: re-run tools/gpu_profile.sh"
+    from faster_whisper_b200.build import source_fingerprint
+
+    assert source_fingerprint(os.path.join(ROOT, "faster_whisper_b200", "csrc", cap["source_file"])) == cap["source_sha16"], \
+        "the ncu capture is older than the kernel code: re-run tools/gpu_profile.sh"
     assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}

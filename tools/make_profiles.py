@@ -13,6 +13,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from faster_whisper_b200.build import source_fingerprint  # noqa: E402
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 TAG = "r2"
@@ -84,7 +86,7 @@ def full_report(name, kernel_file):
     traffic = float(rd[0].replace(",", "")) * mult.get(rd[1], 1) + float(wr[0].replace(",", "")) * mult.get(wr[1], 1)
     dur_us = dur * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(val("gpu__time_duration.sum")[1], 1.0)
     return {"dram_bytes_per_launch": int(traffic), "duration_us": round(dur_us, 2),
-            "source_file": kernel_file, "source_sha16": sha16(os.path.join(ROOT, "faster_whisper_b200", "csrc", kernel_file)),
+            "source_file": kernel_file, "source_sha16": source_fingerprint(os.path.join(ROOT, "faster_whisper_b200", "csrc", kernel_file)),
             "capture": f"profiles/{TAG}_ncu_full_{name}.txt (ncu --set full, one launch, dram__bytes_read.sum + dram__bytes_write.sum)"}
 
 
